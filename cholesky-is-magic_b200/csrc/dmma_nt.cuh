@@ -1,0 +1,288 @@
+// FP64 tensor-core "NT" contraction for column-major operands, the workhorse of the engine:
+//
+//     C(MxN) = alpha * X[rowA0.., k0..k0+K) * diag(scale) * Y[rowB0.., k0..k0+K)^T + beta * C
+//
+// X, Y are column-major (rows contiguous), so a BMxBK operand tile is BK runs of BM contiguous
+// doubles: exactly what one 2D TMA box delivers.  Used for
+//   * K1  formation  M = A diag(theta) A^T      (scale = theta, lower tiles only, X = Y = A)
+//         replaces matlisp m* by an n x n diagonal + CHOLMOD's A*A' assembly
+//         (reference newton-solve.lisp:112-116, sparse-cholesky.lisp:409-419)
+//   * K2  Cholesky trailing update  C -= P P^T  (alpha=-1, beta=1, lower tiles only, X = Y = panel)
+//         replaces dsyrk/dgemm inside cholmod_factorize (sparse-cholesky.lisp:419)
+//   * general rectangular updates (look-ahead column, supernode updates).
+//
+// Structure (one persistent CTA per SM, static tile round-robin):
+//   thread 0      : also the TMA producer.  It issues cp.async.bulk.tensor for the X tile, the Y tile
+//                   (skipped on diagonal tiles of a symmetric product) and a 1D bulk copy of the BK
+//                   scale values, all completing on the stage's "full" mbarrier.  (A dedicated
+//                   producer warp would make 9 warps; registers are allocated per 4 warps, which
+//                   caps the consumers at 168 registers and spills the accumulators.)
+//   warps 0..7    : DMMA consumers, 2 (M) x 4 (N); warp tile 64x32 = 8x4 m8n8k4 accumulators
+//                   (128 accumulator registers per thread).  Each k4 step: 8+4 LDS.64 -> 32 DMMA.
+//
+// Shared-memory layout: the TMA box is 132 rows x BK columns although only 128 rows are used.  The
+// dense box lands as [k][132]; with a row pitch of 132 doubles (== 4 mod 16) the fragment loads of
+// m8n8k4 (lane = 4*g + t reads row g, column t) hit 16 distinct 8-byte bank pairs per half-warp, so
+// they are conflict-free without swizzling.  Cost: 3% extra L2->smem traffic.
+#pragma once
+#include <cstdint>
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include "ptx_util.cuh"
+
+namespace nes {
+
+constexpr int NT_BM = 128;
+constexpr int NT_BN = 128;
+constexpr int NT_BK = 16;
+constexpr int NT_PITCH = 132;  // smem row pitch in doubles (TMA box rows)
+constexpr int NT_STAGES = 5;
+constexpr int NT_CONSUMER_WARPS = 8;
+constexpr int NT_THREADS = NT_CONSUMER_WARPS * 32;
+constexpr int NT_TILE_BYTES = NT_PITCH * NT_BK * 8;            // 16896
+constexpr int NT_STAGE_BYTES = 2 * NT_TILE_BYTES + NT_BK * 8;  // + scale slab
+constexpr int NT_SMEM_BYTES = NT_STAGES * NT_STAGE_BYTES + 2 * NT_STAGES * 8 + 128;
+
+struct NtArgs {
+    double* C;            // origin of the output region (column-major)
+    long long ldc;        // leading dimension of C in doubles
+    int M, N;             // region extent
+    int rowA0, rowB0;     // operand row origins (coordinates in the tensor maps)
+    int k0, K;            // contraction range: operand columns [k0, k0+K)
+    const double* scale;  // per-column scale, indexed by absolute column; padded to a multiple of BK
+    double alpha, beta;
+    int lower;            // only tiles with bj <= bi (region must be square, same row origin)
+    int same_operand;     // X == Y and rowA0 == rowB0: diagonal tiles load one operand tile
+    int ntiles;
+    int tiles_n;
+};
+
+__device__ __forceinline__ void nt_tile_coords(const NtArgs& p, int t, int& bi, int& bj) {
+    if (p.lower) {
+        int r = static_cast<int>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
+        while ((long long)(r + 1) * (r + 2) / 2 <= t) ++r;
+        while ((long long)r * (r + 1) / 2 > t) --r;
+        bi = r;
+        bj = t - static_cast<int>((long long)r * (r + 1) / 2);
+    } else {
+        bi = t / p.tiles_n;
+        bj = t - bi * p.tiles_n;
+    }
+}
+
+// Producer state: walks this CTA's (tile, k-chunk) sequence one chunk ahead of the consumers.
+struct NtProducer {
+    int t;         // current tile (linear index), >= ntiles when exhausted
+    int kc;        // next k-chunk within the tile
+    int bi, bj;    // tile coordinates
+    uint32_t it;   // chunks issued so far (stage = it % STAGES)
+};
+
+template <bool kHasScale>
+__global__ void __launch_bounds__(NT_THREADS, 1)
+dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+               const NtArgs p) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NT_STAGES * NT_STAGE_BYTES);
+    uint64_t* empty = full + NT_STAGES;
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+    const bool is_producer = (threadIdx.x == 0);
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NT_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NT_CONSUMER_WARPS);
+        }
+        fence_mbar_init();
+        prefetch_tmap(&mapX);
+        prefetch_tmap(&mapY);
+    }
+    __syncthreads();
+
+    const int kchunks = (p.K + NT_BK - 1) / NT_BK;
+
+    // The TMA producer is folded into thread 0: it refills the stage released one chunk ago, so its
+    // empty-barrier wait is normally already satisfied (prefetch distance STAGES-1 chunks).
+    NtProducer pr;
+    pr.t = blockIdx.x;
+    pr.kc = 0;
+    pr.it = 0;
+    pr.bi = pr.bj = 0;
+    if (is_producer && pr.t < p.ntiles) nt_tile_coords(p, pr.t, pr.bi, pr.bj);
+    auto produce = [&]() {
+        if (pr.t >= p.ntiles) return;
+        const int s = pr.it % NT_STAGES;
+        const uint32_t ph = (pr.it / NT_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        const bool diag = p.same_operand && (pr.bi == pr.bj);
+        const uint32_t bytes =
+            (diag ? NT_TILE_BYTES : 2 * NT_TILE_BYTES) + (kHasScale ? NT_BK * 8 : 0);
+        uint8_t* st = smem + s * NT_STAGE_BYTES;
+        mbar_expect_tx(&full[s], bytes);
+        const int kk = p.k0 + pr.kc * NT_BK;
+        tma_load_2d(st, &mapX, p.rowA0 + pr.bi * NT_BM, kk, &full[s]);
+        if (!diag) tma_load_2d(st + NT_TILE_BYTES, &mapY, p.rowB0 + pr.bj * NT_BN, kk, &full[s]);
+        if (kHasScale) bulk_load_1d(st + 2 * NT_TILE_BYTES, p.scale + kk, NT_BK * 8, &full[s]);
+        ++pr.it;
+        if (++pr.kc == kchunks) {
+            pr.kc = 0;
+            pr.t += gridDim.x;
+            if (pr.t < p.ntiles) nt_tile_coords(p, pr.t, pr.bi, pr.bj);
+        }
+    };
+    if (is_producer) {
+        for (int i = 0; i < NT_STAGES - 1; ++i) produce();
+    }
+
+    // ---------------- DMMA consumers ----------------
+    const int g = lane >> 2;
+    const int t4 = lane & 3;
+    const int wm = warp >> 2;  // 0..1  -> 64-row slab
+    const int wn = warp & 3;   // 0..3  -> 32-col slab
+    const int a_off = t4 * NT_PITCH + wm * 64 + g;
+    const int b_off = t4 * NT_PITCH + wn * 32 + g;
+
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
+        int bi, bj;
+        nt_tile_coords(p, t, bi, bj);
+        const bool diag = p.same_operand && (bi == bj);
+
+        double acc[8][4][2];
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+        for (int kc = 0; kc < kchunks; ++kc, ++it) {
+            if (is_producer) produce();
+            __syncwarp();
+            const int s = it % NT_STAGES;
+            const uint32_t ph = (it / NT_STAGES) & 1;
+            mbar_wait(&full[s], ph);
+            const double* sA = reinterpret_cast<const double*>(smem + s * NT_STAGE_BYTES);
+            const double* sB = diag ? sA : sA + NT_PITCH * NT_BK;
+            const double* sS = sA + 2 * NT_PITCH * NT_BK;
+            const double* ap = sA + a_off;
+            const double* bp = sB + b_off;
+#pragma unroll
+            for (int ks = 0; ks < NT_BK / 4; ++ks) {
+                double af[8], bf[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) af[i] = ap[ks * 4 * NT_PITCH + i * 8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = bp[ks * 4 * NT_PITCH + j * 8];
+                if (kHasScale) {
+                    const double th = sS[ks * 4 + t4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) bf[j] *= th;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        }
+
+        // epilogue: registers -> global (column-major).  Lane holds rows g (+8i), cols 2*t4, 2*t4+1.
+        const int row_base = bi * NT_BM + wm * 64 + g;
+        const int col_base = bj * NT_BN + wn * 32 + 2 * t4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int col = col_base + j * 8 + c;
+                if (col < p.N) {
+                    double* cp = p.C + (long long)col * p.ldc;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = row_base + i * 8;
+                        if (row < p.M) {
+                            double v = p.alpha * acc[i][j][c];
+                            if (p.beta != 0.0) v += p.beta * cp[row];
+                            cp[row] = v;
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_tiled() {
+    static PFN_encodeTiled fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) !=
+                cudaSuccess ||
+            q != cudaDriverEntryPointSuccess)
+            return nullptr;
+        fn = reinterpret_cast<PFN_encodeTiled>(p);
+    }
+    return fn;
+}
+
+// Tensor map over a column-major rows x cols matrix of doubles (ld even, base 16B aligned) with
+// the 132 x 16 operand box of dmma_nt_kernel.  Returns 0 on success.
+inline int make_operand_map(CUtensorMap* map, const double* base, long long rows, long long cols,
+                            long long ld) {
+    PFN_encodeTiled enc = get_encode_tiled();
+    if (!enc) return -1;
+    cuuint64_t dims[2] = {static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(cols)};
+    cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 8};
+    cuuint32_t box[2] = {NT_PITCH, NT_BK};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims,
+                     strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? 0 : -2;
+}
+
+inline cudaError_t nt_configure() {
+    static bool done = false;
+    if (done) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(dmma_nt_kernel<true>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(dmma_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             NT_SMEM_BYTES);
+    if (e != cudaSuccess) return e;
+    done = true;
+    return cudaSuccess;
+}
+
+// Launch on `stream` with at most `max_ctas` persistent CTAs (normally the SM count).
+inline cudaError_t nt_launch(const CUtensorMap& mapX, const CUtensorMap& mapY, NtArgs a, int max_ctas,
+                             cudaStream_t stream) {
+    if (a.M <= 0 || a.N <= 0) return cudaSuccess;
+    cudaError_t e = nt_configure();
+    if (e != cudaSuccess) return e;
+    const int tm = (a.M + NT_BM - 1) / NT_BM;
+    const int tn = (a.N + NT_BN - 1) / NT_BN;
+    a.tiles_n = tn;
+    a.ntiles = a.lower ? tm * (tm + 1) / 2 : tm * tn;
+    const int grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
+    if (a.scale)
+        dmma_nt_kernel<true><<<grid, NT_THREADS, NT_SMEM_BYTES, stream>>>(mapX, mapY, a);
+    else
+        dmma_nt_kernel<false><<<grid, NT_THREADS, NT_SMEM_BYTES, stream>>>(mapX, mapY, a);
+    return cudaGetLastError();
+}
+
+}  // namespace nes

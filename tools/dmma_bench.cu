@@ -1,0 +1,176 @@
+// Standalone B200 probe: (1) FP64 DMMA / DFMA issue-rate peaks, (2) correctness + timing of the
+// fused scale+SYRK kernel (dmma_nt.cuh).  Not part of the product library; results are recorded
+// under profiles/.
+#include <cstdio>
+#include <cstdlib>
+#include <cmath>
+#include <vector>
+#include "../cholesky-is-magic_b200/csrc/dmma_nt.cuh"
+
+#define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1);} } while (0)
+
+using namespace nes;
+
+template <int ILP>
+__global__ void dmma_peak_kernel(double* out, int iters) {
+    double c[ILP][2];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) c[i][0] = c[i][1] = 0.0;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) dmma884(c[i][0], c[i][1], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += c[i][0] + c[i][1];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+template <int ILP>
+__global__ void dfma_peak_kernel(double* out, int iters) {
+    double c[ILP];
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) c[i] = i;
+    double a = 1.0 + threadIdx.x * 1e-9, b = 1e-9 * threadIdx.x;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int i = 0; i < ILP; ++i) c[i] = fma(c[i], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int i = 0; i < ILP; ++i) s += c[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+__global__ void naive_syrk(const double* A, const double* th, double* C, int m, int n) {
+    int i = blockIdx.x * 16 + threadIdx.x, j = blockIdx.y * 16 + threadIdx.y;
+    if (i >= m || j >= m || j > i) return;
+    double s = 0;
+    for (int k = 0; k < n; ++k) s += A[i + (size_t)k * m] * th[k] * A[j + (size_t)k * m];
+    C[i + (size_t)j * m] = s;
+}
+
+static float time_ms(cudaEvent_t a, cudaEvent_t b) { float ms; cudaEventElapsedTime(&ms, a, b); return ms; }
+
+template <int ILP>
+void run_dmma(int warps, int ctas_per_sm, double* out, int sms) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int iters = 20000;
+    dim3 grid(sms * ctas_per_sm), block(warps * 32);
+    dmma_peak_kernel<ILP><<<grid, block>>>(out, 100);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) {
+        cudaEventRecord(e0);
+        dmma_peak_kernel<ILP><<<grid, block>>>(out, iters);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        best = fminf(best, time_ms(e0, e1));
+    }
+    double flops = 2.0 * 256 * ILP * (double)iters * warps * grid.x;
+    printf("DMMA peak: ilp=%2d warps/cta=%2d ctas/sm=%d  %.3f ms  %.2f TFLOP/s\n", ILP, warps, ctas_per_sm, best, flops / best * 1e-9);
+}
+
+template <int ILP>
+void run_dfma(int warps, int ctas_per_sm, double* out, int sms) {
+    cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+    int iters = 20000;
+    dim3 grid(sms * ctas_per_sm), block(warps * 32);
+    dfma_peak_kernel<ILP><<<grid, block>>>(out, 100);
+    CK(cudaDeviceSynchronize());
+    float best = 1e30f;
+    for (int r = 0; r < 3; ++r) {
+        cudaEventRecord(e0);
+        dfma_peak_kernel<ILP><<<grid, block>>>(out, iters);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        best = fminf(best, time_ms(e0, e1));
+    }
+    double flops = 2.0 * 32 * ILP * (double)iters * warps * grid.x;
+    printf("DFMA peak: ilp=%2d warps/cta=%2d ctas/sm=%d  %.3f ms  %.2f TFLOP/s\n", ILP, warps, ctas_per_sm, best, flops / best * 1e-9);
+}
+
+static void syrk_case(int m, int n, int sms, bool check, int reps) {
+    size_t ld = m + (m & 1);
+    double *A, *C, *Cref, *th;
+    int npad = (n + NT_BK - 1) / NT_BK * NT_BK;
+    CK(cudaMalloc(&A, ld * (size_t)n * 8));
+    CK(cudaMalloc(&C, ld * (size_t)m * 8));
+    CK(cudaMalloc(&th, (size_t)npad * 8));
+    CK(cudaMemset(th, 0, (size_t)npad * 8));
+    std::vector<double> hA(ld * (size_t)n), hth(n);
+    unsigned long long s = 88172645463325252ULL;
+    auto rnd = [&]() { s ^= s << 13; s ^= s >> 7; s ^= s << 17; return (double)(s >> 11) / 9007199254740992.0; };
+    for (auto& v : hA) v = rnd();
+    for (int i = 0; i < m && i < n; ++i) hA[i + (size_t)i * ld] += 1.0;
+    for (auto& v : hth) v = 0.1 + 10 * rnd();
+    CK(cudaMemcpy(A, hA.data(), hA.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(th, hth.data(), hth.size() * 8, cudaMemcpyHostToDevice));
+    CK(cudaMemset(C, 0, ld * (size_t)m * 8));
+    CUtensorMap map;
+    int rc = make_operand_map(&map, A, m, n, ld);
+    if (rc) { printf("tensor map failed %d\n", rc); exit(1); }
+    NtArgs a{};
+    a.C = C; a.ldc = ld; a.M = m; a.N = m; a.rowA0 = 0; a.rowB0 = 0; a.k0 = 0; a.K = n;
+    a.scale = th; a.alpha = 1.0; a.beta = 0.0; a.lower = 1; a.same_operand = 1;
+    CK(nt_launch(map, map, a, sms, 0));
+    CK(cudaDeviceSynchronize());
+    if (check) {
+        CK(cudaMalloc(&Cref, ld * (size_t)m * 8));
+        CK(cudaMemset(Cref, 0, ld * (size_t)m * 8));
+        // naive reference uses ld == m layout only when m even; pass ld via m param trick
+        std::vector<double> hC(ld * (size_t)m), hR((size_t)m * m, 0.0);
+        CK(cudaMemcpy(hC.data(), C, hC.size() * 8, cudaMemcpyDeviceToHost));
+        double num = 0, den = 0;
+        for (int j = 0; j < m; ++j)
+            for (int i = j; i < m; ++i) {
+                double sacc = 0;
+                for (int k = 0; k < n; ++k) sacc += hA[i + (size_t)k * ld] * hth[k] * hA[j + (size_t)k * ld];
+                double d = hC[i + (size_t)j * ld] - sacc;
+                num += d * d; den += sacc * sacc;
+            }
+        printf("SYRK check m=%d n=%d: rel fro err (lower) = %.3e\n", m, n, sqrt(num / den));
+        cudaFree(Cref);
+    }
+    if (reps > 0) {
+        cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+        float best = 1e30f, tot = 0;
+        for (int r = 0; r < reps; ++r) {
+            cudaEventRecord(e0);
+            CK(nt_launch(map, map, a, sms, 0));
+            cudaEventRecord(e1);
+            CK(cudaDeviceSynchronize());
+            float ms = time_ms(e0, e1); best = fminf(best, ms); tot += ms;
+        }
+        double flops = (double)m * m * n;  // lower-triangle algorithmic flops (m(m+1)/2 * 2n)
+        printf("SYRK time m=%d n=%d: best %.3f ms avg %.3f ms -> %.2f TFLOP/s (algorithmic m^2 n)\n", m, n, best, tot / reps, flops / best * 1e-9);
+    }
+    cudaFree(A); cudaFree(C); cudaFree(th);
+}
+
+int main(int argc, char** argv) {
+    cudaDeviceProp prop; CK(cudaGetDeviceProperties(&prop, 0));
+    int sms = prop.multiProcessorCount;
+    printf("device %s, %d SMs, clock %d kHz\n", prop.name, sms, prop.clockRate);
+    double* out; CK(cudaMalloc(&out, (size_t)sms * 8 * 1024 * 8));
+    run_dmma<4>(4, 1, out, sms);
+    run_dmma<8>(4, 1, out, sms);
+    run_dmma<16>(4, 1, out, sms);
+    run_dmma<8>(8, 1, out, sms);
+    run_dmma<16>(8, 1, out, sms);
+    run_dmma<32>(8, 1, out, sms);
+    run_dmma<8>(16, 1, out, sms);
+    run_dmma<8>(8, 2, out, sms);
+    run_dmma<8>(32, 1, out, sms);
+    run_dfma<8>(8, 1, out, sms);
+    run_dfma<8>(16, 1, out, sms);
+    run_dfma<8>(32, 2, out, sms);
+    syrk_case(200, 500, sms, true, 0);
+    syrk_case(130, 37, sms, true, 0);
+    syrk_case(517, 1001, sms, true, 0);
+    syrk_case(1024, 2048, sms, true, 3);
+    syrk_case(4096, 8192, sms, false, 3);
+    syrk_case(8192, 16384, sms, false, 5);
+    return 0;
+}
