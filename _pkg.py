@@ -1,0 +1,20 @@
+"""Import helper: the product package lives in ``cholesky-is-magic_b200/`` (hyphenated, named after
+the reference); this registers it under the importable name ``cholesky_is_magic_b200``."""
+import importlib.util
+import os
+import sys
+
+NAME = "cholesky_is_magic_b200"
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG_DIR = os.path.join(ROOT, "cholesky-is-magic_b200")
+
+
+def load():
+    if NAME in sys.modules:
+        return sys.modules[NAME]
+    spec = importlib.util.spec_from_file_location(
+        NAME, os.path.join(PKG_DIR, "__init__.py"), submodule_search_locations=[PKG_DIR])
+    mod = importlib.util.module_from_spec(spec)
+    sys.modules[NAME] = mod
+    spec.loader.exec_module(mod)
+    return mod

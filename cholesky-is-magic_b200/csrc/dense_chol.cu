@@ -1,0 +1,292 @@
+// K1 + K2 for a dense constraint matrix: normal-matrix formation and blocked right-looking Cholesky.
+//
+// Replaces, for dense A, what the reference obtains from CHOLMOD in solve-dense
+// (sparse-cholesky.lisp:409-431): cholmod_factorize on an unsymmetric B = A diag(s) forms B B' and
+// factorizes it as one dense supernode (LAPACK dpotrf).  Failure protocol is the reference's:
+// a non-positive pivot sets status = 1 (CHOLMOD_NOT_POSDEF) and records the column ("minor");
+// the Lisp maps any non-zero status to NIL (:420-421).
+//
+// Step k (block column of NB=128):
+//   potrf_diag_kernel   one CTA: 128x128 diagonal block in shared memory; 16-column sub-panels, the
+//                       16x16 pivot block by ONE WARP with shuffles (lane = row), rows below by one
+//                       thread per row, trailing rank-16 update register-tiled over a 16x16 thread grid
+//   trsm_panel_kernel   X L_kk' = B for the rows below: one thread per row, 32-column register blocks,
+//                       L_kk broadcast from shared memory (true substitution, no explicit inverse)
+//   dmma_nt_kernel      trailing update C -= P P' on the FP64 tensor cores (lower tiles only)
+#include "dmma_nt.cuh"
+#include "nes_internal.h"
+
+namespace nes {
+
+constexpr int CH_NB = 128;
+constexpr int CH_W = 16;
+constexpr int CH_P = 129;  // smem pitch of the diagonal block (column-major)
+constexpr int CH_DIAG_SMEM = (CH_NB * CH_P + CH_NB) * 8;
+
+__global__ void __launch_bounds__(256)
+potrf_diag_kernel(double* __restrict__ M, long long ld, int j0, int jb, double* __restrict__ dinv_out,
+                  double dbound, int* __restrict__ info) {
+    extern __shared__ double S[];
+    double* dinv = S + CH_NB * CH_P;
+    const int tid = threadIdx.x;
+    double* Mb = M + j0 + (long long)j0 * ld;
+
+    for (int idx = tid; idx < jb * jb; idx += 256) {
+        const int cc = idx / jb, r = idx - cc * jb;
+        if (r >= cc) S[r + cc * CH_P] = Mb[r + (long long)cc * ld];
+    }
+    __syncthreads();
+
+    for (int c0 = 0; c0 < jb; c0 += CH_W) {
+        const int w = min(CH_W, jb - c0);
+        // (1) pivot block, one warp, lane = row
+        if (tid < 32) {
+            const int lane = tid;
+            double a[CH_W];
+#pragma unroll
+            for (int cc = 0; cc < CH_W; ++cc)
+                a[cc] = (lane < w && cc <= lane) ? S[(c0 + lane) + (c0 + cc) * CH_P] : 0.0;
+#pragma unroll
+            for (int cc = 0; cc < CH_W; ++cc) {
+                if (cc < w) {
+                    double d = __shfl_sync(0xffffffffu, a[cc], cc);
+                    // CHOLMOD dbound for LL': L_jj is not allowed below dbound (0 = off)
+                    if (dbound > 0.0 && d < dbound * dbound) d = dbound * dbound;
+                    if (!(d > 0.0)) {  // also catches NaN
+                        if (lane == 0 && info[0] == 0) {
+                            info[0] = NES_NOT_POSDEF;
+                            info[1] = j0 + c0 + cc;
+                        }
+                        d = 1.0;
+                    }
+                    double ri = rsqrt(d);
+                    double sq = d * ri;
+                    sq = fma(0.5 * fma(-sq, sq, d), ri, sq);  // one Newton step: sqrt to <1 ulp
+                    ri = fma(fma(-sq, ri, 1.0), ri, ri);        // and its reciprocal
+                    a[cc] = (lane == cc) ? sq : a[cc] * ri;
+#pragma unroll
+                    for (int c2 = cc + 1; c2 < CH_W; ++c2) {
+                        const double l = __shfl_sync(0xffffffffu, a[cc], c2);
+                        a[c2] = fma(-a[cc], l, a[c2]);
+                    }
+                    if (lane == 0) dinv[c0 + cc] = ri;
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < CH_W; ++cc)
+                if (lane < w && cc <= lane) S[(c0 + lane) + (c0 + cc) * CH_P] = a[cc];
+        }
+        __syncthreads();
+        const int base = c0 + w;
+        const int T = jb - base;
+        if (T <= 0) break;
+        // (2) rows below the pivot block: x L_d' = a, one thread per row
+        if (tid < T) {
+            const int r = base + tid;
+            double x[CH_W];
+#pragma unroll
+            for (int cc = 0; cc < CH_W; ++cc) x[cc] = (cc < w) ? S[r + (c0 + cc) * CH_P] : 0.0;
+#pragma unroll
+            for (int cc = 0; cc < CH_W; ++cc) {
+                if (cc < w) {
+                    double acc = x[cc];
+#pragma unroll
+                    for (int p = 0; p < cc; ++p)
+                        acc = fma(-x[p], S[(c0 + cc) + (c0 + p) * CH_P], acc);
+                    x[cc] = acc * dinv[c0 + cc];
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < CH_W; ++cc)
+                if (cc < w) S[r + (c0 + cc) * CH_P] = x[cc];
+        }
+        __syncthreads();
+        // (3) trailing rank-w update of the lower triangle, 16x16 thread grid, interleaved 7x7 tiles
+        {
+            const int ti = tid & 15, tj = tid >> 4;
+            double acc[7][7];
+#pragma unroll
+            for (int a_ = 0; a_ < 7; ++a_)
+#pragma unroll
+                for (int b_ = 0; b_ < 7; ++b_) acc[a_][b_] = 0.0;
+            for (int p = 0; p < w; ++p) {
+                const double* col = S + (c0 + p) * CH_P + base;
+                double xi[7], xj[7];
+#pragma unroll
+                for (int a_ = 0; a_ < 7; ++a_) {
+                    const int i = ti + 16 * a_, j = tj + 16 * a_;
+                    xi[a_] = (i < T) ? col[i] : 0.0;
+                    xj[a_] = (j < T) ? col[j] : 0.0;
+                }
+#pragma unroll
+                for (int a_ = 0; a_ < 7; ++a_) {
+                    if (16 * a_ < T) {
+#pragma unroll
+                        for (int b_ = 0; b_ <= a_; ++b_) acc[a_][b_] = fma(xi[a_], xj[b_], acc[a_][b_]);
+                    }
+                }
+            }
+#pragma unroll
+            for (int a_ = 0; a_ < 7; ++a_) {
+#pragma unroll
+                for (int b_ = 0; b_ <= a_; ++b_) {
+                    const int i = ti + 16 * a_, j = tj + 16 * b_;
+                    if (i < T && j <= i) S[(base + i) + (base + j) * CH_P] -= acc[a_][b_];
+                }
+            }
+        }
+        __syncthreads();
+    }
+
+    for (int idx = tid; idx < jb * jb; idx += 256) {
+        const int cc = idx / jb, r = idx - cc * jb;
+        if (r >= cc) Mb[r + (long long)cc * ld] = S[r + cc * CH_P];
+    }
+    if (tid < jb) dinv_out[j0 + tid] = dinv[tid];
+}
+
+// X L' = B for a 64-row slab of the panel below a full 128x128 diagonal block.
+constexpr int TR_ROWS = 64;
+constexpr int TR_SMEM = (CH_NB * CH_NB + TR_ROWS * CH_NB + CH_NB) * 8;
+
+constexpr int TR_THREADS = 256;  // all threads stage L and the slab; threads 0..63 substitute
+
+__global__ void __launch_bounds__(TR_THREADS)
+trsm_panel_kernel(double* __restrict__ M, long long ld, int j0, int m, const double* __restrict__ dinv_g) {
+    extern __shared__ double sm[];
+    double* Ls = sm;                       // Ls[c + p*128] = L[c][p]
+    double* Xs = Ls + CH_NB * CH_NB;       // Xs[p*64 + row]
+    double* dv = Xs + TR_ROWS * CH_NB;
+    const int tid = threadIdx.x;
+    const int row0 = j0 + CH_NB + blockIdx.x * TR_ROWS;
+    const int nrows = min(TR_ROWS, m - row0);
+    const double* Lg = M + j0 + (long long)j0 * ld;
+#pragma unroll 8
+    for (int idx = tid; idx < CH_NB * CH_NB; idx += TR_THREADS) {
+        const int p = idx >> 7, cc = idx & 127;
+        Ls[idx] = (cc >= p) ? Lg[cc + (long long)p * ld] : 0.0;
+    }
+    if (tid < CH_NB) dv[tid] = dinv_g[j0 + tid];
+    double* Bg = M + row0 + (long long)j0 * ld;
+#pragma unroll 8
+    for (int idx = tid; idx < TR_ROWS * CH_NB; idx += TR_THREADS) {
+        const int p = idx >> 6, rr = idx & 63;
+        if (rr < nrows) Xs[idx] = Bg[rr + (long long)p * ld];
+    }
+    __syncthreads();
+
+    if (tid < nrows) {
+        for (int cb = 0; cb < CH_NB; cb += 32) {
+            double b[32];
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) b[cc] = Xs[(cb + cc) * TR_ROWS + tid];
+            for (int p = 0; p < cb; ++p) {
+                const double xp = Xs[p * TR_ROWS + tid];
+                const double2* lrow = reinterpret_cast<const double2*>(Ls + cb + p * CH_NB);
+#pragma unroll
+                for (int cc = 0; cc < 16; ++cc) {
+                    const double2 l2 = lrow[cc];
+                    b[2 * cc] = fma(-xp, l2.x, b[2 * cc]);
+                    b[2 * cc + 1] = fma(-xp, l2.y, b[2 * cc + 1]);
+                }
+            }
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) {
+                const double x = b[cc] * dv[cb + cc];
+                b[cc] = x;
+#pragma unroll
+                for (int c2 = cc + 1; c2 < 32; ++c2)
+                    b[c2] = fma(-x, Ls[(cb + c2) + (cb + cc) * CH_NB], b[c2]);
+            }
+#pragma unroll
+            for (int cc = 0; cc < 32; ++cc) Xs[(cb + cc) * TR_ROWS + tid] = b[cc];
+        }
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int idx = tid; idx < TR_ROWS * CH_NB; idx += TR_THREADS) {
+        const int p = idx >> 6, rr = idx & 63;
+        if (rr < nrows) Bg[rr + (long long)p * ld] = Xs[idx];
+    }
+}
+
+static int chol_configure(nes_ctx* c) {
+    static bool done = false;
+    if (done) return 0;
+    NES_CUDA(c, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     CH_DIAG_SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TR_SMEM));
+    done = true;
+    return 0;
+}
+
+int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L) {
+    StageTimer timer(c, NES_STAGE_FORM);
+    const MatrixBase* b = A->base;
+    NtArgs a{};
+    a.C = L->d_M;
+    a.ldc = (long long)L->ld;
+    a.M = a.N = (int)b->m;
+    a.rowA0 = a.rowB0 = 0;
+    a.k0 = 0;
+    a.K = (int)b->n;
+    a.scale = A->d_theta;  // nullptr: unscaled A A'
+    a.alpha = 1.0;
+    a.beta = 0.0;
+    a.lower = 1;
+    a.same_operand = 1;
+    cudaError_t e = nt_launch(b->map, b->map, a, c->num_sms, c->stream);
+    ++c->launches;
+    if (e != cudaSuccess)
+        return fail(c, NES_ERR_CUDA, "formation kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int dense_cholesky(nes_ctx* c, nes_factor* L) {
+    StageTimer timer(c, NES_STAGE_FACTOR);
+    NES_TRY(chol_configure(c));
+    const int m = (int)L->m;
+    const long long ld = (long long)L->ld;
+    NES_CUDA(c, cudaMemsetAsync(L->d_info, 0, 2 * sizeof(int), c->stream));
+    for (int j0 = 0; j0 < m; j0 += CH_NB) {
+        const int jb = (m - j0 < CH_NB) ? m - j0 : CH_NB;
+        potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->d_M, ld, j0, jb, L->d_dinv,
+                                                              c->dbound, L->d_info);
+        NES_CHECK_LAUNCH(c);
+        const int rest = m - j0 - jb;
+        if (rest <= 0) break;
+        trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM, c->stream>>>(
+            L->d_M, ld, j0, m, L->d_dinv);
+        NES_CHECK_LAUNCH(c);
+        NtArgs a{};
+        a.C = L->d_M + (j0 + jb) + (long long)(j0 + jb) * ld;
+        a.ldc = ld;
+        a.M = a.N = rest;
+        a.rowA0 = a.rowB0 = j0 + jb;
+        a.k0 = j0;
+        a.K = jb;
+        a.scale = nullptr;
+        a.alpha = -1.0;
+        a.beta = 1.0;
+        a.lower = 1;
+        a.same_operand = 1;
+        cudaError_t e = nt_launch(L->mapM, L->mapM, a, c->num_sms, c->stream);
+        ++c->launches;
+        if (e != cudaSuccess)
+            return fail(c, NES_ERR_CUDA, "trailing update launch failed: %s", cudaGetErrorString(e));
+    }
+    int info[2] = {0, 0};
+    NES_TRY(download(c, info, L->d_info, sizeof(info)));
+    if (info[0] != 0) {
+        c->status = NES_NOT_POSDEF;
+        c->minor = info[1];
+        L->factorized = 0;
+        return NES_NOT_POSDEF;
+    }
+    c->minor = m;
+    L->factorized = 1;
+    return 0;
+}
+
+}  // namespace nes

@@ -1,0 +1,137 @@
+// K5: forward / backward triangular solves with the dense Cholesky factor, one right-hand side.
+// Replaces cholmod_solve(CHOLMOD_A, L, b) / cholmod_solve2 (sparse-cholesky.lisp:422, 515, 546).
+// HBM-bound: each sweep reads tril(L) once (4 m^2 bytes).  Blocked by 128:
+//   trsv_diag_kernel     one CTA, 128x128 triangular block staged in shared memory, one thread per
+//                        unknown, one barrier per column
+//   trsv_update_*_kernel rank-128 update of the remaining right-hand side, coalesced along rows of L
+#include "nes_internal.h"
+
+namespace nes {
+
+constexpr int SV_NB = 128;
+constexpr int SV_P = 129;
+constexpr int SV_SMEM = (SV_NB * SV_P + SV_NB) * 8;
+
+__global__ void __launch_bounds__(256)
+trsv_diag_kernel(const double* __restrict__ M, long long ld, int j0, int jb,
+                 const double* __restrict__ dinv, double* __restrict__ x, int transposed) {
+    extern __shared__ double S[];
+    double* xs = S + SV_NB * SV_P;
+    const int tid = threadIdx.x;
+    const double* Lb = M + j0 + (long long)j0 * ld;
+#pragma unroll 8
+    for (int idx = tid; idx < jb * jb; idx += 256) {
+        const int cc = idx / jb, r = idx - cc * jb;
+        if (r > cc) S[r + cc * SV_P] = Lb[r + (long long)cc * ld];
+    }
+    double v = 0.0, di = 0.0;
+    if (tid < jb) {
+        v = x[j0 + tid];
+        di = dinv[j0 + tid];
+    }
+    __syncthreads();
+    if (!transposed) {
+        for (int cc = 0; cc < jb; ++cc) {
+            if (tid == cc) xs[cc] = v = v * di;
+            __syncthreads();
+            if (tid > cc && tid < jb) v = fma(-S[tid + cc * SV_P], xs[cc], v);
+        }
+    } else {
+        for (int cc = jb - 1; cc >= 0; --cc) {
+            if (tid == cc) xs[cc] = v = v * di;
+            __syncthreads();
+            if (tid < cc) v = fma(-S[cc + tid * SV_P], xs[cc], v);
+        }
+    }
+    if (tid < jb) x[j0 + tid] = v;
+}
+
+// forward: x[r] -= sum_c L[r, j0+c] x[j0+c] for r >= r0.  CTA = 32 rows x 8 column groups.
+__global__ void __launch_bounds__(256)
+trsv_update_fwd_kernel(const double* __restrict__ M, long long ld, int j0, int jb, int r0, int m,
+                       double* __restrict__ x) {
+    __shared__ double part[8][33];
+    __shared__ double xk[SV_NB];
+    const int tid = threadIdx.x;
+    const int lr = tid & 31, grp = tid >> 5;
+    if (tid < jb) xk[tid] = x[j0 + tid];
+    __syncthreads();
+    const int r = r0 + blockIdx.x * 32 + lr;
+    double acc = 0.0;
+    if (r < m) {
+        const double* Lr = M + r + (long long)j0 * ld;
+        const int c_lo = grp * 16, c_hi = min(jb, c_lo + 16);
+#pragma unroll 16
+        for (int cc = c_lo; cc < c_hi; ++cc) acc = fma(Lr[(long long)cc * ld], xk[cc], acc);
+    }
+    part[grp][lr] = acc;
+    __syncthreads();
+    if (grp == 0 && r < m) {
+        double s = 0.0;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) s += part[q][lr];
+        x[r] -= s;
+    }
+}
+
+// backward: x[c] -= sum_r L[j0+r, c] x[j0+r] for c < j0.  One warp per column c.
+__global__ void __launch_bounds__(256)
+trsv_update_bwd_kernel(const double* __restrict__ M, long long ld, int j0, int jb,
+                       double* __restrict__ x) {
+    __shared__ double xk[SV_NB];
+    const int tid = threadIdx.x;
+    if (tid < jb) xk[tid] = x[j0 + tid];
+    __syncthreads();
+    const int lane = tid & 31;
+    const int cc = blockIdx.x * 8 + (tid >> 5);
+    if (cc >= j0) return;
+    const double* Lc = M + j0 + (long long)cc * ld;
+    double acc = 0.0;
+#pragma unroll
+    for (int q = 0; q < SV_NB / 32; ++q) {
+        const int r = lane + 32 * q;
+        if (r < jb) acc = fma(Lc[r], xk[r], acc);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if (lane == 0) x[cc] -= acc;
+}
+
+int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
+    StageTimer timer(c, NES_STAGE_SOLVE);
+    static bool configured = false;
+    if (!configured) {
+        NES_CUDA(c, cudaFuncSetAttribute(trsv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         SV_SMEM));
+        configured = true;
+    }
+    const int m = (int)L->m;
+    const long long ld = (long long)L->ld;
+    // L y = b
+    for (int j0 = 0; j0 < m; j0 += SV_NB) {
+        const int jb = (m - j0 < SV_NB) ? m - j0 : SV_NB;
+        trsv_diag_kernel<<<1, 256, SV_SMEM, c->stream>>>(L->d_M, ld, j0, jb, L->d_dinv, d_x, 0);
+        NES_CHECK_LAUNCH(c);
+        const int r0 = j0 + jb;
+        if (r0 < m) {
+            trsv_update_fwd_kernel<<<(m - r0 + 31) / 32, 256, 0, c->stream>>>(L->d_M, ld, j0, jb, r0, m,
+                                                                             d_x);
+            NES_CHECK_LAUNCH(c);
+        }
+    }
+    // L' x = y
+    const int nblk = (m + SV_NB - 1) / SV_NB;
+    for (int k = nblk - 1; k >= 0; --k) {
+        const int j0 = k * SV_NB;
+        const int jb = (m - j0 < SV_NB) ? m - j0 : SV_NB;
+        trsv_diag_kernel<<<1, 256, SV_SMEM, c->stream>>>(L->d_M, ld, j0, jb, L->d_dinv, d_x, 1);
+        NES_CHECK_LAUNCH(c);
+        if (j0 > 0) {
+            trsv_update_bwd_kernel<<<(j0 + 7) / 8, 256, 0, c->stream>>>(L->d_M, ld, j0, jb, d_x);
+            NES_CHECK_LAUNCH(c);
+        }
+    }
+    return 0;
+}
+
+}  // namespace nes

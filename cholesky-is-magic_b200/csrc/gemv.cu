@@ -1,0 +1,175 @@
+// K6: y <- alpha * op(A diag(s)) x + beta * y on device vectors.
+// Replaces cholmod_sdmult as driven by sparse-m* (sparse-cholesky.lisp:567-614) and the dense
+// gemm!/m* matrix-vector products of newton-solve.lisp:62, 98, 129.  All variants are HBM-bound
+// (dense: 8mn bytes per product) and atomic-free, so results are bitwise reproducible.
+//   dense  N : row-pair per thread (16B loads), columns split across CTAs, partials + fixed-order sum
+//   dense  T : one warp per column pair, 16B loads along the column, shuffle reduction
+//   CSC    N : row gather over the CSR mirror (thread per row)
+//   CSC    T : column gather (thread per column)
+// The column scale s of nes_scale is folded in: N uses x_k*s_k, T multiplies the result by s_j.
+#include "nes_internal.h"
+
+namespace nes {
+
+constexpr int GN_THREADS = 128;   // rows per CTA = 256
+constexpr int GN_CHUNK = 512;     // columns staged per smem refill
+
+__global__ void __launch_bounds__(GN_THREADS)
+gemv_n_partial_kernel(const double* __restrict__ A, size_t ld, int m, int n, int cols_per_cta,
+                      const double* __restrict__ x, const double* __restrict__ s,
+                      double* __restrict__ partial, size_t ldp) {
+    __shared__ double xs[GN_CHUNK];
+    const int tid = threadIdx.x;
+    const int r = (blockIdx.x * GN_THREADS + tid) * 2;
+    const int k_begin = blockIdx.y * cols_per_cta;
+    const int k_end = min(n, k_begin + cols_per_cta);
+    double a0 = 0.0, a1 = 0.0;
+    for (int kc = k_begin; kc < k_end; kc += GN_CHUNK) {
+        const int kn = min(GN_CHUNK, k_end - kc);
+        __syncthreads();
+        for (int i = tid; i < kn; i += GN_THREADS) xs[i] = s ? x[kc + i] * s[kc + i] : x[kc + i];
+        __syncthreads();
+        if (r < m) {
+            const double* Ap = A + r + (size_t)kc * ld;
+#pragma unroll 8
+            for (int k = 0; k < kn; ++k) {
+                const double2 v = *reinterpret_cast<const double2*>(Ap + (size_t)k * ld);
+                a0 = fma(v.x, xs[k], a0);
+                a1 = fma(v.y, xs[k], a1);
+            }
+        }
+    }
+    if (r < m) {
+        partial[blockIdx.y * ldp + r] = a0;
+        if (r + 1 < m) partial[blockIdx.y * ldp + r + 1] = a1;
+    }
+}
+
+__global__ void gemv_n_finish_kernel(const double* __restrict__ partial, size_t ldp, int nparts, int m,
+                                     double alpha, double beta, double* __restrict__ y) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    double acc = 0.0;
+    for (int p = 0; p < nparts; ++p) acc += partial[p * ldp + r];
+    y[r] = (beta == 0.0) ? alpha * acc : fma(alpha, acc, beta * y[r]);
+}
+
+// warp handles columns j, j+1
+__global__ void __launch_bounds__(256)
+gemv_t_kernel(const double* __restrict__ A, size_t ld, int m, int n, const double* __restrict__ x,
+              const double* __restrict__ s, double alpha, double beta, double* __restrict__ y) {
+    const int lane = threadIdx.x & 31;
+    const int j = (blockIdx.x * 8 + (threadIdx.x >> 5)) * 2;
+    if (j >= n) return;
+    const bool two = (j + 1 < n);
+    const double* A0 = A + (size_t)j * ld;
+    const double* A1 = A0 + (two ? ld : 0);
+    double acc0 = 0.0, acc1 = 0.0;
+    const int m2 = m & ~1;
+#pragma unroll 4
+    for (int i = lane * 2; i < m2; i += 64) {
+        const double2 xv = *reinterpret_cast<const double2*>(x + i);
+        const double2 v0 = *reinterpret_cast<const double2*>(A0 + i);
+        const double2 v1 = *reinterpret_cast<const double2*>(A1 + i);
+        acc0 = fma(v0.x, xv.x, acc0);
+        acc0 = fma(v0.y, xv.y, acc0);
+        acc1 = fma(v1.x, xv.x, acc1);
+        acc1 = fma(v1.y, xv.y, acc1);
+    }
+    if (lane == 0 && m2 < m) {
+        acc0 = fma(A0[m2], x[m2], acc0);
+        acc1 = fma(A1[m2], x[m2], acc1);
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, off);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, off);
+    }
+    if (lane == 0) {
+        if (s) acc0 *= s[j];
+        y[j] = (beta == 0.0) ? alpha * acc0 : fma(alpha, acc0, beta * y[j]);
+        if (two) {
+            if (s) acc1 *= s[j + 1];
+            y[j + 1] = (beta == 0.0) ? alpha * acc1 : fma(alpha, acc1, beta * y[j + 1]);
+        }
+    }
+}
+
+__global__ void spmv_csr_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx,
+                                const double* __restrict__ val, int m, const double* __restrict__ x,
+                                const double* __restrict__ s, double alpha, double beta,
+                                double* __restrict__ y) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= m) return;
+    double acc = 0.0;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
+        const int j = colidx[k];
+        acc = fma(val[k], s ? x[j] * s[j] : x[j], acc);
+    }
+    y[r] = (beta == 0.0) ? alpha * acc : fma(alpha, acc, beta * y[r]);
+}
+
+__global__ void spmv_csc_t_kernel(const int* __restrict__ colptr, const int* __restrict__ rowidx,
+                                  const double* __restrict__ val, int n, const double* __restrict__ x,
+                                  const double* __restrict__ s, double alpha, double beta,
+                                  double* __restrict__ y) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double acc = 0.0;
+    for (int k = colptr[j]; k < colptr[j + 1]; ++k) acc = fma(val[k], x[rowidx[k]], acc);
+    if (s) acc *= s[j];
+    y[j] = (beta == 0.0) ? alpha * acc : fma(alpha, acc, beta * y[j]);
+}
+
+static int matvec_impl(nes_ctx* c, const MatrixBase* b, const double* d_s, int transpose, double alpha,
+                       const double* d_x, double beta, double* d_y) {
+    StageTimer timer(c, NES_STAGE_GEMV);
+    const int m = (int)b->m, n = (int)b->n;
+    if (b->dense) {
+        if (!transpose) {
+            const int rowblocks = (m + 2 * GN_THREADS - 1) / (2 * GN_THREADS);
+            int want = (c->num_sms * 4 + rowblocks - 1) / rowblocks;
+            int cols = (n + want - 1) / want;
+            cols = (cols + 63) / 64 * 64;
+            const int nparts = (n + cols - 1) / cols;
+            const size_t ldp = (size_t)(m + 1) / 2 * 2;
+            double* part = ensure_ws(c, WS_MATVEC, (size_t)nparts * ldp * sizeof(double));
+            if (!part) return c->status;
+            gemv_n_partial_kernel<<<dim3(rowblocks, nparts), GN_THREADS, 0, c->stream>>>(
+                b->d_val, b->ld, m, n, cols, d_x, d_s, part, ldp);
+            NES_CHECK_LAUNCH(c);
+            gemv_n_finish_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(part, ldp, nparts, m, alpha,
+                                                                        beta, d_y);
+            NES_CHECK_LAUNCH(c);
+        } else {
+            gemv_t_kernel<<<(n + 15) / 16, 256, 0, c->stream>>>(b->d_val, b->ld, m, n, d_x, d_s, alpha,
+                                                                beta, d_y);
+            NES_CHECK_LAUNCH(c);
+        }
+    } else {
+        if (!transpose) {
+            spmv_csr_kernel<<<(m + 127) / 128, 128, 0, c->stream>>>(b->d_rowptr, b->d_colidx,
+                                                                    b->d_csr_val, m, d_x, d_s, alpha,
+                                                                    beta, d_y);
+            NES_CHECK_LAUNCH(c);
+        } else {
+            spmv_csc_t_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(b->d_colptr, b->d_rowidx,
+                                                                      b->d_values, n, d_x, d_s, alpha,
+                                                                      beta, d_y);
+            NES_CHECK_LAUNCH(c);
+        }
+    }
+    return 0;
+}
+
+int matvec(nes_ctx* c, const nes_matrix* A, int transpose, double alpha, const double* d_x,
+           double beta, double* d_y) {
+    return matvec_impl(c, A->base, A->d_scale, transpose, alpha, d_x, beta, d_y);
+}
+
+int matvec_unscaled(nes_ctx* c, const MatrixBase* A, int transpose, double alpha, const double* d_x,
+                    double beta, double* d_y) {
+    return matvec_impl(c, A, nullptr, transpose, alpha, d_x, beta, d_y);
+}
+
+}  // namespace nes

@@ -1,0 +1,198 @@
+// analyze / factorize / solve / sdmult entry points: the CHOLMOD-shaped part of the boundary
+// (sparse-cholesky.lisp:261-288, 335-342 declarations; call sites :409-431, :506-560, :567-614).
+#include "dmma_nt.cuh"
+#include "nes_internal.h"
+
+using namespace nes;
+
+namespace nes {
+int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L);       // sparse_chol.cu
+int sparse_factorize(nes_ctx* c, nes_matrix* A, nes_factor* L);
+int sparse_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x);
+void sparse_free(nes_ctx* c, nes_factor* L);
+
+int factorize_dev(nes_ctx* c, nes_matrix* A, nes_factor* L) {
+    c->status = 0;  // the Lisp does cholmod_set_status 0 before every factorize (:418, :511, :541)
+    if (!L->dense) return sparse_factorize(c, A, L);
+    L->factorized = 0;
+    NES_TRY(dense_form_normal(c, A, L));
+    return dense_cholesky(c, L);
+}
+
+int solve_dev(nes_ctx* c, nes_factor* L, double* d_x) {
+    if (!L->factorized) return fail(c, NES_ERR_INVALID, "solve on a factor that is not factorized");
+    if (!L->dense) return sparse_solve_inplace(c, L, d_x);
+    return dense_solve_inplace(c, L, d_x);
+}
+}  // namespace nes
+
+extern "C" {
+
+nes_factor* nes_analyze(nes_matrix* A, nes_ctx* c) {
+    NES_ENTER_PTR(c);
+    if (!A) {
+        fail(c, NES_ERR_INVALID, "nes_analyze: null matrix");
+        return nullptr;
+    }
+    nes_factor* L = new nes_factor();
+    L->analyzed_for = A;
+    L->m = A->base->m;
+    if (!A->base->dense) {
+        L->dense = false;
+        if (sparse_analyze(c, A, L) != 0) {
+            nes_free_factor(&L, c);
+            return nullptr;
+        }
+        return L;
+    }
+    const size_t m = L->m, n = A->base->n;
+    L->dense = true;
+    L->ld = (m + 15) / 16 * 16;
+    L->d_M = static_cast<double*>(dev_alloc(c, L->ld * m * sizeof(double)));
+    L->d_dinv = static_cast<double*>(dev_alloc(c, (m + 16) * sizeof(double)));
+    L->d_rhs = static_cast<double*>(dev_alloc(c, (m + 16) * sizeof(double)));
+    L->d_info = static_cast<int*>(dev_alloc(c, 4 * sizeof(int)));
+    if (!L->d_M || !L->d_dinv || !L->d_rhs || !L->d_info) {
+        nes_free_factor(&L, c);
+        return nullptr;
+    }
+    // pad rows m..ld of M are never written by the kernels; keep them finite for the TMA boxes
+    cudaMemsetAsync(L->d_M, 0, L->ld * m * sizeof(double), c->stream);
+    if (make_operand_map(&L->mapM, L->d_M, (long long)m, (long long)m, (long long)L->ld) != 0) {
+        fail(c, NES_ERR_CUDA, "cuTensorMapEncodeTiled failed for M (%zu x %zu)", m, m);
+        nes_free_factor(&L, c);
+        return nullptr;
+    }
+    // the analytic counters the reference prints after cholmod_analyze (affine-scaling.lisp:273-279)
+    const double dm = (double)m, dn = (double)n;
+    c->anz = dm * (dm + 1) / 2;
+    c->aatfl = dm * (dm + 1) * dn;
+    c->lnz = dm * (dm + 1) / 2;
+    c->fl = dm * (dm + 1) * (2 * dm + 1) / 6;
+    c->status = 0;
+    return L;
+}
+
+int nes_factorize(nes_matrix* A, nes_factor* L, nes_ctx* c) {
+    if (!c || !c->started) return 0;
+    cudaSetDevice(c->device);
+    if (!A || !L || A->base->m != L->m || A->base->dense != L->dense) {
+        fail(c, NES_ERR_INVALID, "nes_factorize: factor was not analyzed for this matrix");
+        return 0;
+    }
+    const int rc = factorize_dev(c, A, L);
+    return rc < 0 ? 0 : 1;  // CHOLMOD returns TRUE even when the matrix is not positive definite
+}
+
+int nes_solve(int sys, nes_factor* L, const double* b, double* x, nes_ctx* c) {
+    NES_ENTER(c);
+    if (sys != 0) return fail(c, NES_ERR_INVALID, "nes_solve: only sys = 0 (CHOLMOD_A) is supported");
+    if (!L || !b || !x) return fail(c, NES_ERR_INVALID, "nes_solve: null argument");
+    NES_TRY(upload(c, L->d_rhs, b, L->m * sizeof(double)));
+    const int rc = solve_dev(c, L, L->d_rhs);
+    if (rc != 0) return rc;
+    NES_TRY(download(c, x, L->d_rhs, L->m * sizeof(double)));
+    return 0;
+}
+
+int nes_solve2(int sys, nes_factor* L, const double* b, double* x, nes_ctx* c) {
+    // cholmod_solve2 differs from cholmod_solve only in reusing caller-held workspaces
+    // (X, Y, E of solve-sparse-state); here they live inside the factor already.
+    const int rc = nes_solve(sys, L, b, x, c);
+    return rc == 0 ? 1 : 0;  // solve2 returns TRUE/FALSE (sparse-cholesky.lisp:546-554)
+}
+
+static void nes_free_factor_impl(nes_factor* L, nes_ctx* c) {
+    if (!L->dense) sparse_free(c, L);
+    dev_free(c, L->d_M);
+    dev_free(c, L->d_dinv);
+    dev_free(c, L->d_rhs);
+    dev_free(c, L->d_info);
+}
+
+int nes_free_factor(nes_factor** L, nes_ctx* c) {
+    if (!c) return 0;
+    if (!L || !*L) return 1;
+    if (c->started) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+    }
+    nes_free_factor_impl(*L, c);
+    delete *L;
+    *L = nullptr;
+    return 1;
+}
+
+int nes_solve_dense(const double* B, size_t nrow, size_t ncol, const double* b, double* x,
+                    nes_ctx* c) {
+    NES_ENTER(c);
+    nes_matrix* A = nes_dense_to_matrix(B, nrow, ncol, nrow, c);
+    if (!A) return c->status;
+    nes_factor* L = nes_analyze(A, c);
+    int rc = L ? 0 : c->status;
+    if (L) {
+        rc = factorize_dev(c, A, L);
+        if (rc == 0) rc = nes_solve(0, L, b, x, c);
+    }
+    nes_free_factor(&L, c);
+    nes_free_matrix(&A, c);
+    if (rc > 0) c->status = rc;  // NOT_POSDEF survives the frees, like cholmod_common.status
+    return rc;
+}
+
+int nes_factor_to_dense(nes_factor* L, double* Lout, size_t ld, int* perm, nes_ctx* c) {
+    NES_ENTER(c);
+    if (!L || !Lout || ld < L->m) return fail(c, NES_ERR_INVALID, "nes_factor_to_dense: bad argument");
+    if (!L->dense) return fail(c, NES_ERR_INVALID, "nes_factor_to_dense: sparse factor not supported yet");
+    const size_t m = L->m;
+    NES_CUDA(c, cudaMemcpy2DAsync(Lout, ld * sizeof(double), L->d_M, L->ld * sizeof(double),
+                                  m * sizeof(double), m, cudaMemcpyDeviceToHost, c->stream));
+    NES_CUDA(c, cudaStreamSynchronize(c->stream));
+    for (size_t j = 0; j < m; ++j)
+        for (size_t i = 0; i < j; ++i) Lout[i + j * ld] = 0.0;
+    if (perm)
+        for (size_t i = 0; i < m; ++i) perm[i] = (int)i;
+    return 0;
+}
+
+int nes_normal_matrix_to_dense(nes_matrix* A, double* Mout, size_t ld, nes_ctx* c) {
+    NES_ENTER(c);
+    if (!A || !Mout || ld < A->base->m) return fail(c, NES_ERR_INVALID, "bad argument");
+    if (!A->base->dense) return fail(c, NES_ERR_INVALID, "dense matrices only");
+    nes_factor* L = nes_analyze(A, c);
+    if (!L) return c->status;
+    int rc = dense_form_normal(c, A, L);
+    const size_t m = L->m;
+    if (rc == 0) {
+        cudaError_t e = cudaMemcpy2DAsync(Mout, ld * sizeof(double), L->d_M, L->ld * sizeof(double),
+                                          m * sizeof(double), m, cudaMemcpyDeviceToHost, c->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+        if (e != cudaSuccess) rc = fail(c, NES_ERR_CUDA, "copy back failed: %s", cudaGetErrorString(e));
+    }
+    nes_free_factor(&L, c);
+    return rc;
+}
+
+int nes_sdmult(nes_matrix* A, int transpose, const double alpha[2], const double beta[2],
+               const double* x, double* y, nes_ctx* c) {
+    if (!c || !c->started) return 0;
+    cudaSetDevice(c->device);
+    if (!A || !alpha || !beta || !x || !y) {
+        fail(c, NES_ERR_INVALID, "nes_sdmult: null argument");
+        return 0;
+    }
+    const size_t m = A->base->m, n = A->base->n;
+    const size_t nx = transpose ? m : n, ny = transpose ? n : m;
+    const size_t px = (nx + 1) / 2 * 2, py = (ny + 1) / 2 * 2;
+    double* ws = ensure_ws(c, WS_API, (px + py) * sizeof(double));
+    if (!ws) return 0;
+    double* d_x = ws;
+    double* d_y = ws + px;
+    if (upload(c, d_x, x, nx * sizeof(double)) != 0) return 0;
+    if (beta[0] != 0.0 && upload(c, d_y, y, ny * sizeof(double)) != 0) return 0;
+    if (matvec(c, A, transpose, alpha[0], d_x, beta[0], d_y) != 0) return 0;
+    if (download(c, y, d_y, ny * sizeof(double)) != 0) return 0;
+    return 1;  // cholmod_sdmult returns TRUE on success (sparse-cholesky.lisp:600)
+}
+
+}  // extern "C"

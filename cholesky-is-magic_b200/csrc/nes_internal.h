@@ -1,0 +1,183 @@
+// Internal structures of libnes.so.  Public contract: include/nes.h.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <unordered_map>
+#include <vector>
+
+#include "../../include/nes.h"
+
+// ---- context (plays cholmod_common; wrapper.c:18-52 lists the fields the Lisp touches) ----------
+struct nes_ctx {
+    // wrapper.c accessor fields
+    int print = 3;
+    void* print_function = nullptr;
+    double dbound = 0.0;
+    double supernodal_switch = 40.0;
+    int supernodal = 1;  // CHOLMOD_AUTO
+    int selected = 0;
+    int itype = 0;
+    int dtype = 0;
+    int status = 0;
+    double fl = 0, lnz = 0, anz = 0, modfl = 0;
+    size_t malloc_count = 0, memory_usage = 0, memory_inuse = 0;
+    double rowfacfl = 0, aatfl = 0;
+    int blas_ok = 1;
+    int minor = -1;
+
+    // runtime
+    int started = 0;
+    int device = -1;
+    int num_sms = 0;
+    cudaStream_t stream = nullptr;
+    char err[512] = {0};
+    long long launches = 0;
+
+    // allocation ledger (device + pinned host), so frees can be accounted without sizes
+    std::unordered_map<void*, size_t> ledger;
+
+    // workspaces owned by the context ("Common workspace", released by nes_free_work / nes_finish).
+    // One slot per internal user so nested stages never alias each other's scratch.
+    static constexpr int kNumWs = 4;
+    double* d_ws[kNumWs] = {nullptr, nullptr, nullptr, nullptr};
+    size_t ws_bytes[kNumWs] = {0, 0, 0, 0};
+    double* h_pinned = nullptr;  // small pinned staging buffer for scalar read-backs
+    size_t pinned_bytes = 0;
+
+    // stage timing
+    int timing = 0;
+    struct Interval {
+        int stage;
+        cudaEvent_t a, b;
+    };
+    std::vector<Interval> intervals;
+    std::vector<cudaEvent_t> event_pool;
+    double stage_ms[NES_NUM_STAGES] = {0};
+    long long stage_count[NES_NUM_STAGES] = {0};
+};
+
+namespace nes {
+
+int fail(nes_ctx* c, int status, const char* fmt, ...);
+#define NES_CUDA(c, call)                                                                  \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess)                                                            \
+            return nes::fail((c), NES_ERR_CUDA, "%s failed: %s (%s:%d)", #call,            \
+                             cudaGetErrorString(e__), __FILE__, __LINE__);                 \
+    } while (0)
+#define NES_CHECK_LAUNCH(c)                                                                \
+    do {                                                                                   \
+        ++(c)->launches;                                                                   \
+        cudaError_t e__ = cudaGetLastError();                                              \
+        if (e__ != cudaSuccess)                                                            \
+            return nes::fail((c), NES_ERR_CUDA, "kernel launch failed: %s (%s:%d)",        \
+                             cudaGetErrorString(e__), __FILE__, __LINE__);                 \
+    } while (0)
+#define NES_TRY(expr)                \
+    do {                             \
+        int rc__ = (expr);           \
+        if (rc__ < 0) return rc__;   \
+    } while (0)
+
+#define NES_ENTER_PTR(c)                                                 \
+    do {                                                                 \
+        if (!(c) || !(c)->started) {                                     \
+            if (c) nes::fail((c), NES_ERR_NO_DEVICE, "context not started"); \
+            return nullptr;                                              \
+        }                                                                \
+        cudaSetDevice((c)->device);                                      \
+    } while (0)
+#define NES_ENTER(c)                                                                        \
+    do {                                                                                    \
+        if (!(c)) return NES_ERR_INVALID;                                                   \
+        if (!(c)->started) return nes::fail((c), NES_ERR_NO_DEVICE, "context not started"); \
+        cudaSetDevice((c)->device);                                                         \
+    } while (0)
+
+void* dev_alloc(nes_ctx* c, size_t bytes);  // nullptr on failure (status set)
+void dev_free(nes_ctx* c, void* p);
+void* pinned_alloc(nes_ctx* c, size_t bytes);
+void pinned_free(nes_ctx* c, void* p);
+enum { WS_API = 0, WS_MATVEC = 1, WS_REDUCE = 2, WS_DRIVER = 3 };
+// grow-only device workspace slot; returns nullptr on failure (status set)
+double* ensure_ws(nes_ctx* c, int slot, size_t bytes);
+int ensure_pinned(nes_ctx* c, size_t bytes);
+int upload(nes_ctx* c, void* dst_dev, const void* src_host, size_t bytes);
+int download(nes_ctx* c, void* dst_host, const void* src_dev, size_t bytes);
+
+// RAII stage timer: records CUDA events on the context's stream around a library stage.
+struct StageTimer {
+    nes_ctx* c;
+    int idx;
+    StageTimer(nes_ctx* c, int stage);
+    ~StageTimer();
+};
+
+// ---- matrices ----------------------------------------------------------------------------------
+struct MatrixBase {
+    int refs = 1;
+    bool dense = true;
+    size_t m = 0, n = 0;
+    // dense: column-major, ld multiple of 16 doubles (columns 128B aligned)
+    size_t ld = 0;
+    double* d_val = nullptr;
+    CUtensorMap map;  // operand map for dmma_nt (dense only)
+    // sparse: CSC (sorted, packed, duplicates summed), int32 indices like the reference's itype 0
+    size_t nnz = 0;
+    int* d_colptr = nullptr;
+    int* d_rowidx = nullptr;
+    double* d_values = nullptr;
+    // CSR mirror (row-gather SpMV without atomics => deterministic): values are re-gathered
+    // from the CSC array through d_csr_src whenever the CSC values change (row scaling)
+    int* d_rowptr = nullptr;
+    int* d_colidx = nullptr;
+    int* d_csr_src = nullptr;
+    double* d_csr_val = nullptr;
+    std::vector<int> h_colptr, h_rowidx;  // host copy of the pattern for symbolic analysis
+};
+
+}  // namespace nes
+
+struct nes_matrix {
+    nes::MatrixBase* base = nullptr;
+    double* d_scale = nullptr;  // column scale s (n doubles) or nullptr (cholmod_scale folded lazily)
+    double* d_theta = nullptr;  // s^2 padded to a multiple of 16 (formation operand), or nullptr
+};
+
+struct nes_factor {
+    bool dense = true;
+    size_t m = 0;
+    size_t ld = 0;
+    double* d_M = nullptr;     // m x m column-major: lower triangle holds M, then L in place
+    double* d_dinv = nullptr;  // 1/L_jj
+    double* d_rhs = nullptr;   // solve workspace (solve2's Y/E)
+    int* d_info = nullptr;     // {status, minor}
+    CUtensorMap mapM;
+    int factorized = 0;
+    nes_matrix* analyzed_for = nullptr;
+};
+
+namespace nes {
+
+// ---- kernels / stage drivers (one per .cu) ------------------------------------------------------
+// K1: M(lower) = A diag(theta) A'  (dense_form.cu)
+int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L);
+// K2: in-place blocked Cholesky of L->d_M (dense_chol.cu); sets c->status / c->minor
+int dense_cholesky(nes_ctx* c, nes_factor* L);
+// K5: x <- (L L')^{-1} x, x device vector of length m (dense_solve.cu)
+int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x);
+// K6: y <- alpha op(A diag(s)) x + beta y on device vectors (gemv.cu); handles dense and CSC
+int matvec(nes_ctx* c, const nes_matrix* A, int transpose, double alpha, const double* d_x,
+           double beta, double* d_y);
+// install a column scale that already lives on the device (nes_scale without the PCIe hop)
+int set_scale_dev(nes_ctx* c, nes_matrix* A, const double* d_s);
+// plain op(A) product ignoring the column scale
+int matvec_unscaled(nes_ctx* c, const MatrixBase* A, int transpose, double alpha, const double* d_x,
+                    double beta, double* d_y);
+
+}  // namespace nes

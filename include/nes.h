@@ -1,0 +1,198 @@
+/* nes.h -- C ABI of the B200-native normal-equations engine (libnes.so).
+ *
+ * Drop-in boundary for the hot path of pkhuong/cholesky-is-magic's interior-point LP solvers.
+ * The reference crosses from Common Lisp into C through sb-alien (sparse-cholesky.lisp:1-342) to
+ * SuiteSparse CHOLMOD plus the accessor shim wrapper.c.  This header declares what a maintainer
+ * binds instead: the same call shapes (context with get/set accessors, analyze / factorize / solve /
+ * sdmult / scale on opaque handles, handle-taking frees that return non-zero on success), with all
+ * arithmetic executed by hand-written sm_100a CUDA kernels.  Plain C types only; every pointer
+ * argument is a HOST pointer unless its name ends in _dev.  There is no CPU fallback: if no CUDA
+ * device is usable nes_start() fails and every later call returns NES_ERR_NO_DEVICE.
+ *
+ * Each entry point cites the reference interface it replaces (file:line in the reference tree).
+ */
+#ifndef NES_H
+#define NES_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default) /* the library itself is built with -fvisibility=hidden */
+#endif
+
+/* status codes: same sign convention as cholmod_common.status (0 ok, >0 warning, <0 error) */
+#define NES_OK 0
+#define NES_NOT_POSDEF 1        /* CHOLMOD_NOT_POSDEF: non-positive pivot, see nes_get_minor() */
+#define NES_ERR_NO_DEVICE (-1)  /* no usable sm_100 device / library not started */
+#define NES_ERR_OUT_OF_MEMORY (-2)
+#define NES_ERR_INVALID (-4)    /* CHOLMOD_INVALID: bad argument */
+#define NES_ERR_CUDA (-5)       /* CUDA runtime error; text in nes_last_error() */
+#define NES_ERR_COMM (-6)       /* NCCL error */
+
+typedef struct nes_ctx nes_ctx;       /* replaces cholmod_common   (sparse-cholesky.lisp:3) */
+typedef struct nes_matrix nes_matrix; /* replaces cholmod_sparse* / cholmod_dense* holding A
+                                         (sparse-cholesky.lisp:45-63, 162-171) */
+typedef struct nes_factor nes_factor; /* replaces cholmod_factor* + the solve2 workspaces of
+                                         solve-sparse-state (sparse-cholesky.lisp:143, 479-484) */
+
+/* ---- context lifetime: wrapper.c:8-16, sparse-cholesky.lisp:389-406 (with-cholmod) ---------- */
+nes_ctx* nes_allocate(void);            /* cholmod_allocate  (wrapper.c:8)  */
+void nes_release(nes_ctx* c);           /* cholmod_release   (wrapper.c:13) */
+int nes_start(nes_ctx* c);              /* cholmod_start     (sparse-cholesky.lisp:40): binds the
+                                           current CUDA device (nes_set_device first to pick one) */
+int nes_finish(nes_ctx* c);             /* cholmod_finish    (sparse-cholesky.lisp:41) */
+int nes_defaults(nes_ctx* c);           /* cholmod_defaults  (sparse-cholesky.lisp:42) */
+int nes_free_work(nes_ctx* c);          /* cholmod_free_work (sparse-cholesky.lisp:43) */
+int nes_set_device(nes_ctx* c, int device);
+const char* nes_last_error(const nes_ctx* c);
+int nes_version(int version[3]);        /* cholmod_version   (sparse-cholesky.lisp:258) */
+
+/* ---- accessors: the 19 fields of wrapper.c:31-52, same get/set-returns-old contract --------- */
+#define NES_DECLARE_ACCESSOR(FIELD, TYPE)              \
+    TYPE nes_get_##FIELD(const nes_ctx* c);            \
+    TYPE nes_set_##FIELD(nes_ctx* c, TYPE new_value);
+NES_DECLARE_ACCESSOR(print, int)
+NES_DECLARE_ACCESSOR(print_function, void*)
+NES_DECLARE_ACCESSOR(dbound, double)            /* diagonal clamp; 0 = off like cholmod_defaults */
+NES_DECLARE_ACCESSOR(supernodal_switch, double)
+NES_DECLARE_ACCESSOR(supernodal, int)
+NES_DECLARE_ACCESSOR(selected, int)
+NES_DECLARE_ACCESSOR(itype, int)                /* 0: int32 indices (sparse-cholesky.lisp:26) */
+NES_DECLARE_ACCESSOR(dtype, int)                /* 0: double */
+NES_DECLARE_ACCESSOR(status, int)
+NES_DECLARE_ACCESSOR(fl, double)                /* factorization flop count from analyze */
+NES_DECLARE_ACCESSOR(lnz, double)               /* nnz(L) */
+NES_DECLARE_ACCESSOR(anz, double)               /* nnz(tril(A A')) */
+NES_DECLARE_ACCESSOR(modfl, double)
+NES_DECLARE_ACCESSOR(malloc_count, size_t)      /* live device+host blocks owned by the context */
+NES_DECLARE_ACCESSOR(memory_usage, size_t)      /* peak bytes */
+NES_DECLARE_ACCESSOR(memory_inuse, size_t)      /* live bytes (leak test, sparse-newton-solve.lisp:255-258) */
+NES_DECLARE_ACCESSOR(rowfacfl, double)
+NES_DECLARE_ACCESSOR(aatfl, double)             /* flops to form A A' */
+NES_DECLARE_ACCESSOR(blas_ok, int)
+#undef NES_DECLARE_ACCESSOR
+int nes_get_minor(const nes_ctx* c);            /* column of the failed pivot (cholmod_factor.minor) */
+
+/* ---- constraint matrix A (device resident, immutable values + optional column scale) --------- */
+/* make-dense-from-matlisp + cholmod_dense_to_sparse (sparse-cholesky.lisp:346-368, 411-414):
+ * A is m x n column-major with leading dimension ld >= m. */
+nes_matrix* nes_dense_to_matrix(const double* A, size_t nrow, size_t ncol, size_t ld, nes_ctx* c);
+/* make-sparse-from-triplet-vector (sparse-cholesky.lisp:433-459): cholmod_allocate_triplet +
+ * cholmod_triplet_to_sparse (duplicates summed) + cholmod_sort. */
+nes_matrix* nes_triplet_to_sparse(const int* row, const int* col, const double* val, size_t nnz,
+                                  size_t nrow, size_t ncol, nes_ctx* c);
+/* compressed-column input (cholmod_sparse layout p/i/x, sorted or not; packed). */
+nes_matrix* nes_csc_to_matrix(const int* colptr, const int* rowidx, const double* val, size_t nrow,
+                              size_t ncol, nes_ctx* c);
+/* the dense synthetic test matrix of newton-solve.lisp:194-195, A = U(0,1) + eye(m,n), generated on
+ * the device from a counter-based hash (same values as lpgen.dense_entry on the host). */
+nes_matrix* nes_generate_dense(size_t nrow, size_t ncol, unsigned long long seed, nes_ctx* c);
+/* cholmod_copy_sparse (sparse-cholesky.lisp:128): shares the immutable values, own column scale. */
+nes_matrix* nes_copy_matrix(nes_matrix* A, nes_ctx* c);
+/* cholmod_free_sparse (sparse-cholesky.lisp:75): frees *A, stores NULL, returns non-zero on success. */
+int nes_free_matrix(nes_matrix** A, nes_ctx* c);
+/* cholmod_scale(s, CHOLMOD_COL=2, A) (sparse-cholesky.lisp:461-473): A <- A diag(s).  `scale` must be
+ * 2 (columns).  The product is never materialised: s is folded into formation and sdmult. */
+int nes_scale(const double* s, int scale, nes_matrix* A, nes_ctx* c);
+/* affine-A-copy (affine-scaling.lisp:29-35): restore the pristine values (drop the column scale). */
+int nes_unscale(nes_matrix* A, nes_ctx* c);
+size_t nes_matrix_nrow(const nes_matrix* A);
+size_t nes_matrix_ncol(const nes_matrix* A);
+size_t nes_matrix_nnz(const nes_matrix* A);     /* cholmod_nnz (sparse-cholesky.lisp:84) */
+int nes_matrix_is_dense(const nes_matrix* A);
+/* row scaling of scale-constraints / rescale-sf (primal-dual-affine-scaling.lisp:50-73,
+ * standard-form.lisp:107-134): row i *= 1/max_j|a_ij| when that max >= 1e-6; rowscale_out[i]
+ * receives the factor (so the caller can scale b alike).  Modifies the shared values in place. */
+int nes_scale_rows_maxabs(nes_matrix* A, double* rowscale_out, nes_ctx* c);
+
+/* ---- y <- alpha*op(A)*x + beta*y : cholmod_sdmult via sparse-m* (sparse-cholesky.lisp:567-614) */
+int nes_sdmult(nes_matrix* A, int transpose, const double alpha[2], const double beta[2],
+               const double* x, double* y, nes_ctx* c);
+
+/* ---- normal equations: analyze / factorize / solve -------------------------------------------
+ * With an unsymmetric A (stype 0) CHOLMOD factorizes A*A' (sparse-cholesky.lisp:408); after
+ * nes_scale that is (A diag s)(A diag s)' = A diag(s^2) A'. */
+nes_factor* nes_analyze(nes_matrix* A, nes_ctx* c);          /* cholmod_analyze   (:261) */
+int nes_factorize(nes_matrix* A, nes_factor* L, nes_ctx* c); /* cholmod_factorize (:265); always
+                                   returns 1 like CHOLMOD; failure is reported in status (NOT_POSDEF) */
+/* cholmod_solve(sys, L, b) (:270): sys must be 0 (CHOLMOD_A).  x and b are nrow doubles. */
+int nes_solve(int sys, nes_factor* L, const double* b, double* x, nes_ctx* c);
+/* cholmod_solve2 (:276) as used by solve-sparse-recycle (:524-560): same, workspaces live in L. */
+int nes_solve2(int sys, nes_factor* L, const double* b, double* x, nes_ctx* c);
+int nes_free_factor(nes_factor** L, nes_ctx* c);             /* cholmod_free_factor (:145) */
+/* solve-dense (sparse-cholesky.lisp:409-431) in one call: x with (B B') x = b, B m x n column-major.
+ * Returns 0 and fills x, or returns NES_NOT_POSDEF (the Lisp returns NIL). */
+int nes_solve_dense(const double* B, size_t nrow, size_t ncol, const double* b, double* x,
+                    nes_ctx* c);
+/* copy the factor back (testing / parity): L is nrow x nrow column-major lower triangular (dense
+ * factor; sparse factors are expanded, with the fill-reducing permutation in perm if non-NULL). */
+int nes_factor_to_dense(nes_factor* L, double* Lout, size_t ld, int* perm, nes_ctx* c);
+/* copy the formed normal matrix A diag(s^2) A' back (lower triangle valid). */
+int nes_normal_matrix_to_dense(nes_matrix* A, double* Mout, size_t ld, nes_ctx* c);
+
+/* ---- solve-kkt-newton (newton-solve.lisp:139-154 dense, sparse-newton-solve.lisp:150-168 sparse)
+ * Inputs l,u,w,z,e,f,h are ncol doubles, g is nrow doubles (none is modified; the Lisp destroys its
+ * arguments and callers pass copies).  filters != 0 applies filter-U / filter-Z first
+ * (sparse-newton-solve.lisp:30-45).  L may be NULL (analyze per call, like solve-sparse-one-shot) or
+ * a factor from nes_analyze (symbolic reuse).  Outputs dw,dx,dz (ncol) and dy (nrow).
+ * Returns 0, or NES_NOT_POSDEF when the Cholesky fails (the Lisp signals on the NIL). */
+int nes_kkt_newton(nes_matrix* A, nes_factor* L, int filters, const double* l, const double* u,
+                   const double* w, const double* z, const double* e, const double* f,
+                   const double* g, const double* h, double* dw, double* dx, double* dy, double* dz,
+                   nes_ctx* c);
+
+/* ---- device-resident primal-dual affine scaling state (primal-dual-affine-scaling.lisp) -------
+ * Holds c, b, lo, hi, x, y, w, z and all iteration temporaries on the GPU; only scalars cross PCIe
+ * per iteration.  Function names follow the Lisp. */
+typedef struct nes_pdas nes_pdas;
+/* make-pdas-state (:8-15, :120-133): vectors are copied to the device.  lo/hi already clamped. */
+nes_pdas* nes_pdas_create(nes_matrix* A, const double* cvec, const double* b, const double* lo,
+                          const double* hi, const double* x, const double* y, const double* w,
+                          const double* z, int filters, nes_ctx* c);
+int nes_pdas_free(nes_pdas** st, nes_ctx* c);
+/* violation (:135-150) + the scalars of one-pdas-iteration (:325-332): out[0..7] =
+ * pobj, dobj, |Ax-b|inf, |dual|inf, |w.u|inf, |z.l|inf, min(l), min(u). */
+int nes_pdas_violation(nes_pdas* st, double out[8], nes_ctx* c);
+/* direction (:152-164): solve-kkt-newton on the current violation vectors, then pdas-step
+ * (:194-198) = min(box-step, pos-step w, pos-step z).  *step receives alpha_max (+inf if none). */
+int nes_pdas_newton_direction(nes_pdas* st, double* step, nes_ctx* c);
+/* apply-step (:200-207): w,x,y,z -= alpha * (dw,dx,dy,dz). */
+int nes_pdas_apply_step(nes_pdas* st, double alpha, nes_ctx* c);
+/* one-repair-iteration (:268-288).  out[0] = |g|, out[1] = step. */
+int nes_pdas_repair(nes_pdas* st, double out[2], nes_ctx* c);
+/* the recentring branch of one-pdas-iteration (:348-366): w,z += 1e-4, projected centering step. */
+int nes_pdas_recentre(nes_pdas* st, double out[2], nes_ctx* c);
+/* one-pdas-iteration (:319-383) entirely in the library: out[0..2] = gap, dobj, step (NaN when the
+ * Lisp returns no step), out[3..8] = pobj and the four violations + branch taken (0 newton,
+ * 1 repair, 2 recentre). */
+int nes_pdas_one_iteration(nes_pdas* st, int repair, double out[9], nes_ctx* c);
+/* pdas (:385-396): loop until gap < 1e-4 or max_iter; returns iterations in *iters, (dobj, gap). */
+int nes_pdas_solve(nes_pdas* st, int max_iter, int* iters, double* obj, double* gap, nes_ctx* c);
+/* read / write state vectors: which = 'x','y','w','z' or direction 'X','Y','W','Z' (dx,dy,dw,dz) */
+int nes_pdas_get(nes_pdas* st, int which, double* out, nes_ctx* c);
+int nes_pdas_set(nes_pdas* st, int which, const double* in, nes_ctx* c);
+
+/* ---- instrumentation (bench.py / roofline): device time of the library's own stages ---------- */
+#define NES_STAGE_FORM 0      /* K1 fused scale+SYRK   */
+#define NES_STAGE_FACTOR 1    /* K2 Cholesky            */
+#define NES_STAGE_SOLVE 2     /* K5 triangular solves   */
+#define NES_STAGE_GEMV 3      /* K6 GEMV / SpMV         */
+#define NES_STAGE_VECTOR 4    /* K7/K8 elementwise + reductions */
+#define NES_NUM_STAGES 5
+int nes_timing_enable(nes_ctx* c, int on);            /* CUDA events on the library's stream */
+int nes_timing_reset(nes_ctx* c);
+/* accumulated milliseconds and number of timed intervals for a stage since the last reset */
+int nes_timing_get(nes_ctx* c, int stage, double* ms, long long* count);
+long long nes_get_launch_count(const nes_ctx* c);     /* kernels launched by this context */
+int nes_synchronize(nes_ctx* c);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif /* NES_H */
