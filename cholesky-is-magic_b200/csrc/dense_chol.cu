@@ -20,22 +20,28 @@ namespace nes {
 
 constexpr int CH_NB = 128;
 constexpr int CH_W = 16;
-constexpr int CH_P = 129;  // smem pitch of the diagonal block (column-major)
-constexpr int CH_DIAG_SMEM = (CH_NB * CH_P + CH_NB) * 8;
+constexpr int CH_P = 128;  // smem pitch of the diagonal block (column-major, dense TMA box)
+constexpr int CH_DIAG_SMEM = (CH_NB * CH_P + CH_NB) * 8 + 128 + 16;
 
 __global__ void __launch_bounds__(256)
-potrf_diag_kernel(double* __restrict__ M, long long ld, int j0, int jb, double* __restrict__ dinv_out,
-                  double dbound, int* __restrict__ info) {
-    extern __shared__ double S[];
+potrf_diag_kernel(const __grid_constant__ CUtensorMap mapBlk, int j0, int jb,
+                  double* __restrict__ dinv_out, double dbound, int* __restrict__ info) {
+    extern __shared__ uint8_t potrf_smem_raw[];
+    double* S = reinterpret_cast<double*>(
+        (reinterpret_cast<uintptr_t>(potrf_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
     double* dinv = S + CH_NB * CH_P;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dinv + CH_NB);
     const int tid = threadIdx.x;
-    double* Mb = M + j0 + (long long)j0 * ld;
 
-    for (int idx = tid; idx < jb * jb; idx += 256) {
-        const int cc = idx / jb, r = idx - cc * jb;
-        if (r >= cc) S[r + cc * CH_P] = Mb[r + (long long)cc * ld];
+    // one TMA box brings the whole 128x128 diagonal block (rows/cols past m are zero-filled)
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar, CH_NB * CH_NB * 8);
+        tma_load_2d(S, &mapBlk, j0, j0, bar);
     }
     __syncthreads();
+    mbar_wait(bar, 0);
 
     for (int c0 = 0; c0 < jb; c0 += CH_W) {
         const int w = min(CH_W, jb - c0);
@@ -138,11 +144,13 @@ potrf_diag_kernel(double* __restrict__ M, long long ld, int j0, int jb, double* 
         __syncthreads();
     }
 
-    for (int idx = tid; idx < jb * jb; idx += 256) {
-        const int cc = idx / jb, r = idx - cc * jb;
-        if (r >= cc) Mb[r + (long long)cc * ld] = S[r + cc * CH_P];
-    }
     if (tid < jb) dinv_out[j0 + tid] = dinv[tid];
+    fence_proxy_async();
+    __syncthreads();
+    if (tid == 0) {
+        tma_store_2d(&mapBlk, j0, j0, S);  // clipped at the matrix edge by the tensor map
+        tma_store_commit_and_wait();
+    }
 }
 
 // X L' = B for a 64-row slab of the panel below a full 128x128 diagonal block.
@@ -236,6 +244,26 @@ int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L) {
     a.beta = 0.0;
     a.lower = 1;
     a.same_operand = 1;
+    // balance the partial last wave of the static tile round-robin (6% at m=8192 on 148 SMs)
+    {
+        const int tm = (a.M + NT_BM - 1) / NT_BM;
+        const int ntiles = tm * (tm + 1) / 2;
+        const int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
+        int sr = 0, ss = 0;
+        nt_plan_split(ntiles, (a.K + NT_BK - 1) / NT_BK, grid, &sr, &ss);
+        if (sr > 0) {
+            if (!c->d_split_counters) {
+                c->d_split_counters = static_cast<int*>(dev_alloc(c, 1024 * sizeof(int)));
+                if (!c->d_split_counters) return c->status;
+                NES_CUDA(c, cudaMemsetAsync(c->d_split_counters, 0, 1024 * sizeof(int), c->stream));
+            }
+            a.split_ws = ensure_ws(c, WS_SPLIT, (size_t)sr * ss * NT_BM * NT_BN * sizeof(double));
+            if (!a.split_ws) return c->status;
+            a.split_counters = c->d_split_counters;
+            a.split_r = sr;
+            a.split_s = ss;
+        }
+    }
     cudaError_t e = nt_launch(b->map, b->map, a, c->num_sms, c->stream);
     ++c->launches;
     if (e != cudaSuccess)
@@ -251,8 +279,8 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
     NES_CUDA(c, cudaMemsetAsync(L->d_info, 0, 2 * sizeof(int), c->stream));
     for (int j0 = 0; j0 < m; j0 += CH_NB) {
         const int jb = (m - j0 < CH_NB) ? m - j0 : CH_NB;
-        potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->d_M, ld, j0, jb, L->d_dinv,
-                                                              c->dbound, L->d_info);
+        potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->mapBlk, j0, jb, L->d_dinv, c->dbound,
+                                                              L->d_info);
         NES_CHECK_LAUNCH(c);
         const int rest = m - j0 - jb;
         if (rest <= 0) break;

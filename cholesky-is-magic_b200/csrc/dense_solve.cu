@@ -5,42 +5,87 @@
 //                        unknown, one barrier per column
 //   trsv_update_*_kernel rank-128 update of the remaining right-hand side, coalesced along rows of L
 #include "nes_internal.h"
+#include "ptx_util.cuh"
 
 namespace nes {
 
 constexpr int SV_NB = 128;
-constexpr int SV_P = 129;
-constexpr int SV_SMEM = (SV_NB * SV_P + SV_NB) * 8;
+constexpr int SV_P = 130;  // smem pitch: 16B-aligned columns for bulk copies, <= 2-way conflicts on L'
+constexpr int SV_SMEM = (SV_NB * SV_P + SV_NB) * 8 + 16;
 
-__global__ void __launch_bounds__(256)
+// One CTA of 128 threads (thread = unknown).  The lower triangle of the 128x128 block arrives by
+// one cp.async.bulk per column; the solve proceeds in four 32x32 sub-blocks, each by ONE WARP with
+// shuffles (lane = row), followed by a rank-32 update of the remaining unknowns by all warps.
+__global__ void __launch_bounds__(SV_NB)
 trsv_diag_kernel(const double* __restrict__ M, long long ld, int j0, int jb,
                  const double* __restrict__ dinv, double* __restrict__ x, int transposed) {
-    extern __shared__ double S[];
+    extern __shared__ __align__(16) double S[];
     double* xs = S + SV_NB * SV_P;
-    const int tid = threadIdx.x;
-    const double* Lb = M + j0 + (long long)j0 * ld;
-#pragma unroll 8
-    for (int idx = tid; idx < jb * jb; idx += 256) {
-        const int cc = idx / jb, r = idx - cc * jb;
-        if (r > cc) S[r + cc * SV_P] = Lb[r + (long long)cc * ld];
+    uint64_t* bar = reinterpret_cast<uint64_t*>(xs + SV_NB);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int jbp = (jb + 1) & ~1;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        uint32_t total = 0;
+        for (int cc = 0; cc < jb; ++cc) total += (uint32_t)(jbp - (cc & ~1)) * 8u;
+        mbar_expect_tx(bar, total);
     }
-    double v = 0.0, di = 0.0;
+    __syncthreads();
+    if (tid < jb) {
+        const int r0 = tid & ~1;
+        bulk_load_1d(S + r0 + tid * SV_P, M + (j0 + r0) + (long long)(j0 + tid) * ld,
+                     (uint32_t)(jbp - r0) * 8u, bar);
+    }
+    double v = 0.0, di = 1.0;
     if (tid < jb) {
         v = x[j0 + tid];
         di = dinv[j0 + tid];
     }
-    __syncthreads();
+    mbar_wait(bar, 0);
     if (!transposed) {
-        for (int cc = 0; cc < jb; ++cc) {
-            if (tid == cc) xs[cc] = v = v * di;
+        for (int sb = 0; sb < SV_NB / 32; ++sb) {
+            const int base = 32 * sb;
+            if (base >= jb) break;
+            if (warp == sb) {
+#pragma unroll 8
+                for (int cc = 0; cc < 32; ++cc) {
+                    const double xc = __shfl_sync(0xffffffffu, v * di, cc);
+                    if (lane == cc) v = xc;
+                    else if (lane > cc) v = fma(-S[(base + lane) + (base + cc) * SV_P], xc, v);
+                }
+                xs[base + lane] = v;
+            }
             __syncthreads();
-            if (tid > cc && tid < jb) v = fma(-S[tid + cc * SV_P], xs[cc], v);
+            if (tid >= base + 32) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int cc = 0; cc < 32; ++cc) acc = fma(S[tid + (base + cc) * SV_P], xs[base + cc], acc);
+                v -= acc;
+            }
         }
     } else {
-        for (int cc = jb - 1; cc >= 0; --cc) {
-            if (tid == cc) xs[cc] = v = v * di;
+        for (int sb = SV_NB / 32 - 1; sb >= 0; --sb) {
+            const int base = 32 * sb;
+            if (base >= jb) continue;
+            if (warp == sb) {
+#pragma unroll 8
+                for (int cc = 31; cc >= 0; --cc) {
+                    const double xc = __shfl_sync(0xffffffffu, v * di, cc);
+                    if (lane == cc) v = xc;
+                    else if (lane < cc && base + cc < jb)
+                        v = fma(-S[(base + cc) + (base + lane) * SV_P], xc, v);
+                }
+                xs[base + lane] = v;
+            }
             __syncthreads();
-            if (tid < cc) v = fma(-S[cc + tid * SV_P], xs[cc], v);
+            if (tid < base) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int cc = 0; cc < 32; ++cc)
+                    if (base + cc < jb) acc = fma(S[(base + cc) + tid * SV_P], xs[base + cc], acc);
+                v -= acc;
+            }
         }
     }
     if (tid < jb) x[j0 + tid] = v;
@@ -110,7 +155,7 @@ int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
     // L y = b
     for (int j0 = 0; j0 < m; j0 += SV_NB) {
         const int jb = (m - j0 < SV_NB) ? m - j0 : SV_NB;
-        trsv_diag_kernel<<<1, 256, SV_SMEM, c->stream>>>(L->d_M, ld, j0, jb, L->d_dinv, d_x, 0);
+        trsv_diag_kernel<<<1, SV_NB, SV_SMEM, c->stream>>>(L->d_M, ld, j0, jb, L->d_dinv, d_x, 0);
         NES_CHECK_LAUNCH(c);
         const int r0 = j0 + jb;
         if (r0 < m) {
@@ -124,7 +169,7 @@ int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
     for (int k = nblk - 1; k >= 0; --k) {
         const int j0 = k * SV_NB;
         const int jb = (m - j0 < SV_NB) ? m - j0 : SV_NB;
-        trsv_diag_kernel<<<1, 256, SV_SMEM, c->stream>>>(L->d_M, ld, j0, jb, L->d_dinv, d_x, 1);
+        trsv_diag_kernel<<<1, SV_NB, SV_SMEM, c->stream>>>(L->d_M, ld, j0, jb, L->d_dinv, d_x, 1);
         NES_CHECK_LAUNCH(c);
         if (j0 > 0) {
             trsv_update_bwd_kernel<<<(j0 + 7) / 8, 256, 0, c->stream>>>(L->d_M, ld, j0, jb, d_x);

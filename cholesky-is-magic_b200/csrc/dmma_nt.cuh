@@ -56,6 +56,12 @@ struct NtArgs {
     int same_operand;     // X == Y and rowA0 == rowB0: diagonal tiles load one operand tile
     int ntiles;
     int tiles_n;
+    // tail balancing: the last `split_r` tiles (the partial wave of the static round-robin) are cut
+    // into `split_s` k-ranges each; partial tiles go to split_ws and the last CTA to arrive sums them
+    // in k-range order (fixed order => bitwise reproducible, no floating-point atomics).
+    int split_r, split_s;
+    double* split_ws;     // split_r * split_s * 128*128 doubles
+    int* split_counters;  // split_r ints, zero on entry, reset to zero by the last arriver
 };
 
 __device__ __forceinline__ void nt_tile_coords(const NtArgs& p, int t, int& bi, int& bj) {
@@ -71,13 +77,33 @@ __device__ __forceinline__ void nt_tile_coords(const NtArgs& p, int t, int& bi, 
     }
 }
 
-// Producer state: walks this CTA's (tile, k-chunk) sequence one chunk ahead of the consumers.
-struct NtProducer {
-    int t;         // current tile (linear index), >= ntiles when exhausted
-    int kc;        // next k-chunk within the tile
-    int bi, bj;    // tile coordinates
-    uint32_t it;   // chunks issued so far (stage = it % STAGES)
+// One unit of work for a CTA: a tile and a range of k-chunks of it.
+struct NtWork {
+    int tile, bi, bj;
+    int kc_begin, kc_end;
+    int split;  // -1: whole tile, else k-range index of a split tail tile
 };
+
+// Items 0..nfull-1 are whole tiles, nfull.. are (tail tile, k-range) pairs; CTA b takes b, b+G, ...
+__device__ __forceinline__ bool nt_get_work(const NtArgs& p, int kchunks, int item, NtWork& w) {
+    const int nfull = p.ntiles - p.split_r;
+    if (item < nfull) {
+        w.tile = item;
+        w.kc_begin = 0;
+        w.kc_end = kchunks;
+        w.split = -1;
+    } else {
+        const int q = item - nfull;
+        if (q >= p.split_r * p.split_s) return false;
+        w.tile = nfull + q / p.split_s;
+        w.split = q - (q / p.split_s) * p.split_s;
+        const int per = (kchunks + p.split_s - 1) / p.split_s;
+        w.kc_begin = min(kchunks, w.split * per);
+        w.kc_end = min(kchunks, w.kc_begin + per);
+    }
+    nt_tile_coords(p, w.tile, w.bi, w.bj);
+    return true;
+}
 
 template <bool kHasScale>
 __global__ void __launch_bounds__(NT_THREADS, 1)
@@ -88,6 +114,7 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NT_STAGES * NT_STAGE_BYTES);
     uint64_t* empty = full + NT_STAGES;
+    __shared__ int s_last;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -108,31 +135,40 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 
     // The TMA producer is folded into thread 0: it refills the stage released one chunk ago, so its
     // empty-barrier wait is normally already satisfied (prefetch distance STAGES-1 chunks).
-    NtProducer pr;
-    pr.t = blockIdx.x;
-    pr.kc = 0;
-    pr.it = 0;
-    pr.bi = pr.bj = 0;
-    if (is_producer && pr.t < p.ntiles) nt_tile_coords(p, pr.t, pr.bi, pr.bj);
+    NtWork pw;            // producer's current work item
+    int p_item = blockIdx.x;
+    int p_kc = 0;
+    uint32_t p_it = 0;
+    bool p_valid = false;
+    if (is_producer) {
+        p_valid = nt_get_work(p, kchunks, p_item, pw);
+        while (p_valid && pw.kc_begin >= pw.kc_end) {  // empty k-range (never for whole tiles)
+            p_item += gridDim.x;
+            p_valid = nt_get_work(p, kchunks, p_item, pw);
+        }
+        if (p_valid) p_kc = pw.kc_begin;
+    }
     auto produce = [&]() {
-        if (pr.t >= p.ntiles) return;
-        const int s = pr.it % NT_STAGES;
-        const uint32_t ph = (pr.it / NT_STAGES) & 1;
+        if (!p_valid) return;
+        const int s = p_it % NT_STAGES;
+        const uint32_t ph = (p_it / NT_STAGES) & 1;
         mbar_wait(&empty[s], ph ^ 1);
-        const bool diag = p.same_operand && (pr.bi == pr.bj);
+        const bool diag = p.same_operand && (pw.bi == pw.bj);
         const uint32_t bytes =
             (diag ? NT_TILE_BYTES : 2 * NT_TILE_BYTES) + (kHasScale ? NT_BK * 8 : 0);
         uint8_t* st = smem + s * NT_STAGE_BYTES;
         mbar_expect_tx(&full[s], bytes);
-        const int kk = p.k0 + pr.kc * NT_BK;
-        tma_load_2d(st, &mapX, p.rowA0 + pr.bi * NT_BM, kk, &full[s]);
-        if (!diag) tma_load_2d(st + NT_TILE_BYTES, &mapY, p.rowB0 + pr.bj * NT_BN, kk, &full[s]);
+        const int kk = p.k0 + p_kc * NT_BK;
+        tma_load_2d(st, &mapX, p.rowA0 + pw.bi * NT_BM, kk, &full[s]);
+        if (!diag) tma_load_2d(st + NT_TILE_BYTES, &mapY, p.rowB0 + pw.bj * NT_BN, kk, &full[s]);
         if (kHasScale) bulk_load_1d(st + 2 * NT_TILE_BYTES, p.scale + kk, NT_BK * 8, &full[s]);
-        ++pr.it;
-        if (++pr.kc == kchunks) {
-            pr.kc = 0;
-            pr.t += gridDim.x;
-            if (pr.t < p.ntiles) nt_tile_coords(p, pr.t, pr.bi, pr.bj);
+        ++p_it;
+        if (++p_kc >= pw.kc_end) {
+            do {
+                p_item += gridDim.x;
+                p_valid = nt_get_work(p, kchunks, p_item, pw);
+            } while (p_valid && pw.kc_begin >= pw.kc_end);
+            if (p_valid) p_kc = pw.kc_begin;
         }
     };
     if (is_producer) {
@@ -148,10 +184,28 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     const int b_off = t4 * NT_PITCH + wn * 32 + g;
 
     uint32_t it = 0;
-    for (int t = blockIdx.x; t < p.ntiles; t += gridDim.x) {
-        int bi, bj;
-        nt_tile_coords(p, t, bi, bj);
+    NtWork w;
+    for (int item = blockIdx.x; nt_get_work(p, kchunks, item, w); item += gridDim.x) {
+        const int bi = w.bi, bj = w.bj;
         const bool diag = p.same_operand && (bi == bj);
+        const int row_base = bi * NT_BM + wm * 64 + g;
+        const int col_base = bj * NT_BN + wn * 32 + 2 * t4;
+
+        // warm L2 with the C tile while the mainloop runs (beta path reads it in the epilogue)
+        if (p.beta != 0.0 && g == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int col = col_base + j * 8 + c;
+                    if (col < p.N) {
+                        const double* cp = p.C + (long long)col * p.ldc;
+#pragma unroll
+                        for (int i = 0; i < 8; i += 2)
+                            if (row_base + i * 8 < p.M) prefetch_l2(cp + row_base + i * 8);
+                    }
+                }
+        }
 
         double acc[8][4][2];
 #pragma unroll
@@ -159,7 +213,7 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
 
-        for (int kc = 0; kc < kchunks; ++kc, ++it) {
+        for (int kc = w.kc_begin; kc < w.kc_end; ++kc, ++it) {
             if (is_producer) produce();
             __syncwarp();
             const int s = it % NT_STAGES;
@@ -191,11 +245,58 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
             if (lane == 0) mbar_arrive(&empty[s]);
         }
 
+        if (w.split >= 0) {
+            // ---- split tail tile: park the partial tile, last arriver reduces in k-range order ----
+            const int slot = w.tile - (p.ntiles - p.split_r);
+            double* ws = p.split_ws + ((size_t)slot * p.split_s + w.split) * (NT_BM * NT_BN);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c)
+                        __stcg(ws + ((i * 4 + j) * 2 + c) * NT_THREADS + threadIdx.x, acc[i][j][c]);
+            __threadfence();
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                const int old = atomicAdd(p.split_counters + slot, 1);
+                s_last = (old == p.split_s - 1);
+                if (s_last) p.split_counters[slot] = 0;
+            }
+            __syncthreads();
+            if (!s_last) continue;
+            __threadfence();
+            const double* base = p.split_ws + (size_t)slot * p.split_s * (NT_BM * NT_BN);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < 2; ++c) {
+                        double sum = 0.0;
+                        const double* q = base + ((i * 4 + j) * 2 + c) * NT_THREADS + threadIdx.x;
+                        for (int sp = 0; sp < p.split_s; ++sp) sum += __ldcg(q + (size_t)sp * (NT_BM * NT_BN));
+                        acc[i][j][c] = sum;
+                    }
+        }
+
         // epilogue: registers -> global (column-major).  Lane holds rows g (+8i), cols 2*t4, 2*t4+1.
-        const int row_base = bi * NT_BM + wm * 64 + g;
-        const int col_base = bj * NT_BN + wn * 32 + 2 * t4;
+        // The beta path loads a whole column pair (16 values) before storing, so the loads overlap.
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
+            double old[2][8];
+            if (p.beta != 0.0) {
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const int col = col_base + j * 8 + c;
+                    const double* cp = p.C + (long long)col * p.ldc;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = row_base + i * 8;
+                        old[c][i] = (col < p.N && row < p.M) ? __ldcg(cp + row) : 0.0;
+                    }
+                }
+            }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 const int col = col_base + j * 8 + c;
@@ -206,7 +307,7 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                         const int row = row_base + i * 8;
                         if (row < p.M) {
                             double v = p.alpha * acc[i][j][c];
-                            if (p.beta != 0.0) v += p.beta * cp[row];
+                            if (p.beta != 0.0) v = fma(p.beta, old[c][i], v);
                             cp[row] = v;
                         }
                     }
@@ -241,12 +342,12 @@ inline PFN_encodeTiled get_encode_tiled() {
 // Tensor map over a column-major rows x cols matrix of doubles (ld even, base 16B aligned) with
 // the 132 x 16 operand box of dmma_nt_kernel.  Returns 0 on success.
 inline int make_operand_map(CUtensorMap* map, const double* base, long long rows, long long cols,
-                            long long ld) {
+                            long long ld, int box_rows = NT_PITCH, int box_cols = NT_BK) {
     PFN_encodeTiled enc = get_encode_tiled();
     if (!enc) return -1;
     cuuint64_t dims[2] = {static_cast<cuuint64_t>(rows), static_cast<cuuint64_t>(cols)};
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 8};
-    cuuint32_t box[2] = {NT_PITCH, NT_BK};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_cols)};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
@@ -267,6 +368,20 @@ inline cudaError_t nt_configure() {
     return cudaSuccess;
 }
 
+// Tail-balancing plan for a launch with `ntiles` equal-cost tiles of `kchunks` k-chunks on `grid`
+// CTAs: returns the number of tail tiles to split (0 = none) and the k-ranges per tile.
+inline void nt_plan_split(int ntiles, int kchunks, int grid, int* split_r, int* split_s) {
+    *split_r = *split_s = 0;
+    if (ntiles <= grid) return;
+    const int r = ntiles % grid;
+    if (r == 0) return;
+    int s = grid / r;
+    if (s > kchunks / 8) s = kchunks / 8;  // keep every k-range at least 8 chunks long
+    if (s < 2) return;
+    *split_r = r;
+    *split_s = s;
+}
+
 // Launch on `stream` with at most `max_ctas` persistent CTAs (normally the SM count).
 inline cudaError_t nt_launch(const CUtensorMap& mapX, const CUtensorMap& mapY, NtArgs a, int max_ctas,
                              cudaStream_t stream) {
@@ -278,6 +393,12 @@ inline cudaError_t nt_launch(const CUtensorMap& mapX, const CUtensorMap& mapY, N
     a.tiles_n = tn;
     a.ntiles = a.lower ? tm * (tm + 1) / 2 : tm * tn;
     const int grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
+    if (a.split_ws == nullptr || a.split_counters == nullptr) a.split_r = a.split_s = 0;
+    if (a.split_r > 0) {
+        // caller proposes; validate against this grid
+        const int r = a.ntiles % grid;
+        if (r != a.split_r || a.split_s < 2 || a.split_r * a.split_s > grid) a.split_r = a.split_s = 0;
+    }
     if (a.scale)
         dmma_nt_kernel<true><<<grid, NT_THREADS, NT_SMEM_BYTES, stream>>>(mapX, mapY, a);
     else

@@ -391,7 +391,7 @@ int nes_kkt_newton(nes_matrix* A, nes_factor* L, int filters, const double* l, c
     if (!A || !l || !u || !w || !z || !e || !f || !g || !h || !dw || !dx || !dy || !dz)
         return fail(c, NES_ERR_INVALID, "nes_kkt_newton: null argument");
     const size_t n = A->base->n, m = A->base->m, pn = pad2(n), pm = pad2(m);
-    double* ws = ensure_ws(c, WS_DRIVER, (19 * pn + 2 * pm) * sizeof(double));
+    double* ws = ensure_ws(c, WS_DRIVER, (21 * pn + 2 * pm) * sizeof(double));
     if (!ws) return c->status;
     double* p = ws;
     auto take = [&](size_t len) {
@@ -415,16 +415,18 @@ int nes_kkt_newton(nes_matrix* A, nes_factor* L, int filters, const double* l, c
     NES_CUDA(c, cudaStreamSynchronize(c->stream));
 
     // solve-delta-y works on a scaled copy of A (cholmod_copy_sparse + scale-sparse!,
-    // sparse-newton-solve.lisp:121-126); analysis per call unless the caller recycles a factor
-    nes_matrix* As = nes_copy_matrix(A, c);
-    if (!As) return c->status;
+    // sparse-newton-solve.lisp:121-126).  The copy is a view: shared values, its own column scale
+    // carved out of the workspace (no allocation per call).  Analysis per call unless the caller
+    // recycles a factor.
+    nes_matrix view;
+    view.base = A->base;
+    view.d_scale = take(pn);
+    view.d_theta = take(pn);
+    nes_matrix* As = &view;
     nes_factor* Lown = nullptr;
     if (!L) {
         Lown = nes_analyze(As, c);
-        if (!Lown) {
-            nes_free_matrix(&As, c);
-            return c->status;
-        }
+        if (!Lown) return c->status;
         L = Lown;
     }
     int rc = kkt_newton_dev(c, As, L, filters, kv, nullptr, nullptr);
@@ -437,7 +439,6 @@ int nes_kkt_newton(nes_matrix* A, nes_factor* L, int filters, const double* l, c
             rc = fail(c, NES_ERR_CUDA, "nes_kkt_newton: copy back failed");
     }
     if (Lown) nes_free_factor(&Lown, c);
-    nes_free_matrix(&As, c);
     if (rc > 0) c->status = rc;
     return rc;
 }

@@ -243,6 +243,8 @@ int nes_free_work(nes_ctx* c) {
         c->d_ws[i] = nullptr;
         c->ws_bytes[i] = 0;
     }
+    if (c->d_split_counters) dev_free(c, c->d_split_counters);
+    c->d_split_counters = nullptr;
     if (c->h_pinned) pinned_free(c, c->h_pinned);
     c->h_pinned = nullptr;
     c->pinned_bytes = 0;
@@ -256,6 +258,9 @@ int nes_finish(nes_ctx* c) {
     collect_timing(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);
     c->event_pool.clear();
+    if (c->mark_a) cudaEventDestroy(c->mark_a);
+    if (c->mark_b) cudaEventDestroy(c->mark_b);
+    c->mark_a = c->mark_b = nullptr;
     if (c->stream) cudaStreamDestroy(c->stream);
     c->stream = nullptr;
     c->started = 0;
@@ -327,6 +332,28 @@ int nes_timing_get(nes_ctx* c, int stage, double* ms, long long* count) {
 }
 
 long long nes_get_launch_count(const nes_ctx* c) { return c ? c->launches : 0; }
+
+int nes_mark_begin(nes_ctx* c) {
+    NES_ENTER(c);
+    if (!c->mark_a) {
+        NES_CUDA(c, cudaEventCreate(&c->mark_a));
+        NES_CUDA(c, cudaEventCreate(&c->mark_b));
+    }
+    NES_CUDA(c, cudaStreamSynchronize(c->stream));
+    NES_CUDA(c, cudaEventRecord(c->mark_a, c->stream));
+    return 0;
+}
+
+int nes_mark_end(nes_ctx* c, double* ms) {
+    NES_ENTER(c);
+    if (!c->mark_a || !ms) return fail(c, NES_ERR_INVALID, "nes_mark_end without nes_mark_begin");
+    NES_CUDA(c, cudaEventRecord(c->mark_b, c->stream));
+    NES_CUDA(c, cudaEventSynchronize(c->mark_b));
+    float f = 0.f;
+    NES_CUDA(c, cudaEventElapsedTime(&f, c->mark_a, c->mark_b));
+    *ms = f;
+    return 0;
+}
 
 int nes_synchronize(nes_ctx* c) {
     if (!c || !c->started) return NES_ERR_NO_DEVICE;

@@ -42,9 +42,10 @@ struct nes_ctx {
 
     // workspaces owned by the context ("Common workspace", released by nes_free_work / nes_finish).
     // One slot per internal user so nested stages never alias each other's scratch.
-    static constexpr int kNumWs = 4;
-    double* d_ws[kNumWs] = {nullptr, nullptr, nullptr, nullptr};
-    size_t ws_bytes[kNumWs] = {0, 0, 0, 0};
+    static constexpr int kNumWs = 5;
+    double* d_ws[kNumWs] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    size_t ws_bytes[kNumWs] = {0, 0, 0, 0, 0};
+    int* d_split_counters = nullptr;  // tail-split arrival counters of dmma_nt (zero between launches)
     double* h_pinned = nullptr;  // small pinned staging buffer for scalar read-backs
     size_t pinned_bytes = 0;
 
@@ -56,6 +57,7 @@ struct nes_ctx {
     };
     std::vector<Interval> intervals;
     std::vector<cudaEvent_t> event_pool;
+    cudaEvent_t mark_a = nullptr, mark_b = nullptr;
     double stage_ms[NES_NUM_STAGES] = {0};
     long long stage_count[NES_NUM_STAGES] = {0};
 };
@@ -103,7 +105,7 @@ void* dev_alloc(nes_ctx* c, size_t bytes);  // nullptr on failure (status set)
 void dev_free(nes_ctx* c, void* p);
 void* pinned_alloc(nes_ctx* c, size_t bytes);
 void pinned_free(nes_ctx* c, void* p);
-enum { WS_API = 0, WS_MATVEC = 1, WS_REDUCE = 2, WS_DRIVER = 3 };
+enum { WS_API = 0, WS_MATVEC = 1, WS_REDUCE = 2, WS_DRIVER = 3, WS_SPLIT = 4 };
 // grow-only device workspace slot; returns nullptr on failure (status set)
 double* ensure_ws(nes_ctx* c, int slot, size_t bytes);
 int ensure_pinned(nes_ctx* c, size_t bytes);
@@ -157,7 +159,8 @@ struct nes_factor {
     double* d_dinv = nullptr;  // 1/L_jj
     double* d_rhs = nullptr;   // solve workspace (solve2's Y/E)
     int* d_info = nullptr;     // {status, minor}
-    CUtensorMap mapM;
+    CUtensorMap mapM;    // 132 x 16 operand boxes (dmma_nt)
+    CUtensorMap mapBlk;  // 128 x 128 block boxes (diagonal-block kernels)
     int factorized = 0;
     nes_matrix* analyzed_for = nullptr;
 };

@@ -65,6 +65,19 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, i
         : "memory");
 }
 
+// 2D tiled TMA store: shared -> global (bulk async group).  Writes by ordinary threads must be
+// published to the async proxy first: fence_proxy_async() by the writers, then a barrier.
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, int c0, int c1, const void* src) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1), "r"(smem_u32(src))
+                 : "memory");
+}
+
+__device__ __forceinline__ void tma_store_commit_and_wait() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
 // 1D bulk copy global -> shared (bytes multiple of 16, both sides 16B aligned).
 __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_t bytes,
                                              uint64_t* bar) {

@@ -100,6 +100,8 @@ def _prototypes(lib):
     fn("nes_timing_reset", C.c_int, _vp)
     fn("nes_timing_get", C.c_int, _vp, C.c_int, _dp, C.POINTER(C.c_longlong))
     fn("nes_get_launch_count", C.c_longlong, _vp)
+    fn("nes_mark_begin", C.c_int, _vp)
+    fn("nes_mark_end", C.c_int, _vp, _dp)
 
 
 _lib = None
@@ -198,6 +200,14 @@ class Common:
             self.lib.nes_timing_get(self.ptr, i, C.byref(ms), C.byref(cnt))
             out[name] = (ms.value, cnt.value)
         return out
+
+    def mark_begin(self):
+        self.check(self.lib.nes_mark_begin(self.ptr), "nes_mark_begin")
+
+    def mark_end(self):
+        ms = C.c_double(0)
+        self.check(self.lib.nes_mark_end(self.ptr, C.byref(ms)), "nes_mark_end")
+        return ms.value
 
     @property
     def launches(self):

@@ -187,6 +187,10 @@ int nes_timing_reset(nes_ctx* c);
 /* accumulated milliseconds and number of timed intervals for a stage since the last reset */
 int nes_timing_get(nes_ctx* c, int stage, double* ms, long long* count);
 long long nes_get_launch_count(const nes_ctx* c);     /* kernels launched by this context */
+/* whole-region device timing: nes_mark_begin records a CUDA event on the library's stream,
+ * nes_mark_end records a second one, waits for it and returns the elapsed milliseconds. */
+int nes_mark_begin(nes_ctx* c);
+int nes_mark_end(nes_ctx* c, double* ms);
 int nes_synchronize(nes_ctx* c);
 
 #if defined(__GNUC__)
