@@ -26,9 +26,10 @@ constexpr int CH_DIAG_SMEM = (CH_NB * CH_P + CH_NB) * 8 + 128 + 16;
 __global__ void __launch_bounds__(256)
 potrf_diag_kernel(const __grid_constant__ CUtensorMap mapBlk, int j0, int jb,
                   double* __restrict__ dinv_out, double dbound, int* __restrict__ info) {
-    extern __shared__ uint8_t potrf_smem_raw[];
-    double* S = reinterpret_cast<double*>(
-        (reinterpret_cast<uintptr_t>(potrf_smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+    // dynamic shared memory of a kernel without static __shared__ starts at the CTA window base,
+    // which satisfies the 128B alignment TMA needs; keeping S a plain shared pointer lets ptxas
+    // use 32-bit shared addressing in the hot loops.
+    extern __shared__ __align__(128) double S[];
     double* dinv = S + CH_NB * CH_P;
     uint64_t* bar = reinterpret_cast<uint64_t*>(dinv + CH_NB);
     const int tid = threadIdx.x;
@@ -65,11 +66,10 @@ potrf_diag_kernel(const __grid_constant__ CUtensorMap mapBlk, int j0, int jb,
                         }
                         d = 1.0;
                     }
-                    double ri = rsqrt(d);
-                    double sq = d * ri;
-                    sq = fma(0.5 * fma(-sq, sq, d), ri, sq);  // one Newton step: sqrt to <1 ulp
-                    ri = fma(fma(-sq, ri, 1.0), ri, ri);        // and its reciprocal
-                    a[cc] = (lane == cc) ? sq : a[cc] * ri;
+                    // rsqrt is the latency floor of the pivot chain (66 cycles on B200); it is good to
+                    // 1 ulp, so L_jj = d * rsqrt(d) is within 2 ulp of sqrt(d)
+                    const double ri = rsqrt(d);
+                    a[cc] = (lane == cc) ? d * ri : a[cc] * ri;
 #pragma unroll
                     for (int c2 = cc + 1; c2 < CH_W; ++c2) {
                         const double l = __shfl_sync(0xffffffffu, a[cc], c2);
@@ -107,7 +107,9 @@ potrf_diag_kernel(const __grid_constant__ CUtensorMap mapBlk, int j0, int jb,
                 if (cc < w) S[r + (c0 + cc) * CH_P] = x[cc];
         }
         __syncthreads();
-        // (3) trailing rank-w update of the lower triangle, 16x16 thread grid, interleaved 7x7 tiles
+        // (3) trailing rank-w update of the lower triangle, 16x16 thread grid, interleaved 7x7 tiles.
+        // Loads are unconditional: rows past T alias the top of the next column (finite, and the
+        // products land in accumulators that are never stored).
         {
             const int ti = tid & 15, tj = tid >> 4;
             double acc[7][7];
@@ -115,29 +117,51 @@ potrf_diag_kernel(const __grid_constant__ CUtensorMap mapBlk, int j0, int jb,
             for (int a_ = 0; a_ < 7; ++a_)
 #pragma unroll
                 for (int b_ = 0; b_ < 7; ++b_) acc[a_][b_] = 0.0;
-            for (int p = 0; p < w; ++p) {
-                const double* col = S + (c0 + p) * CH_P + base;
-                double xi[7], xj[7];
+            const double* colbase = S + c0 * CH_P + base;
+            const int na = (T + 15) >> 4;  // 16-row groups in the trailing block (uniform)
+            if (w == CH_W) {
+#pragma unroll 4
+                for (int p = 0; p < CH_W; ++p) {
+                    const double* col = colbase + p * CH_P;
+                    double xi[7], xj[7];
 #pragma unroll
-                for (int a_ = 0; a_ < 7; ++a_) {
-                    const int i = ti + 16 * a_, j = tj + 16 * a_;
-                    xi[a_] = (i < T) ? col[i] : 0.0;
-                    xj[a_] = (j < T) ? col[j] : 0.0;
+                    for (int a_ = 0; a_ < 7; ++a_) {
+                        if (a_ < na) {
+                            xi[a_] = col[ti + 16 * a_];
+                            xj[a_] = col[tj + 16 * a_];
+                        }
+                    }
+#pragma unroll
+                    for (int a_ = 0; a_ < 7; ++a_) {
+                        if (a_ < na) {
+#pragma unroll
+                            for (int b_ = 0; b_ <= a_; ++b_)
+                                acc[a_][b_] = fma(xi[a_], xj[b_], acc[a_][b_]);
+                        }
+                    }
                 }
+            } else {
+                for (int p = 0; p < w; ++p) {
+                    const double* col = colbase + p * CH_P;
 #pragma unroll
-                for (int a_ = 0; a_ < 7; ++a_) {
-                    if (16 * a_ < T) {
+                    for (int a_ = 0; a_ < 7; ++a_) {
+                        if (a_ < na) {
+                            const double xa = col[ti + 16 * a_];
 #pragma unroll
-                        for (int b_ = 0; b_ <= a_; ++b_) acc[a_][b_] = fma(xi[a_], xj[b_], acc[a_][b_]);
+                            for (int b_ = 0; b_ <= a_; ++b_)
+                                acc[a_][b_] = fma(xa, col[tj + 16 * b_], acc[a_][b_]);
+                        }
                     }
                 }
             }
 #pragma unroll
             for (int a_ = 0; a_ < 7; ++a_) {
+                if (a_ < na) {
 #pragma unroll
-                for (int b_ = 0; b_ <= a_; ++b_) {
-                    const int i = ti + 16 * a_, j = tj + 16 * b_;
-                    if (i < T && j <= i) S[(base + i) + (base + j) * CH_P] -= acc[a_][b_];
+                    for (int b_ = 0; b_ <= a_; ++b_) {
+                        const int i = ti + 16 * a_, j = tj + 16 * b_;
+                        if (i < T && j <= i) S[(base + i) + (base + j) * CH_P] -= acc[a_][b_];
+                    }
                 }
             }
         }
@@ -271,38 +295,59 @@ int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L) {
     return 0;
 }
 
+// One dmma_nt launch: C[r0.., c0..c0+ncols) -= X[r0.., k0..k0+K) X[c0..c0+ncols, k0..k0+K)^T
+static int chol_update(nes_ctx* c, nes_factor* L, int r0, int c0, int nrows, int ncols, int k0, int K,
+                       int lower) {
+    NtArgs a{};
+    a.C = L->d_M + r0 + (long long)c0 * (long long)L->ld;
+    a.ldc = (long long)L->ld;
+    a.M = nrows;
+    a.N = ncols;
+    a.rowA0 = r0;
+    a.rowB0 = c0;
+    a.k0 = k0;
+    a.K = K;
+    a.scale = nullptr;
+    a.alpha = -1.0;
+    a.beta = 1.0;
+    a.lower = lower;
+    a.same_operand = (r0 == c0) ? 1 : 0;
+    cudaError_t e = nt_launch(L->mapM, L->mapM, a, c->num_sms, c->stream);
+    ++c->launches;
+    if (e != cudaSuccess)
+        return fail(c, NES_ERR_CUDA, "Cholesky update launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// Two-level blocking: outer panels of NBO columns, factored left-looking in 128-column inner
+// panels (narrow DMMA update, diagonal block, TRSM), then one wide trailing update with K = NBO.
+// A larger K halves (NBO=256) or quarters (512) the number of passes over the trailing matrix and
+// the epilogue share of each tile.
 int dense_cholesky(nes_ctx* c, nes_factor* L) {
     StageTimer timer(c, NES_STAGE_FACTOR);
     NES_TRY(chol_configure(c));
     const int m = (int)L->m;
     const long long ld = (long long)L->ld;
+    const int NBO = (m > 12288) ? 512 : 256;
     NES_CUDA(c, cudaMemsetAsync(L->d_info, 0, 2 * sizeof(int), c->stream));
-    for (int j0 = 0; j0 < m; j0 += CH_NB) {
-        const int jb = (m - j0 < CH_NB) ? m - j0 : CH_NB;
-        potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->mapBlk, j0, jb, L->d_dinv, c->dbound,
-                                                              L->d_info);
-        NES_CHECK_LAUNCH(c);
-        const int rest = m - j0 - jb;
-        if (rest <= 0) break;
-        trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM, c->stream>>>(
-            L->d_M, ld, j0, m, L->d_dinv);
-        NES_CHECK_LAUNCH(c);
-        NtArgs a{};
-        a.C = L->d_M + (j0 + jb) + (long long)(j0 + jb) * ld;
-        a.ldc = ld;
-        a.M = a.N = rest;
-        a.rowA0 = a.rowB0 = j0 + jb;
-        a.k0 = j0;
-        a.K = jb;
-        a.scale = nullptr;
-        a.alpha = -1.0;
-        a.beta = 1.0;
-        a.lower = 1;
-        a.same_operand = 1;
-        cudaError_t e = nt_launch(L->mapM, L->mapM, a, c->num_sms, c->stream);
-        ++c->launches;
-        if (e != cudaSuccess)
-            return fail(c, NES_ERR_CUDA, "trailing update launch failed: %s", cudaGetErrorString(e));
+    for (int j0 = 0; j0 < m; j0 += NBO) {
+        const int jbo = (m - j0 < NBO) ? m - j0 : NBO;
+        for (int i0 = j0; i0 < j0 + jbo; i0 += CH_NB) {
+            const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
+            if (i0 > j0)  // bring block column i0 up to date with the inner panels already factored
+                NES_TRY(chol_update(c, L, i0, i0, m - i0, ib, j0, i0 - j0, 0));
+            potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->mapBlk, i0, ib, L->d_dinv,
+                                                                  c->dbound, L->d_info);
+            NES_CHECK_LAUNCH(c);
+            const int rest = m - i0 - ib;
+            if (rest > 0) {
+                trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM, c->stream>>>(
+                    L->d_M, ld, i0, m, L->d_dinv);
+                NES_CHECK_LAUNCH(c);
+            }
+        }
+        const int r0 = j0 + jbo;
+        if (r0 < m) NES_TRY(chol_update(c, L, r0, r0, m - r0, m - r0, j0, jbo, 1));
     }
     int info[2] = {0, 0};
     NES_TRY(download(c, info, L->d_info, sizeof(info)));
