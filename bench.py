@@ -127,14 +127,21 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--m", type=int, default=8192)
-    ap.add_argument("--n", type=int, default=16384)
+    ap.add_argument("--m", type=int, default=None, help="rows (default: 8192 on 1 GPU, 32768 on N>1)")
+    ap.add_argument("--n", type=int, default=None, help="columns (default 2m)")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work per baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-solve", action="store_true", help="skip the whole-LP-solve timing")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
+    world_env = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.m is None:
+        # N = 1: BASELINE config 2 (the configuration the metric is quoted on); N > 1: config 3, the
+        # one BASELINE.json distributes over 2/4/8 GPUs (strong scaling of one LP)
+        args.m = 8192 if max(world_env, args.gpus) == 1 else 32768
+    if args.n is None:
+        args.n = 2 * args.m
 
     if args.impl == "reference":
         reference_arm(args)
@@ -166,16 +173,25 @@ def main():
         torch.cuda.synchronize()
 
     with with_cholmod(device=local, timing=True) as c:
-        # ---- problem: generated on the device, b and c through the library's own GEMV ----------
-        A = nes.Matrix.generate_dense(c, m, n, args.seed + 1000 * rank)
-        xs, ys, zs = lpgen.aux_vectors(m, n, args.seed + 1000 * rank)
+        if world > 1:
+            # the NCCL unique id travels through torch.distributed (plumbing); the library owns the
+            # communicator it uses for the panel broadcasts
+            idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+            if rank == 0:
+                idt.copy_(torch.frombuffer(bytearray(nes.unique_id()), dtype=torch.uint8))
+            dist.broadcast(idt, 0)
+            c.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
+        # ---- problem: generated on the device (replicated on every rank), b and c through the
+        # library's own GEMV ----------
+        A = nes.Matrix.generate_dense(c, m, n, args.seed)
+        xs, ys, zs = lpgen.aux_vectors(m, n, args.seed)
         b = A.sdmult(xs)
         cvec = A.sdmult(ys, transpose=True) + zs
         A.free()
         from cholesky_is_magic_b200.standard_form import StandardForm
         sf = StandardForm(nvars=n, ncons=m, c=list(enumerate(cvec.tolist())), A=None, b=b,
                           l=np.zeros(n), u=np.full(n, np.inf), initial_vars=n)
-        st = pdas.make_pdas(sf, scale=True, generated_seed=args.seed + 1000 * rank)
+        st = pdas.make_pdas(sf, scale=True, generated_seed=args.seed)
         h = st.handle()
         import ctypes as C
         out9 = (C.c_double * 9)()
@@ -220,8 +236,7 @@ def main():
         outs = {k: torch.empty(n if k != "dy" else m, dtype=torch.float64).pin_memory()
                 for k in ("dw", "dx", "dy", "dz")}
         ptr = lambda t: C.cast(t.data_ptr(), nes._dp)
-        Ak = nes.Matrix.generate_dense(c, m, n, args.seed + 1000 * rank)
-        Ak.scale_rows_maxabs()
+        Ak = st.A()            # the state's resident (row-scaled) matrix
         Lk = nes.Factor(c, Ak)
 
         def kkt_call():
@@ -249,14 +264,13 @@ def main():
         barrier()
         stage_e2e = c.timing()
         Lk.free()
-        Ak.free()
 
         # ---- whole LP solve (second half of the BASELINE metric) --------------------------------
         solve_s, solve_iters = None, None
-        if not args.no_solve:
+        if not args.no_solve and world == 1 and m <= 8192:
             from cholesky_is_magic_b200.pdas import free_pdas_A
             free_pdas_A(st)
-            st2 = pdas.make_pdas(sf, scale=True, generated_seed=args.seed + 1000 * rank)
+            st2 = pdas.make_pdas(sf, scale=True, generated_seed=args.seed)
             st2.handle()
             c.synchronize()
             t0 = time.perf_counter()
@@ -272,12 +286,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total, ms_e2e = t.tolist()
     F = flops_step(m, n)
-    value = world * F * K / (ms_total * 1e-3) / 1e9
-    e2e_val = world * flops_kkt(m, n) * K / (ms_e2e * 1e-3) / 1e9
+    # one LP distributed over the ranks: the job's flops are F per step whatever N is
+    value = F * K / (ms_total * 1e-3) / 1e9
+    e2e_val = flops_kkt(m, n) * K / (ms_e2e * 1e-3) / 1e9
     form_ms, form_cnt = stage["form"]
     roof = None
     if form_cnt:
-        ach = (float(m) * m * n) / (form_ms / form_cnt * 1e-3) / 1e12
+        ach = (float(m) * m * n) / world / (form_ms / form_cnt * 1e-3) / 1e12  # this rank's share
         roof = {"bound": "tensor", "kernel": "dmma_nt_kernel<true> (fused scale+SYRK)",
                 "achieved": ach, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": ach / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
@@ -286,11 +301,15 @@ def main():
                 "step_frac_of_peak": value / world / 1e3 / FP64_DMMA_PEAK_TFLOPS}
     line = {
         "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": ms_total / K, "higher_is_better": True,
+        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"dense LP m={m} n={n} primal-dual affine scaling iteration (BASELINE config 2)",
-                   "parallelism": f"replicas x{world}" if world > 1 else "single GPU",
-                   "l2": "inputs larger than L2 (A 1.07 GB, M 0.54 GB vs 126 MB)"},
+        "config": {"workload": f"dense LP m={m} n={n} primal-dual affine scaling iteration "
+                               f"(BASELINE config {2 if m == 8192 else 3 if m == 32768 else 'custom'})",
+                   "parallelism": (f"M and L block-cyclic by {256 if m <= 12288 else 512}-column panels over "
+                                   f"{world} GPUs (1 x {world} grid), ncclBroadcast per panel; A and vectors replicated")
+                   if world > 1 else "single GPU",
+                   "l2": f"inputs larger than L2 (A {8e-9 * m * n:.2f} GB, M {8e-9 * m * m:.2f} GB vs 126 MB)"},
         "e2e": {"value": e2e_val, "unit": "GFLOP/s", "ms_per_step": ms_e2e / K,
                 "h2d_bytes_per_step": 8 * (7 * n + m), "d2h_bytes_per_step": 8 * (3 * n + m),
                 "call": "nes_kkt_newton (solve-kkt-newton) with pinned host vectors, A resident",

@@ -268,10 +268,15 @@ int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L) {
     a.beta = 0.0;
     a.lower = 1;
     a.same_operand = 1;
+    if (c->nranks > 1) {  // only the tiles this rank owns (block-cyclic outer block columns)
+        a.tile_list = L->d_tile_list;
+        a.ntiles = L->ntiles_owned;
+        a.lower = 0;
+    }
     // balance the partial last wave of the static tile round-robin (6% at m=8192 on 148 SMs)
     {
         const int tm = (a.M + NT_BM - 1) / NT_BM;
-        const int ntiles = tm * (tm + 1) / 2;
+        const int ntiles = (c->nranks > 1) ? L->ntiles_owned : tm * (tm + 1) / 2;
         const int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
         int sr = 0, ss = 0;
         nt_plan_split(ntiles, (a.K + NT_BK - 1) / NT_BK, grid, &sr, &ss);
@@ -323,15 +328,73 @@ static int chol_update(nes_ctx* c, nes_factor* L, int r0, int c0, int nrows, int
 // panels (narrow DMMA update, diagonal block, TRSM), then one wide trailing update with K = NBO.
 // A larger K halves (NBO=256) or quarters (512) the number of passes over the trailing matrix and
 // the epilogue share of each tile.
+__global__ void info_to_minor_kernel(int* info) {
+    // info = {status, minor}  ->  {status, status ? minor : INT_MAX} so MIN over ranks finds the first
+    if (threadIdx.x == 0 && info[0] == 0) info[1] = 0x7fffffff;
+}
+
 int dense_cholesky(nes_ctx* c, nes_factor* L) {
     StageTimer timer(c, NES_STAGE_FACTOR);
     NES_TRY(chol_configure(c));
     const int m = (int)L->m;
     const long long ld = (long long)L->ld;
-    const int NBO = (m > 12288) ? 512 : 256;
+    const int NBO = dense_outer_block(m);
+    const int P = c->nranks;
     NES_CUDA(c, cudaMemsetAsync(L->d_info, 0, 2 * sizeof(int), c->stream));
-    for (int j0 = 0; j0 < m; j0 += NBO) {
+    for (int j0 = 0, J = 0; j0 < m; j0 += NBO, ++J) {
         const int jbo = (m - j0 < NBO) ? m - j0 : NBO;
+        if (P > 1) {
+            // ---- distributed step: owner factors the panel, everyone receives it, everyone updates
+            // the block columns it owns.
+            const int owner = dist_owner(J, P);
+            const size_t rows = (size_t)(m - j0);
+            if (c->rank == owner) {
+                for (int i0 = j0; i0 < j0 + jbo; i0 += CH_NB) {
+                    const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
+                    if (i0 > j0) NES_TRY(chol_update(c, L, i0, i0, m - i0, ib, j0, i0 - j0, 0));
+                    potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->mapBlk, i0, ib, L->d_dinv,
+                                                                          c->dbound, L->d_info);
+                    NES_CHECK_LAUNCH(c);
+                    const int rest = m - i0 - ib;
+                    if (rest > 0) {
+                        trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM,
+                                            c->stream>>>(L->d_M, ld, i0, m, L->d_dinv);
+                        NES_CHECK_LAUNCH(c);
+                    }
+                }
+                NES_CUDA(c, cudaMemcpy2DAsync(L->d_stage, rows * 8, L->d_M + j0 + (long long)j0 * ld,
+                                              ld * 8, rows * 8, jbo, cudaMemcpyDeviceToDevice, c->stream));
+                NES_CUDA(c, cudaMemcpyAsync(L->d_stage + rows * jbo, L->d_dinv + j0, jbo * sizeof(double),
+                                            cudaMemcpyDeviceToDevice, c->stream));
+            }
+            NES_TRY(dist_broadcast(c, L->d_stage, rows * jbo + jbo, owner));
+            if (c->rank != owner) {
+                NES_CUDA(c, cudaMemcpy2DAsync(L->d_M + j0 + (long long)j0 * ld, ld * 8, L->d_stage,
+                                              rows * 8, rows * 8, jbo, cudaMemcpyDeviceToDevice, c->stream));
+                NES_CUDA(c, cudaMemcpyAsync(L->d_dinv + j0, L->d_stage + rows * jbo, jbo * sizeof(double),
+                                            cudaMemcpyDeviceToDevice, c->stream));
+            }
+            const int first = L->tile_first[J + 1];
+            if (first < L->ntiles_owned) {
+                NtArgs a{};
+                a.C = L->d_M;
+                a.ldc = ld;
+                a.M = a.N = m;
+                a.rowA0 = a.rowB0 = 0;
+                a.k0 = j0;
+                a.K = jbo;
+                a.alpha = -1.0;
+                a.beta = 1.0;
+                a.same_operand = 1;
+                a.tile_list = L->d_tile_list + first;
+                a.ntiles = L->ntiles_owned - first;
+                cudaError_t e = nt_launch(L->mapM, L->mapM, a, c->num_sms, c->stream);
+                ++c->launches;
+                if (e != cudaSuccess)
+                    return fail(c, NES_ERR_CUDA, "distributed update launch failed: %s", cudaGetErrorString(e));
+            }
+            continue;
+        }
         for (int i0 = j0; i0 < j0 + jbo; i0 += CH_NB) {
             const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
             if (i0 > j0)  // bring block column i0 up to date with the inner panels already factored
@@ -348,6 +411,12 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
         }
         const int r0 = j0 + jbo;
         if (r0 < m) NES_TRY(chol_update(c, L, r0, r0, m - r0, m - r0, j0, jbo, 1));
+    }
+    if (P > 1) {  // a failed pivot is only seen by the owner of its panel: agree on {status, first minor}
+        info_to_minor_kernel<<<1, 32, 0, c->stream>>>(L->d_info);
+        NES_CHECK_LAUNCH(c);
+        NES_TRY(dist_allreduce_int(c, L->d_info, 1, 1));
+        NES_TRY(dist_allreduce_int(c, L->d_info + 1, 1, 0));
     }
     int info[2] = {0, 0};
     NES_TRY(download(c, info, L->d_info, sizeof(info)));

@@ -62,15 +62,45 @@ struct NtArgs {
     int split_r, split_s;
     double* split_ws;     // split_r * split_s * 128*128 doubles
     int* split_counters;  // split_r ints, zero on entry, reset to zero by the last arriver
+    // explicit tile list (multi-GPU ownership): tile t is (tile_list[t].x, tile_list[t].y) in absolute
+    // 128-row / 128-column units of the region; overrides the lower/rectangular enumeration
+    const int2* tile_list;
 };
 
+// Tile order.  A wave of the persistent grid is ~148 consecutive tiles and only tiles that run at the
+// same time share operand rows through L2 (one 128-row block of A is 8*128*n bytes, far more than L2
+// holds for all blocks), so consecutive tiles should form a squarish patch: the lower triangle is cut
+// into bands of NT_BAND tile rows, each band walked column by column (a wave then touches about
+// NT_BAND + 148/NT_BAND row blocks instead of ~64).
+constexpr int NT_BAND = 12;
+
 __device__ __forceinline__ void nt_tile_coords(const NtArgs& p, int t, int& bi, int& bj) {
-    if (p.lower) {
-        int r = static_cast<int>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5);
-        while ((long long)(r + 1) * (r + 2) / 2 <= t) ++r;
-        while ((long long)r * (r + 1) / 2 > t) --r;
-        bi = r;
-        bj = t - static_cast<int>((long long)r * (r + 1) / 2);
+    if (p.tile_list) {
+        const int2 v = p.tile_list[t];
+        bi = v.x;
+        bj = v.y;
+    } else if (p.lower) {
+        // band r holds tile rows [r*H, r*H+h); tiles before band r: (rH)(rH+1)/2
+        const int H = NT_BAND;
+        int r = static_cast<int>((sqrt(8.0 * static_cast<double>(t) + 1.0) - 1.0) * 0.5) / H;
+        while ((long long)((r + 1) * H) * ((r + 1) * H + 1) / 2 <= t) ++r;
+        while ((long long)(r * H) * (r * H + 1) / 2 > t) --r;
+        const int r0 = r * H;
+        const int h = min(H, p.tiles_n - r0);
+        int q = t - static_cast<int>((long long)r0 * (r0 + 1) / 2);
+        if (q < r0 * h) {  // full-height columns left of the band's diagonal block
+            bj = q / h;
+            bi = r0 + q - bj * h;
+        } else {           // the h x h lower triangle on the diagonal, column by column
+            q -= r0 * h;
+            int cj = 0;
+            while (q >= h - cj) {
+                q -= h - cj;
+                ++cj;
+            }
+            bj = r0 + cj;
+            bi = bj + q;
+        }
     } else {
         bi = t / p.tiles_n;
         bj = t - bi * p.tiles_n;
@@ -391,7 +421,8 @@ inline cudaError_t nt_launch(const CUtensorMap& mapX, const CUtensorMap& mapY, N
     const int tm = (a.M + NT_BM - 1) / NT_BM;
     const int tn = (a.N + NT_BN - 1) / NT_BN;
     a.tiles_n = tn;
-    a.ntiles = a.lower ? tm * (tm + 1) / 2 : tm * tn;
+    if (!a.tile_list) a.ntiles = a.lower ? tm * (tm + 1) / 2 : tm * tn;
+    if (a.ntiles <= 0) return cudaSuccess;
     const int grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
     if (a.split_ws == nullptr || a.split_counters == nullptr) a.split_r = a.split_s = 0;
     if (a.split_r > 0) {

@@ -254,6 +254,7 @@ int nes_free_work(nes_ctx* c) {
 int nes_finish(nes_ctx* c) {
     if (!c) return 0;
     if (!c->started) return 1;
+    nes_comm_finalize(c);
     nes_free_work(c);
     collect_timing(c);
     for (auto e : c->event_pool) cudaEventDestroy(e);

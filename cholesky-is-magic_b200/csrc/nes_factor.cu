@@ -64,6 +64,19 @@ nes_factor* nes_analyze(nes_matrix* A, nes_ctx* c) {
         nes_free_factor(&L, c);
         return nullptr;
     }
+    if (c->nranks > 1) {
+        // distributed factorization: owned-tile list + packed-panel staging buffer
+        L->nbo = dense_outer_block((int)m);
+        std::vector<int2> tiles;
+        L->ntiles_owned = dist_plan_tiles((int)m, L->nbo, c->nranks, c->rank, tiles, L->tile_first);
+        L->d_tile_list = static_cast<int2*>(dev_alloc(c, (tiles.size() + 1) * sizeof(int2)));
+        L->d_stage = static_cast<double*>(dev_alloc(c, ((size_t)m * L->nbo + L->nbo + 16) * sizeof(double)));
+        if (!L->d_tile_list || !L->d_stage ||
+            upload(c, L->d_tile_list, tiles.data(), tiles.size() * sizeof(int2)) != 0) {
+            nes_free_factor(&L, c);
+            return nullptr;
+        }
+    }
     // the analytic counters the reference prints after cholmod_analyze (affine-scaling.lisp:273-279)
     const double dm = (double)m, dn = (double)n;
     c->anz = dm * (dm + 1) / 2;
@@ -109,6 +122,8 @@ static void nes_free_factor_impl(nes_factor* L, nes_ctx* c) {
     dev_free(c, L->d_dinv);
     dev_free(c, L->d_rhs);
     dev_free(c, L->d_info);
+    dev_free(c, L->d_tile_list);
+    dev_free(c, L->d_stage);
 }
 
 int nes_free_factor(nes_factor** L, nes_ctx* c) {

@@ -37,6 +37,10 @@ struct nes_ctx {
     char err[512] = {0};
     long long launches = 0;
 
+    // multi-GPU (one process per GPU; 1 x Q block-cyclic column distribution of M, see nes_dist.cu)
+    int nranks = 1, rank = 0;
+    void* nccl_comm = nullptr;
+
     // allocation ledger (device + pinned host), so frees can be accounted without sizes
     std::unordered_map<void*, size_t> ledger;
 
@@ -163,6 +167,13 @@ struct nes_factor {
     CUtensorMap mapBlk;  // 128 x 128 block boxes (diagonal-block kernels)
     int factorized = 0;
     nes_matrix* analyzed_for = nullptr;
+    // distributed factorization (nranks > 1): tiles of the lower triangle owned by this rank, ordered by
+    // outer block column; tile_first[J] = index of the first owned tile whose block column is > J
+    int nbo = 0;                 // distribution block = outer panel width
+    int2* d_tile_list = nullptr;
+    int ntiles_owned = 0;
+    std::vector<int> tile_first;
+    double* d_stage = nullptr;   // packed panel for ncclBroadcast (+ dinv tail)
 };
 
 namespace nes {
@@ -177,6 +188,13 @@ int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x);
 // K6: y <- alpha op(A diag(s)) x + beta y on device vectors (gemv.cu); handles dense and CSC
 int matvec(nes_ctx* c, const nes_matrix* A, int transpose, double alpha, const double* d_x,
            double beta, double* d_y);
+// multi-GPU pieces (nes_dist.cu)
+int dist_plan_tiles(int m, int nbo, int nranks, int rank, std::vector<int2>& tiles,
+                    std::vector<int>& tile_first);
+int dist_broadcast(nes_ctx* c, double* d_buf, size_t count, int root);
+int dist_allreduce_int(nes_ctx* c, int* d_buf, size_t count, int op_max_else_min);
+int dense_outer_block(int m);
+int dist_owner(int J, int nranks);
 // install a column scale that already lives on the device (nes_scale without the PCIe hop)
 int set_scale_dev(nes_ctx* c, nes_matrix* A, const double* d_s);
 // plain op(A) product ignoring the column scale

@@ -100,6 +100,12 @@ def _prototypes(lib):
     fn("nes_timing_reset", C.c_int, _vp)
     fn("nes_timing_get", C.c_int, _vp, C.c_int, _dp, C.POINTER(C.c_longlong))
     fn("nes_get_launch_count", C.c_longlong, _vp)
+    fn("nes_comm_unique_id", C.c_int, C.c_char_p)
+    fn("nes_comm_init", C.c_int, _vp, C.c_int, C.c_int, C.c_char_p)
+    fn("nes_comm_finalize", C.c_int, _vp)
+    fn("nes_comm_rank", C.c_int, _vp)
+    fn("nes_comm_nranks", C.c_int, _vp)
+    fn("nes_dist_plan", C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int)
     fn("nes_mark_begin", C.c_int, _vp)
     fn("nes_mark_end", C.c_int, _vp, _dp)
 
@@ -118,6 +124,27 @@ def load_library():
         _lib = C.CDLL(LIB_PATH)
         _prototypes(_lib)
     return _lib
+
+
+def unique_id() -> bytes:
+    """ncclGetUniqueId through the library (call on rank 0, ship the 128 bytes to the other ranks)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    if lib.nes_comm_unique_id(buf) != 0:
+        raise NesError("nes_comm_unique_id failed (libnccl.so.2 not loadable)")
+    return buf.raw
+
+
+def dist_plan(m, nranks, rank):
+    """Tiles of tril(M) owned by `rank` as an (ntiles, 2) int array (host-only, no GPU needed)."""
+    lib = load_library()
+    n = lib.nes_dist_plan(m, nranks, rank, None, None, 0)
+    if n < 0:
+        raise NesError("nes_dist_plan: bad arguments")
+    rows = np.empty(max(n, 1), dtype=np.int32)
+    cols = np.empty(max(n, 1), dtype=np.int32)
+    lib.nes_dist_plan(m, nranks, rank, rows.ctypes.data_as(_ip), cols.ctypes.data_as(_ip), n)
+    return np.stack([rows[:n], cols[:n]], axis=1)
 
 
 def vec(a):
@@ -200,6 +227,11 @@ class Common:
             self.lib.nes_timing_get(self.ptr, i, C.byref(ms), C.byref(cnt))
             out[name] = (ms.value, cnt.value)
         return out
+
+    def comm_init(self, nranks, rank, unique_id: bytes):
+        """Join the NCCL communicator of the job (rank 0's id from `unique_id()`)."""
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self.check(self.lib.nes_comm_init(self.ptr, nranks, rank, buf), "nes_comm_init")
 
     def mark_begin(self):
         self.check(self.lib.nes_mark_begin(self.ptr), "nes_mark_begin")

@@ -175,6 +175,22 @@ int nes_pdas_solve(nes_pdas* st, int max_iter, int* iters, double* obj, double* 
 int nes_pdas_get(nes_pdas* st, int which, double* out, nes_ctx* c);
 int nes_pdas_set(nes_pdas* st, int which, const double* in, nes_ctx* c);
 
+/* ---- multi-GPU: one process per GPU, NCCL over NVLink/NVSwitch --------------------------------
+ * The reference has no distributed code at all; these calls are additions.  M and L are distributed
+ * block-cyclically by outer block columns over the ranks (1 x Q grid); each finished panel is
+ * broadcast with ncclBroadcast, so after nes_factorize every rank holds the complete factor and the
+ * solves run replicated.  A and all vectors are replicated.  Rank 0 obtains a 128-byte unique id,
+ * the launcher (torch.distributed, MPI, ...) ships it to the other ranks, and every rank calls
+ * nes_comm_init before the first nes_analyze. */
+int nes_comm_unique_id(unsigned char* id128);
+int nes_comm_init(nes_ctx* c, int nranks, int rank, const unsigned char* id128);
+int nes_comm_finalize(nes_ctx* c);
+int nes_comm_rank(const nes_ctx* c);
+int nes_comm_nranks(const nes_ctx* c);
+/* host-only: the 128x128 tiles of tril(M) owned by `rank` (m rows, `nranks` ranks); returns the count
+ * and fills up to `cap` (tile row, tile column) pairs. */
+int nes_dist_plan(int m, int nranks, int rank, int* tile_rows, int* tile_cols, int cap);
+
 /* ---- instrumentation (bench.py / roofline): device time of the library's own stages ---------- */
 #define NES_STAGE_FORM 0      /* K1 fused scale+SYRK   */
 #define NES_STAGE_FACTOR 1    /* K2 Cholesky            */
