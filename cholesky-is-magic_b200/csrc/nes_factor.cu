@@ -10,6 +10,7 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L);       // sparse_ch
 int sparse_factorize(nes_ctx* c, nes_matrix* A, nes_factor* L);
 int sparse_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x);
 void sparse_free(nes_ctx* c, nes_factor* L);
+int sparse_factor_to_dense(nes_ctx* c, nes_factor* L, double* Lout, size_t ld, int* perm_out);
 
 int factorize_dev(nes_ctx* c, nes_matrix* A, nes_factor* L) {
     c->status = 0;  // the Lisp does cholmod_set_status 0 before every factorize (:418, :511, :541)
@@ -159,7 +160,7 @@ int nes_solve_dense(const double* B, size_t nrow, size_t ncol, const double* b, 
 int nes_factor_to_dense(nes_factor* L, double* Lout, size_t ld, int* perm, nes_ctx* c) {
     NES_ENTER(c);
     if (!L || !Lout || ld < L->m) return fail(c, NES_ERR_INVALID, "nes_factor_to_dense: bad argument");
-    if (!L->dense) return fail(c, NES_ERR_INVALID, "nes_factor_to_dense: sparse factor not supported yet");
+    if (!L->dense) return sparse_factor_to_dense(c, L, Lout, ld, perm);
     const size_t m = L->m;
     NES_CUDA(c, cudaMemcpy2DAsync(Lout, ld * sizeof(double), L->d_M, L->ld * sizeof(double),
                                   m * sizeof(double), m, cudaMemcpyDeviceToHost, c->stream));

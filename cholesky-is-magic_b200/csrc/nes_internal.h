@@ -155,8 +155,13 @@ struct nes_matrix {
     double* d_theta = nullptr;  // s^2 padded to a multiple of 16 (formation operand), or nullptr
 };
 
+namespace nes {
+struct SparseFactor;
+}
+
 struct nes_factor {
     bool dense = true;
+    nes::SparseFactor* sparse = nullptr;  // supernodal factor (sparse_chol.cu) when !dense
     size_t m = 0;
     size_t ld = 0;
     double* d_M = nullptr;     // m x m column-major: lower triangle holds M, then L in place
