@@ -733,3 +733,371 @@ int nes_pdas_set(nes_pdas* st, int which, const double* in, nes_ctx* c) {
 }
 
 }  // extern "C"
+
+// =================================================================================================
+// Primal affine scaling state (affine-scaling.lisp), device resident
+//   nes_affine_residual        residual :209-213 (+ c'x)
+//   nes_affine_repair          one-repair-iteration :226-243, cholesky-ls! :215-221
+//   nes_affine_direction       slack :137-148, centering-direction :150-163, project :98-116,
+//                              g = dg*slack, max-step :120-133 and the norms of :182-186
+//   nes_affine_apply           x <- x + step g (:205-206)
+//   nes_affine_one_iteration   one-iteration :245-263 + one-affine-scaling-iteration :165-207
+//   nes_affine_solve           affine-scaling :265-297 (symbolic analysis once, numeric per iteration)
+// =================================================================================================
+struct nes_affine {
+    nes_matrix* A = nullptr;
+    nes_factor* L = nullptr;
+    size_t n = 0, m = 0;
+    double* d_block = nullptr;
+    double *c, *l, *u, *x, *slack, *sc, *g;  // n
+    double *b, *r, *t;                       // m
+    double* partial;
+    double* scal;
+    int have_direction = 0;
+};
+
+namespace nes {
+
+// slack = min(cap, x-l, u-x); sc = slack * (-(centering ? centering-direction : c)); partial: min slack
+__global__ void affine_slack_kernel(size_t n, double cap, int centering, const double* __restrict__ x,
+                                    const double* __restrict__ lo, const double* __restrict__ hi,
+                                    const double* __restrict__ cvec, double* __restrict__ slack,
+                                    double* __restrict__ sc, double* __restrict__ partial) {
+    __shared__ double buf[32];
+    double mn = INFINITY;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const double xi = x[i], lb = lo[i], ub = hi[i];
+        const double sl = fmin(cap, fmin(xi - lb, ub - xi));
+        slack[i] = sl;
+        mn = fmin(mn, sl);
+        if (sc) {
+            double d = cvec[i];
+            if (centering) {
+                if (isinf(lb) && isinf(ub)) d = 0.0;
+                else if ((xi - lb) < (ub - xi)) d = fmin(1.0, ub - xi);
+                else d = fmax(-1.0, lb - xi);
+            }
+            sc[i] = sl * (-1.0 * d);
+        }
+    }
+    mn = block_reduce(mn, RED_MIN, buf);
+    if (threadIdx.x == 0) partial[blockIdx.x] = mn;
+}
+
+// g = dg*slack; partials: 0 max-step(l,x,u,g)  1 sum g^2  2 sum dg^2  3 sum g*c
+__global__ void affine_direction_kernel(size_t n, const double* __restrict__ dg,
+                                        const double* __restrict__ slack, const double* __restrict__ x,
+                                        const double* __restrict__ lo, const double* __restrict__ hi,
+                                        const double* __restrict__ cvec, double* __restrict__ g,
+                                        double* __restrict__ partial) {
+    __shared__ double buf[32];
+    double mn = INFINITY, sg = 0.0, sd = 0.0, sgc = 0.0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x) {
+        const double di = dg[i], gi = di * slack[i];
+        g[i] = gi;
+        sg = fma(gi, gi, sg);
+        sd = fma(di, di, sd);
+        sgc = fma(gi, cvec[i], sgc);
+        if (gi < 0.0) mn = fmin(mn, (lo[i] - x[i]) / gi);
+        else if (gi > 0.0) mn = fmin(mn, (hi[i] - x[i]) / gi);
+    }
+    double v = block_reduce(mn, RED_MIN, buf);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    v = block_reduce(sg, RED_SUM, buf);
+    if (threadIdx.x == 0) partial[gridDim.x + blockIdx.x] = v;
+    v = block_reduce(sd, RED_SUM, buf);
+    if (threadIdx.x == 0) partial[2 * gridDim.x + blockIdx.x] = v;
+    v = block_reduce(sgc, RED_SUM, buf);
+    if (threadIdx.x == 0) partial[3 * gridDim.x + blockIdx.x] = v;
+}
+
+// partials: 0 sum a.a (first na entries), 1 sum b.c (nb entries)
+__global__ void two_dots_kernel(size_t na, const double* __restrict__ a, size_t nb,
+                                const double* __restrict__ b, const double* __restrict__ cvec,
+                                double* __restrict__ partial) {
+    __shared__ double buf[32];
+    double s0 = 0.0, s1 = 0.0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < na; i += stride) s0 = fma(a[i], a[i], s0);
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < nb; i += stride) s1 = fma(b[i], cvec[i], s1);
+    double v = block_reduce(s0, RED_SUM, buf);
+    if (threadIdx.x == 0) partial[blockIdx.x] = v;
+    v = block_reduce(s1, RED_SUM, buf);
+    if (threadIdx.x == 0) partial[gridDim.x + blockIdx.x] = v;
+}
+
+__global__ void axpy_kernel(size_t n, double alpha, const double* __restrict__ v, double* __restrict__ x) {
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
+         i += (size_t)gridDim.x * blockDim.x)
+        x[i] = fma(alpha, v[i], x[i]);
+}
+
+}  // namespace nes
+
+extern "C" {
+
+nes_affine* nes_affine_create(nes_matrix* A, const double* cvec, const double* b, const double* l,
+                              const double* u, const double* x, nes_ctx* c) {
+    NES_ENTER_PTR(c);
+    if (!A || !cvec || !b || !l || !u || !x) {
+        fail(c, NES_ERR_INVALID, "nes_affine_create: null argument");
+        return nullptr;
+    }
+    nes_affine* st = new nes_affine();
+    st->n = A->base->n;
+    st->m = A->base->m;
+    const size_t n = st->n, m = st->m, pn = pad2(n), pm = pad2(m);
+    const int gmax = c->num_sms * 2;
+    const size_t total = 7 * pn + 3 * pm + (size_t)RED_MAXN * gmax + 16;
+    st->d_block = static_cast<double*>(dev_alloc(c, total * sizeof(double)));
+    if (!st->d_block) {
+        delete st;
+        return nullptr;
+    }
+    cudaMemsetAsync(st->d_block, 0, total * sizeof(double), c->stream);
+    double* p = st->d_block;
+    auto take = [&](size_t len) {
+        double* q = p;
+        p += len;
+        return q;
+    };
+    st->c = take(pn); st->l = take(pn); st->u = take(pn); st->x = take(pn); st->slack = take(pn);
+    st->sc = take(pn); st->g = take(pn);
+    st->b = take(pm); st->r = take(pm); st->t = take(pm);
+    st->partial = take((size_t)RED_MAXN * gmax);
+    st->scal = take(16);
+    const double* hn[4] = {cvec, l, u, x};
+    double* dn[4] = {st->c, st->l, st->u, st->x};
+    bool ok = true;
+    for (int k = 0; k < 4 && ok; ++k)
+        ok = cudaMemcpyAsync(dn[k], hn[k], n * sizeof(double), cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(st->b, b, m * sizeof(double), cudaMemcpyHostToDevice, c->stream) == cudaSuccess;
+    ok = ok && cudaStreamSynchronize(c->stream) == cudaSuccess;
+    if (ok) {
+        st->A = nes_copy_matrix(A, c);                 // affine-A-copy (:29-35): values shared
+        if (st->A) st->L = nes_analyze(st->A, c);      // cholmod_analyze once (:270-271)
+    }
+    if (!ok || !st->A || !st->L) {
+        if (!ok) fail(c, NES_ERR_CUDA, "nes_affine_create: upload failed");
+        nes_affine_free(&st, c);
+        return nullptr;
+    }
+    return st;
+}
+
+int nes_affine_free(nes_affine** st, nes_ctx* c) {
+    if (!c) return 0;
+    if (!st || !*st) return 1;
+    if (c->started) {
+        cudaSetDevice(c->device);
+        cudaStreamSynchronize(c->stream);
+    }
+    nes_free_factor(&(*st)->L, c);
+    nes_free_matrix(&(*st)->A, c);
+    dev_free(c, (*st)->d_block);
+    delete *st;
+    *st = nullptr;
+    return 1;
+}
+
+int nes_affine_residual(nes_affine* st, double out[2], nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st || !out) return fail(c, NES_ERR_INVALID, "nes_affine_residual: null argument");
+    NES_CUDA(c, cudaMemcpyAsync(st->r, st->b, st->m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    NES_TRY(matvec_unscaled(c, st->A->base, 0, -1.0, st->x, 1.0, st->r));
+    {
+        StageTimer t(c, NES_STAGE_VECTOR);
+        const int g = vec_grid(c, st->n > st->m ? st->n : st->m);
+        two_dots_kernel<<<g, RED_THREADS, 0, c->stream>>>(st->m, st->r, st->n, st->x, st->c, st->partial);
+        NES_CHECK_LAUNCH(c);
+        reduce_finish_kernel<<<1, 32, 0, c->stream>>>(st->partial, g, 2, pack_ops(RED_SUM, RED_SUM), st->scal);
+        NES_CHECK_LAUNCH(c);
+    }
+    NES_TRY(read_scalars(c, st->scal, out, 2));
+    out[0] = sqrt(out[0]);
+    return 0;
+}
+
+// shared by repair and direction: given the rhs in st->t, factorize (A diag slack)(A diag slack)' and
+// solve in place.  Returns 0 or NES_NOT_POSDEF.
+static int affine_normal_solve(nes_affine* st, nes_ctx* c) {
+    NES_TRY(set_scale_dev(c, st->A, st->slack));
+    const int rc = factorize_dev(c, st->A, st->L);
+    if (rc != 0) return rc;
+    return solve_dev(c, st->L, st->t);
+}
+
+int nes_affine_repair(nes_affine* st, double out[2], nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st || !out) return fail(c, NES_ERR_INVALID, "nes_affine_repair: null argument");
+    const size_t n = st->n;
+    const int gn = vec_grid(c, n);
+    {
+        StageTimer t(c, NES_STAGE_VECTOR);
+        affine_slack_kernel<<<gn, RED_THREADS, 0, c->stream>>>(n, sqrt(1e8), 0, st->x, st->l, st->u, st->c,
+                                                              st->slack, nullptr, st->partial);
+        NES_CHECK_LAUNCH(c);
+    }
+    // residual was computed by nes_affine_residual into st->r (the Lisp passes it in, :226)
+    NES_CUDA(c, cudaMemcpyAsync(st->t, st->r, st->m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
+    const int rc = affine_normal_solve(st, c);
+    if (rc != 0) return rc;
+    NES_TRY(matvec(c, st->A, 1, 1.0, st->t, 0.0, st->sc));  // dg = (A slack)' t
+    {
+        StageTimer t(c, NES_STAGE_VECTOR);
+        affine_direction_kernel<<<gn, RED_THREADS, 0, c->stream>>>(n, st->sc, st->slack, st->x, st->l,
+                                                                  st->u, st->c, st->g, st->partial);
+        NES_CHECK_LAUNCH(c);
+        reduce_finish_kernel<<<1, 32, 0, c->stream>>>(st->partial, gn, 4,
+                                                     pack_ops(RED_MIN, RED_SUM, RED_SUM, RED_SUM), st->scal);
+        NES_CHECK_LAUNCH(c);
+    }
+    double s4[4];
+    NES_TRY(read_scalars(c, st->scal, s4, 4));
+    const double gamma = 0.9;
+    const double step = gamma * fmin(s4[0], 1.0 / gamma);  // :238
+    out[0] = sqrt(s4[1]);
+    out[1] = step;
+    {
+        StageTimer t(c, NES_STAGE_VECTOR);
+        axpy_kernel<<<gn, RED_THREADS, 0, c->stream>>>(n, step, st->g, st->x);
+        NES_CHECK_LAUNCH(c);
+    }
+    st->have_direction = 0;
+    return 0;
+}
+
+int nes_affine_direction(nes_affine* st, int centering, double out[5], nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st || !out) return fail(c, NES_ERR_INVALID, "nes_affine_direction: null argument");
+    const size_t n = st->n;
+    const int gn = vec_grid(c, n);
+    {
+        StageTimer t(c, NES_STAGE_VECTOR);
+        affine_slack_kernel<<<gn, RED_THREADS, 0, c->stream>>>(n, 1e8, centering, st->x, st->l, st->u, st->c,
+                                                              st->slack, st->sc, st->partial);
+        NES_CHECK_LAUNCH(c);
+        reduce_finish_kernel<<<1, 32, 0, c->stream>>>(st->partial, gn, 1, pack_ops(RED_MIN), st->scal + 8);
+        NES_CHECK_LAUNCH(c);
+    }
+    // project (:98-116): AD = A diag(slack); y = (AD AD')^-1 AD sc; dg = sc - AD' y
+    NES_TRY(set_scale_dev(c, st->A, st->slack));
+    NES_TRY(matvec(c, st->A, 0, 1.0, st->sc, 0.0, st->t));
+    const int rc = affine_normal_solve(st, c);
+    if (rc != 0) return rc;
+    NES_TRY(matvec(c, st->A, 1, -1.0, st->t, 1.0, st->sc));
+    {
+        StageTimer t(c, NES_STAGE_VECTOR);
+        affine_direction_kernel<<<gn, RED_THREADS, 0, c->stream>>>(n, st->sc, st->slack, st->x, st->l,
+                                                                  st->u, st->c, st->g, st->partial);
+        NES_CHECK_LAUNCH(c);
+        reduce_finish_kernel<<<1, 32, 0, c->stream>>>(st->partial, gn, 4,
+                                                     pack_ops(RED_MIN, RED_SUM, RED_SUM, RED_SUM), st->scal);
+        NES_CHECK_LAUNCH(c);
+    }
+    double s9[9];
+    NES_TRY(read_scalars(c, st->scal, s9, 9));
+    out[0] = 0.9 * s9[0];   // step = gamma * max-step (:183)
+    out[1] = sqrt(s9[1]);   // |g|
+    out[2] = sqrt(s9[2]);   // |dg|
+    out[3] = s9[3];         // g.c
+    out[4] = s9[8];         // min slack (must be > 0, :144)
+    st->have_direction = 1;
+    return 0;
+}
+
+int nes_affine_apply(nes_affine* st, double step, nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st || !st->have_direction) return fail(c, NES_ERR_INVALID, "nes_affine_apply: no direction");
+    StageTimer t(c, NES_STAGE_VECTOR);
+    axpy_kernel<<<vec_grid(c, st->n), RED_THREADS, 0, c->stream>>>(st->n, step, st->g, st->x);
+    NES_CHECK_LAUNCH(c);
+    st->have_direction = 0;
+    return 0;
+}
+
+// one-affine-scaling-iteration (:165-207).  *cont receives the Lisp's second value.
+static int affine_optimize(nes_affine* st, int centering, int* cont, nes_ctx* c) {
+    double d[5];
+    const int rc = nes_affine_direction(st, centering, d, c);
+    if (rc < 0) return rc;
+    if (rc != 0) {  // " singular " (:178-181)
+        *cont = 0;
+        return 0;
+    }
+    if (!(d[4] > 0.0)) return fail(c, NES_ERR_INVALID, "affine: iterate left the box (min slack %g)", d[4]);
+    const double step = d[0], norm_g = d[1], norm_dg = d[2], descent = d[3];
+    if (step > 1e10) return fail(c, NES_ERR_INVALID, "Unbounded problem");  // (:187-188)
+    if (!centering) {
+        const double nd = (double)st->n;
+        if (norm_dg < fmin(1e-6, 1e-8 * nd) || descent > 0.0) {
+            *cont = 0;
+            return 0;
+        }
+        if (step * norm_g < 1e-6 || descent > 0.0) return affine_optimize(st, 1, cont, c);
+    }
+    NES_TRY(nes_affine_apply(st, step, c));
+    *cont = 1;
+    return 0;
+}
+
+int nes_affine_one_iteration(nes_affine* st, int centering, double out[4], nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st || !out) return fail(c, NES_ERR_INVALID, "nes_affine_one_iteration: null argument");
+    double r2[2];
+    NES_TRY(nes_affine_residual(st, r2, c));
+    out[0] = r2[0];  // |b - Ax| before the step
+    out[1] = r2[1];  // c'x before the step
+    int cont = 1;
+    if (r2[0] > 1e-6 * (double)st->m) {  // (:248)
+        double rr[2];
+        const int rc = nes_affine_repair(st, rr, c);
+        if (rc < 0) return rc;
+        if (rc != 0) return fail(c, NES_NOT_POSDEF, "affine repair: Cholesky failed"), NES_NOT_POSDEF;
+        out[2] = 1;  // branch: repair
+    } else {
+        NES_TRY(affine_optimize(st, centering, &cont, c));
+        out[2] = centering ? 2 : 0;
+    }
+    out[3] = cont;
+    return 0;
+}
+
+int nes_affine_solve(nes_affine* st, int max_iter, int* iters, double* obj, double* resnorm, nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st) return fail(c, NES_ERR_INVALID, "nes_affine_solve: null state");
+    double out[4], r2[2] = {0, 0};
+    int i = 0;
+    for (; max_iter <= 0 || i < max_iter; ++i) {
+        const int rc = nes_affine_one_iteration(st, ((i + 1) % 16) == 0, out, c);  // (:283)
+        if (rc != 0) {
+            if (iters) *iters = i + 1;
+            return rc;
+        }
+        NES_TRY(nes_affine_residual(st, r2, c));
+        if (!(out[3] != 0.0 || r2[0] > 1e-6 * (double)st->m)) {  // (:284-287)
+            ++i;
+            break;
+        }
+    }
+    if (iters) *iters = i;
+    if (obj) *obj = r2[1];
+    if (resnorm) *resnorm = r2[0];
+    return 0;
+}
+
+int nes_affine_get(nes_affine* st, int which, double* out, nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st || !out) return fail(c, NES_ERR_INVALID, "nes_affine_get: null argument");
+    switch (which) {
+        case 'x': return download(c, out, st->x, st->n * sizeof(double));
+        case 'g': return download(c, out, st->g, st->n * sizeof(double));
+        case 'r': return download(c, out, st->r, st->m * sizeof(double));
+        case 's': return download(c, out, st->slack, st->n * sizeof(double));
+        default: return fail(c, NES_ERR_INVALID, "nes_affine_get: bad selector");
+    }
+}
+
+}  // extern "C"

@@ -563,51 +563,129 @@ __global__ void gather_perm_kernel(int m, const int* __restrict__ perm, const do
     else dst[perm[i]] = src[i];            // x = P' y
 }
 
+// Triangular solve with a diagonal block staged in shared memory (column-major, pitch SN_SP), 128
+// "unknown" threads (tid < 128 own v), four 32x32 sub-blocks: one warp per sub-block with shuffles
+// (lane = row), then a rank-32 update of the other unknowns.  Same scheme as trsv_diag_kernel.
+constexpr int SN_SP = 130;
+constexpr int SN_SOLVE_SMEM = (CH_NB * SN_SP + 2 * CH_NB) * 8;
+
+__device__ __forceinline__ double snode_tri_solve(const double* S, double* xs, double v, double di, int nc,
+                                                  bool transposed) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (!transposed) {
+        for (int sb = 0; sb < CH_NB / 32; ++sb) {
+            const int base = 32 * sb;
+            if (base >= nc) break;
+            if (warp == sb) {
+#pragma unroll 8
+                for (int cc = 0; cc < 32; ++cc) {
+                    const double xc = __shfl_sync(0xffffffffu, v * di, cc);
+                    if (lane == cc) v = xc;
+                    else if (lane > cc && base + lane < nc) v = fma(-S[(base + lane) + (base + cc) * SN_SP], xc, v);
+                }
+                xs[base + lane] = v;
+            }
+            __syncthreads();
+            if (tid >= base + 32 && tid < nc) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int cc = 0; cc < 32; ++cc) acc = fma(S[tid + (base + cc) * SN_SP], xs[base + cc], acc);
+                v -= acc;
+            }
+        }
+    } else {
+        for (int sb = CH_NB / 32 - 1; sb >= 0; --sb) {
+            const int base = 32 * sb;
+            if (base >= nc) continue;
+            if (warp == sb) {
+#pragma unroll 8
+                for (int cc = 31; cc >= 0; --cc) {
+                    const double xc = __shfl_sync(0xffffffffu, v * di, cc);
+                    if (lane == cc) v = xc;
+                    else if (lane < cc && base + cc < nc)
+                        v = fma(-S[(base + cc) + (base + lane) * SN_SP], xc, v);
+                }
+                xs[base + lane] = v;
+            }
+            __syncthreads();
+            if (tid < base) {
+                double acc = 0.0;
+#pragma unroll 8
+                for (int cc = 0; cc < 32; ++cc)
+                    if (base + cc < nc) acc = fma(S[(base + cc) + tid * SN_SP], xs[base + cc], acc);
+                v -= acc;
+            }
+        }
+    }
+    return v;
+}
+
+// forward: x_s <- L_ss^-1 x_s ; x[rows below] -= B x_s.   One CTA (256 threads) per supernode.
 __global__ void __launch_bounds__(256)
 snode_fwd_kernel(const double* __restrict__ Lv, long long off, int nr, int nc, int col0,
                  const int* __restrict__ rows, const double* __restrict__ dinv, double* __restrict__ x) {
-    __shared__ double xs[CH_NB];
+    extern __shared__ double sm[];
+    double* S = sm;
+    double* xs = S + CH_NB * SN_SP;
     const int tid = threadIdx.x;
     const double* blk = Lv + off;
-    if (tid < nc) xs[tid] = x[col0 + tid];
-    __syncthreads();
-    for (int cc = 0; cc < nc; ++cc) {
-        if (tid == cc) xs[cc] *= dinv[col0 + cc];
-        __syncthreads();
-        if (tid > cc && tid < nc) xs[tid] = fma(-blk[tid + (long long)cc * nr], xs[cc], xs[tid]);
-        __syncthreads();
+#pragma unroll 4
+    for (int idx = tid; idx < nc * nc; idx += 256) {
+        const int cc = idx / nc, r = idx - cc * nc;
+        if (r > cc) S[r + cc * SN_SP] = blk[r + (long long)cc * nr];
     }
-    if (tid < nc) x[col0 + tid] = xs[tid];
+    double v = 0.0, di = 1.0;
+    if (tid < nc) {
+        v = x[col0 + tid];
+        di = dinv[col0 + tid];
+    }
+    __syncthreads();
+    v = snode_tri_solve(S, xs, v, di, nc, false);  // all 256 threads walk the same barriers
+    if (tid < nc) {
+        x[col0 + tid] = v;
+        xs[CH_NB + tid] = v;
+    }
+    __syncthreads();
+    const double* xf = xs + CH_NB;
     for (int i = nc + tid; i < nr; i += 256) {
         double acc = 0.0;
-        for (int cc = 0; cc < nc; ++cc) acc = fma(blk[i + (long long)cc * nr], xs[cc], acc);
+#pragma unroll 8
+        for (int cc = 0; cc < nc; ++cc) acc = fma(blk[i + (long long)cc * nr], xf[cc], acc);
         x[rows[i]] -= acc;
     }
 }
 
+// backward: x_s <- L_ss^-T (x_s - B' x[rows below]).
 __global__ void __launch_bounds__(256)
 snode_bwd_kernel(const double* __restrict__ Lv, long long off, int nr, int nc, int col0,
                  const int* __restrict__ rows, const double* __restrict__ dinv, double* __restrict__ x) {
-    __shared__ double xs[CH_NB];
+    extern __shared__ double sm[];
+    double* S = sm;
+    double* xs = S + CH_NB * SN_SP;
+    double* dots = xs + CH_NB;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const double* blk = Lv + off;
-    if (tid < nc) xs[tid] = x[col0 + tid];
-    __syncthreads();
+#pragma unroll 4
+    for (int idx = tid; idx < nc * nc; idx += 256) {
+        const int cc = idx / nc, r = idx - cc * nc;
+        if (r > cc) S[r + cc * SN_SP] = blk[r + (long long)cc * nr];
+    }
     for (int cc = warp; cc < nc; cc += 8) {
         double acc = 0.0;
+#pragma unroll 4
         for (int i = nc + lane; i < nr; i += 32) acc = fma(blk[i + (long long)cc * nr], x[rows[i]], acc);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) xs[cc] -= acc;
+        if (lane == 0) dots[cc] = acc;
     }
     __syncthreads();
-    for (int cc = nc - 1; cc >= 0; --cc) {
-        if (tid == cc) xs[cc] *= dinv[col0 + cc];
-        __syncthreads();
-        if (tid < cc) xs[tid] = fma(-blk[cc + (long long)tid * nr], xs[cc], xs[tid]);
-        __syncthreads();
+    double v = 0.0, di = 1.0;
+    if (tid < nc) {
+        v = x[col0 + tid] - dots[tid];
+        di = dinv[col0 + tid];
     }
-    if (tid < nc) x[col0 + tid] = xs[tid];
+    v = snode_tri_solve(S, xs, v, di, nc, true);
+    if (tid < nc) x[col0 + tid] = v;
 }
 
 static int sparse_configure(nes_ctx* c) {
@@ -616,6 +694,8 @@ static int sparse_configure(nes_ctx* c) {
     NES_CUDA(c, cudaFuncSetAttribute(snode_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_DIAG_SMEM));
     NES_CUDA(c, cudaFuncSetAttribute(snode_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_TR_SMEM));
     NES_CUDA(c, cudaFuncSetAttribute(snode_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_UP_SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(snode_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_SOLVE_SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(snode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_SOLVE_SMEM));
     done = true;
     return 0;
 }
@@ -680,13 +760,13 @@ int sparse_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
     NES_CHECK_LAUNCH(c);
     for (int s = 0; s < sf->nsuper; ++s) {
         const int col0 = sf->first[s], nc = sf->first[s + 1] - col0;
-        snode_fwd_kernel<<<1, 256, 0, c->stream>>>(sf->d_L, sf->off[s], sf->nr[s], nc, col0,
+        snode_fwd_kernel<<<1, 256, SN_SOLVE_SMEM, c->stream>>>(sf->d_L, sf->off[s], sf->nr[s], nc, col0,
                                                   sf->d_rows + sf->rowptr[s], sf->d_dinv, sf->d_x);
         NES_CHECK_LAUNCH(c);
     }
     for (int s = sf->nsuper - 1; s >= 0; --s) {
         const int col0 = sf->first[s], nc = sf->first[s + 1] - col0;
-        snode_bwd_kernel<<<1, 256, 0, c->stream>>>(sf->d_L, sf->off[s], sf->nr[s], nc, col0,
+        snode_bwd_kernel<<<1, 256, SN_SOLVE_SMEM, c->stream>>>(sf->d_L, sf->off[s], sf->nr[s], nc, col0,
                                                   sf->d_rows + sf->rowptr[s], sf->d_dinv, sf->d_x);
         NES_CHECK_LAUNCH(c);
     }

@@ -96,6 +96,15 @@ def _prototypes(lib):
     fn("nes_pdas_solve", C.c_int, _vp, C.c_int, _ip, _dp, _dp, _vp)
     fn("nes_pdas_get", C.c_int, _vp, C.c_int, _dp, _vp)
     fn("nes_pdas_set", C.c_int, _vp, C.c_int, _dp, _vp)
+    fn("nes_affine_create", _vp, _vp, *([_dp] * 5), _vp)
+    fn("nes_affine_free", C.c_int, _vpp, _vp)
+    fn("nes_affine_residual", C.c_int, _vp, _dp, _vp)
+    fn("nes_affine_repair", C.c_int, _vp, _dp, _vp)
+    fn("nes_affine_direction", C.c_int, _vp, C.c_int, _dp, _vp)
+    fn("nes_affine_apply", C.c_int, _vp, C.c_double, _vp)
+    fn("nes_affine_one_iteration", C.c_int, _vp, C.c_int, _dp, _vp)
+    fn("nes_affine_solve", C.c_int, _vp, C.c_int, _ip, _dp, _dp, _vp)
+    fn("nes_affine_get", C.c_int, _vp, C.c_int, _dp, _vp)
     fn("nes_timing_enable", C.c_int, _vp, C.c_int)
     fn("nes_timing_reset", C.c_int, _vp)
     fn("nes_timing_get", C.c_int, _vp, C.c_int, _dp, C.POINTER(C.c_longlong))

@@ -175,6 +175,31 @@ int nes_pdas_solve(nes_pdas* st, int max_iter, int* iters, double* obj, double* 
 int nes_pdas_get(nes_pdas* st, int which, double* out, nes_ctx* c);
 int nes_pdas_set(nes_pdas* st, int which, const double* in, nes_ctx* c);
 
+/* ---- device-resident primal affine scaling state (affine-scaling.lisp) ---------------------------
+ * x and all temporaries live on the GPU; the symbolic analysis is done once at creation
+ * (cholmod_analyze in affine-scaling, :270-271) and every iteration refactorizes numerically
+ * (solve-sparse-recycle, sparse-cholesky.lisp:524-560). */
+typedef struct nes_affine nes_affine;
+/* make-affine-scaling-state (:1-10, :52-90): l,u are the (unclamped, already widened) bounds. */
+nes_affine* nes_affine_create(nes_matrix* A, const double* cvec, const double* b, const double* l,
+                              const double* u, const double* x, nes_ctx* c);
+int nes_affine_free(nes_affine** st, nes_ctx* c);
+/* residual (:209-213): out[0] = |b - Ax|_2, out[1] = c'x; the vector stays on the device. */
+int nes_affine_residual(nes_affine* st, double out[2], nes_ctx* c);
+/* one-repair-iteration (:226-243) on the residual of the last nes_affine_residual.
+ * out[0] = |g|, out[1] = step.  Returns NES_NOT_POSDEF when the Cholesky fails. */
+int nes_affine_repair(nes_affine* st, double out[2], nes_ctx* c);
+/* slack, project (:98-116) of c (or of centering-direction when centering != 0), g = dg*slack:
+ * out = { gamma*max-step, |g|, |dg|, g.c, min slack }.  Returns NES_NOT_POSDEF for " singular ". */
+int nes_affine_direction(nes_affine* st, int centering, double out[5], nes_ctx* c);
+int nes_affine_apply(nes_affine* st, double step, nes_ctx* c);   /* x <- x + step g (:205-206) */
+/* one-iteration (:245-263): out = { |b-Ax| before, c'x before, branch (0 optimize, 1 repair,
+ * 2 recenter), continue flag }. */
+int nes_affine_one_iteration(nes_affine* st, int centering, double out[4], nes_ctx* c);
+/* affine-scaling (:265-297): returns iterations, c'x and the final residual norm. */
+int nes_affine_solve(nes_affine* st, int max_iter, int* iters, double* obj, double* resnorm, nes_ctx* c);
+int nes_affine_get(nes_affine* st, int which, double* out, nes_ctx* c);  /* 'x','g','r','s' */
+
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink/NVSwitch --------------------------------
  * The reference has no distributed code at all; these calls are additions.  M and L are distributed
  * block-cyclically by outer block columns over the ranks (1 x Q grid); each finished panel is
