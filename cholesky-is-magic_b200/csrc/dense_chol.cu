@@ -23,7 +23,11 @@ constexpr int CH_DIAG_SMEM = (CH_NB * CH_P + CH_NB) * 8 + 128 + 16;
 
 __global__ void __launch_bounds__(256)
 potrf_diag_kernel(const __grid_constant__ CUtensorMap mapBlk, int j0, int jb,
-                  double* __restrict__ dinv_out, double dbound, int* __restrict__ info) {
+                  double* __restrict__ dinv_out, double dbound, int* __restrict__ info, int brows) {
+    // batched mode: blockIdx.y = problem, its rows start at blockIdx.y * brows, own {status, minor}
+    const int brow = blockIdx.y * brows;
+    info += 2 * blockIdx.y;
+    dinv_out += brow;
     // dynamic shared memory of a kernel without static __shared__ starts at the CTA window base,
     // which satisfies the 128B alignment TMA needs; keeping S a plain shared pointer lets ptxas
     // use 32-bit shared addressing in the hot loops.
@@ -37,7 +41,7 @@ potrf_diag_kernel(const __grid_constant__ CUtensorMap mapBlk, int j0, int jb,
         mbar_init(bar, 1);
         fence_mbar_init();
         mbar_expect_tx(bar, CH_NB * CH_NB * 8);
-        tma_load_2d(S, &mapBlk, j0, j0, bar);
+        tma_load_2d(S, &mapBlk, j0 + brow, j0, bar);
     }
     __syncthreads();
     mbar_wait(bar, 0);
@@ -48,7 +52,7 @@ potrf_diag_kernel(const __grid_constant__ CUtensorMap mapBlk, int j0, int jb,
     fence_proxy_async();
     __syncthreads();
     if (tid == 0) {
-        tma_store_2d(&mapBlk, j0, j0, S);  // clipped at the matrix edge by the tensor map
+        tma_store_2d(&mapBlk, j0 + brow, j0, S);  // clipped at the matrix edge by the tensor map
         tma_store_commit_and_wait();
     }
 }
@@ -60,8 +64,11 @@ constexpr int TR_SMEM = (CH_NB * CH_NB + TR_ROWS * CH_NB + CH_NB) * 8;
 constexpr int TR_THREADS = 256;  // all threads stage L and the slab; threads 0..63 substitute
 
 __global__ void __launch_bounds__(TR_THREADS)
-trsm_panel_kernel(double* __restrict__ M, long long ld, int j0, int m, const double* __restrict__ dinv_g) {
+trsm_panel_kernel(double* __restrict__ M, long long ld, int j0, int m, const double* __restrict__ dinv_g,
+                  int brows) {
     extern __shared__ double sm[];
+    M += blockIdx.y * brows;      // batched mode: this problem's rows
+    dinv_g += blockIdx.y * brows;
     double* Ls = sm;                       // Ls[c + p*128] = L[c][p]
     double* Xs = Ls + CH_NB * CH_NB;       // Xs[p*64 + row]
     double* dv = Xs + TR_ROWS * CH_NB;
@@ -176,6 +183,23 @@ int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L) {
     return 0;
 }
 
+// Diagonal block + TRSM of one 128-column inner panel for `nbatch` stacked problems (brows = row
+// stride between problems; nbatch = 1, brows = 0 for a single matrix).  Used by batch.cu.
+int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, double* M, long long ld, int i0, int ib,
+                      int m, double* dinv, int* info, int nbatch, int brows) {
+    NES_TRY(chol_configure(c));
+    potrf_diag_kernel<<<dim3(1, nbatch), 256, CH_DIAG_SMEM, c->stream>>>(mapBlk, i0, ib, dinv, c->dbound,
+                                                                        info, brows);
+    NES_CHECK_LAUNCH(c);
+    const int rest = m - i0 - ib;
+    if (rest > 0) {
+        trsm_panel_kernel<<<dim3((rest + TR_ROWS - 1) / TR_ROWS, nbatch), TR_THREADS, TR_SMEM, c->stream>>>(
+            M, ld, i0, m, dinv, brows);
+        NES_CHECK_LAUNCH(c);
+    }
+    return 0;
+}
+
 // One dmma_nt launch: C[r0.., c0..c0+ncols) -= X[r0.., k0..k0+K) X[c0..c0+ncols, k0..k0+K)^T
 static int chol_update(nes_ctx* c, nes_factor* L, int r0, int c0, int nrows, int ncols, int k0, int K,
                        int lower) {
@@ -229,12 +253,12 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
                     const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
                     if (i0 > j0) NES_TRY(chol_update(c, L, i0, i0, m - i0, ib, j0, i0 - j0, 0));
                     potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->mapBlk, i0, ib, L->d_dinv,
-                                                                          c->dbound, L->d_info);
+                                                                          c->dbound, L->d_info, 0);
                     NES_CHECK_LAUNCH(c);
                     const int rest = m - i0 - ib;
                     if (rest > 0) {
                         trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM,
-                                            c->stream>>>(L->d_M, ld, i0, m, L->d_dinv);
+                                            c->stream>>>(L->d_M, ld, i0, m, L->d_dinv, 0);
                         NES_CHECK_LAUNCH(c);
                     }
                 }
@@ -276,12 +300,12 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
             if (i0 > j0)  // bring block column i0 up to date with the inner panels already factored
                 NES_TRY(chol_update(c, L, i0, i0, m - i0, ib, j0, i0 - j0, 0));
             potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->mapBlk, i0, ib, L->d_dinv,
-                                                                  c->dbound, L->d_info);
+                                                                  c->dbound, L->d_info, 0);
             NES_CHECK_LAUNCH(c);
             const int rest = m - i0 - ib;
             if (rest > 0) {
                 trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM, c->stream>>>(
-                    L->d_M, ld, i0, m, L->d_dinv);
+                    L->d_M, ld, i0, m, L->d_dinv, 0);
                 NES_CHECK_LAUNCH(c);
             }
         }

@@ -18,8 +18,11 @@ constexpr int SV_SMEM = (SV_NB * SV_P + SV_NB) * 8 + 16;
 // shuffles (lane = row), followed by a rank-32 update of the remaining unknowns by all warps.
 __global__ void __launch_bounds__(SV_NB)
 trsv_diag_kernel(const double* __restrict__ M, long long ld, int j0, int jb,
-                 const double* __restrict__ dinv, double* __restrict__ x, int transposed) {
+                 const double* __restrict__ dinv, double* __restrict__ x, int transposed, int brows) {
     extern __shared__ __align__(16) double S[];
+    M += blockIdx.y * brows;  // batched mode: blockIdx.y = problem, rows offset by brows
+    dinv += blockIdx.y * brows;
+    x += blockIdx.y * brows;
     double* xs = S + SV_NB * SV_P;
     uint64_t* bar = reinterpret_cast<uint64_t*>(xs + SV_NB);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -94,9 +97,11 @@ trsv_diag_kernel(const double* __restrict__ M, long long ld, int j0, int jb,
 // forward: x[r] -= sum_c L[r, j0+c] x[j0+c] for r >= r0.  CTA = 32 rows x 8 column groups.
 __global__ void __launch_bounds__(256)
 trsv_update_fwd_kernel(const double* __restrict__ M, long long ld, int j0, int jb, int r0, int m,
-                       double* __restrict__ x) {
+                       double* __restrict__ x, int brows) {
     __shared__ double part[8][33];
     __shared__ double xk[SV_NB];
+    M += blockIdx.y * brows;
+    x += blockIdx.y * brows;
     const int tid = threadIdx.x;
     const int lr = tid & 31, grp = tid >> 5;
     if (tid < jb) xk[tid] = x[j0 + tid];
@@ -122,8 +127,10 @@ trsv_update_fwd_kernel(const double* __restrict__ M, long long ld, int j0, int j
 // backward: x[c] -= sum_r L[j0+r, c] x[j0+r] for c < j0.  One warp per column c.
 __global__ void __launch_bounds__(256)
 trsv_update_bwd_kernel(const double* __restrict__ M, long long ld, int j0, int jb,
-                       double* __restrict__ x) {
+                       double* __restrict__ x, int brows) {
     __shared__ double xk[SV_NB];
+    M += blockIdx.y * brows;
+    x += blockIdx.y * brows;
     const int tid = threadIdx.x;
     if (tid < jb) xk[tid] = x[j0 + tid];
     __syncthreads();
@@ -142,25 +149,25 @@ trsv_update_bwd_kernel(const double* __restrict__ M, long long ld, int j0, int j
     if (lane == 0) x[cc] -= acc;
 }
 
-int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
-    StageTimer timer(c, NES_STAGE_SOLVE);
+// Both sweeps for `nbatch` stacked problems (brows = row stride between problems, also the stride of
+// the right-hand sides and of dinv).  nbatch = 1, brows = 0 is the single-matrix case.
+int dense_trsv_sweeps(nes_ctx* c, const double* M, long long ld, int m, const double* dinv, double* d_x,
+                      int nbatch, int brows) {
     static bool configured = false;
     if (!configured) {
         NES_CUDA(c, cudaFuncSetAttribute(trsv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          SV_SMEM));
         configured = true;
     }
-    const int m = (int)L->m;
-    const long long ld = (long long)L->ld;
     // L y = b
     for (int j0 = 0; j0 < m; j0 += SV_NB) {
         const int jb = (m - j0 < SV_NB) ? m - j0 : SV_NB;
-        trsv_diag_kernel<<<1, SV_NB, SV_SMEM, c->stream>>>(L->d_M, ld, j0, jb, L->d_dinv, d_x, 0);
+        trsv_diag_kernel<<<dim3(1, nbatch), SV_NB, SV_SMEM, c->stream>>>(M, ld, j0, jb, dinv, d_x, 0, brows);
         NES_CHECK_LAUNCH(c);
         const int r0 = j0 + jb;
         if (r0 < m) {
-            trsv_update_fwd_kernel<<<(m - r0 + 31) / 32, 256, 0, c->stream>>>(L->d_M, ld, j0, jb, r0, m,
-                                                                             d_x);
+            trsv_update_fwd_kernel<<<dim3((m - r0 + 31) / 32, nbatch), 256, 0, c->stream>>>(M, ld, j0, jb, r0,
+                                                                                           m, d_x, brows);
             NES_CHECK_LAUNCH(c);
         }
     }
@@ -169,14 +176,20 @@ int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
     for (int k = nblk - 1; k >= 0; --k) {
         const int j0 = k * SV_NB;
         const int jb = (m - j0 < SV_NB) ? m - j0 : SV_NB;
-        trsv_diag_kernel<<<1, SV_NB, SV_SMEM, c->stream>>>(L->d_M, ld, j0, jb, L->d_dinv, d_x, 1);
+        trsv_diag_kernel<<<dim3(1, nbatch), SV_NB, SV_SMEM, c->stream>>>(M, ld, j0, jb, dinv, d_x, 1, brows);
         NES_CHECK_LAUNCH(c);
         if (j0 > 0) {
-            trsv_update_bwd_kernel<<<(j0 + 7) / 8, 256, 0, c->stream>>>(L->d_M, ld, j0, jb, d_x);
+            trsv_update_bwd_kernel<<<dim3((j0 + 7) / 8, nbatch), 256, 0, c->stream>>>(M, ld, j0, jb, d_x,
+                                                                                     brows);
             NES_CHECK_LAUNCH(c);
         }
     }
     return 0;
+}
+
+int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
+    StageTimer timer(c, NES_STAGE_SOLVE);
+    return dense_trsv_sweeps(c, L->d_M, (long long)L->ld, (int)L->m, L->d_dinv, d_x, 1, 0);
 }
 
 }  // namespace nes

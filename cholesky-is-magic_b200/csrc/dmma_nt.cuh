@@ -65,6 +65,11 @@ struct NtArgs {
     // explicit tile list (multi-GPU ownership): tile t is (tile_list[t].x, tile_list[t].y) in absolute
     // 128-row / 128-column units of the region; overrides the lower/rectangular enumeration
     const int2* tile_list;
+    // batched mode (many small independent problems stacked along the rows): tile t belongs to problem
+    // t / batch_tiles; operand rows, C rows and the scale vector are offset per problem
+    int batch_tiles;            // tiles per problem (0 = not batched)
+    int batch_rows;             // row stride between problems in the operand / C matrices
+    int batch_scale_stride;     // stride between the problems' scale vectors
 };
 
 // Tile order.  A wave of the persistent grid is ~148 consecutive tiles and only tiles that run at the
@@ -110,6 +115,7 @@ __device__ __forceinline__ void nt_tile_coords(const NtArgs& p, int t, int& bi, 
 // One unit of work for a CTA: a tile and a range of k-chunks of it.
 struct NtWork {
     int tile, bi, bj;
+    int brow;  // row offset of the problem this tile belongs to (batched mode), else 0
     int kc_begin, kc_end;
     int split;  // -1: whole tile, else k-range index of a split tail tile
 };
@@ -131,7 +137,14 @@ __device__ __forceinline__ bool nt_get_work(const NtArgs& p, int kchunks, int it
         w.kc_begin = min(kchunks, w.split * per);
         w.kc_end = min(kchunks, w.kc_begin + per);
     }
-    nt_tile_coords(p, w.tile, w.bi, w.bj);
+    if (p.batch_tiles > 0) {
+        const int bb = w.tile / p.batch_tiles;
+        nt_tile_coords(p, w.tile - bb * p.batch_tiles, w.bi, w.bj);
+        w.brow = bb * p.batch_rows;
+    } else {
+        nt_tile_coords(p, w.tile, w.bi, w.bj);
+        w.brow = 0;
+    }
     return true;
 }
 
@@ -189,9 +202,14 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         uint8_t* st = smem + s * NT_STAGE_BYTES;
         mbar_expect_tx(&full[s], bytes);
         const int kk = p.k0 + p_kc * NT_BK;
-        tma_load_2d(st, &mapX, p.rowA0 + pw.bi * NT_BM, kk, &full[s]);
-        if (!diag) tma_load_2d(st + NT_TILE_BYTES, &mapY, p.rowB0 + pw.bj * NT_BN, kk, &full[s]);
-        if (kHasScale) bulk_load_1d(st + 2 * NT_TILE_BYTES, p.scale + kk, NT_BK * 8, &full[s]);
+        tma_load_2d(st, &mapX, p.rowA0 + pw.brow + pw.bi * NT_BM, kk, &full[s]);
+        if (!diag)
+            tma_load_2d(st + NT_TILE_BYTES, &mapY, p.rowB0 + pw.brow + pw.bj * NT_BN, kk, &full[s]);
+        if (kHasScale) {
+            const double* sc = p.scale + kk;
+            if (p.batch_tiles > 0) sc += (long long)(pw.brow / p.batch_rows) * p.batch_scale_stride;
+            bulk_load_1d(st + 2 * NT_TILE_BYTES, sc, NT_BK * 8, &full[s]);
+        }
         ++p_it;
         if (++p_kc >= pw.kc_end) {
             do {
@@ -220,6 +238,7 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
         const bool diag = p.same_operand && (bi == bj);
         const int row_base = bi * NT_BM + wm * 64 + g;
         const int col_base = bj * NT_BN + wn * 32 + 2 * t4;
+        double* const Cb = p.C + w.brow;  // batched: the problem's rows inside the stacked C
 
         // warm L2 with the C tile while the mainloop runs (beta path reads it in the epilogue)
         if (p.beta != 0.0 && g == 0) {
@@ -229,7 +248,7 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                 for (int c = 0; c < 2; ++c) {
                     const int col = col_base + j * 8 + c;
                     if (col < p.N) {
-                        const double* cp = p.C + (long long)col * p.ldc;
+                        const double* cp = Cb + (long long)col * p.ldc;
 #pragma unroll
                         for (int i = 0; i < 8; i += 2)
                             if (row_base + i * 8 < p.M) prefetch_l2(cp + row_base + i * 8);
@@ -319,7 +338,7 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 #pragma unroll
                 for (int c = 0; c < 2; ++c) {
                     const int col = col_base + j * 8 + c;
-                    const double* cp = p.C + (long long)col * p.ldc;
+                    const double* cp = Cb + (long long)col * p.ldc;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int row = row_base + i * 8;
@@ -331,7 +350,7 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
             for (int c = 0; c < 2; ++c) {
                 const int col = col_base + j * 8 + c;
                 if (col < p.N) {
-                    double* cp = p.C + (long long)col * p.ldc;
+                    double* cp = Cb + (long long)col * p.ldc;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
                         const int row = row_base + i * 8;
@@ -421,7 +440,12 @@ inline cudaError_t nt_launch(const CUtensorMap& mapX, const CUtensorMap& mapY, N
     const int tm = (a.M + NT_BM - 1) / NT_BM;
     const int tn = (a.N + NT_BN - 1) / NT_BN;
     a.tiles_n = tn;
-    if (!a.tile_list) a.ntiles = a.lower ? tm * (tm + 1) / 2 : tm * tn;
+    if (a.batch_tiles > 0) {
+        // caller sets ntiles = problems * batch_tiles; batch_tiles must match the per-problem count
+        a.batch_tiles = a.lower ? tm * (tm + 1) / 2 : tm * tn;
+    } else if (!a.tile_list) {
+        a.ntiles = a.lower ? tm * (tm + 1) / 2 : tm * tn;
+    }
     if (a.ntiles <= 0) return cudaSuccess;
     const int grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
     if (a.split_ws == nullptr || a.split_counters == nullptr) a.split_r = a.split_s = 0;

@@ -38,7 +38,7 @@ __device__ __forceinline__ double block_reduce(double v, int op, double* buf) {
 }
 
 // partial[k * nblocks + b], k < nred; ops packed 2 bits each.
-__global__ void reduce_finish_kernel(const double* __restrict__ partial, int nblocks, int nred,
+static __global__ void reduce_finish_kernel(const double* __restrict__ partial, int nblocks, int nred,
                                      unsigned ops, double* __restrict__ out) {
     const int k = threadIdx.x;
     if (k >= nred) return;

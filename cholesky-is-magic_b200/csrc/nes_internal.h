@@ -193,6 +193,11 @@ int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x);
 // K6: y <- alpha op(A diag(s)) x + beta y on device vectors (gemv.cu); handles dense and CSC
 int matvec(nes_ctx* c, const nes_matrix* A, int transpose, double alpha, const double* d_x,
            double beta, double* d_y);
+// batched building blocks (dense_chol.cu / dense_solve.cu), used by batch.cu
+int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, double* M, long long ld, int i0, int ib,
+                      int m, double* dinv, int* info, int nbatch, int brows);
+int dense_trsv_sweeps(nes_ctx* c, const double* M, long long ld, int m, const double* dinv, double* d_x,
+                      int nbatch, int brows);
 // multi-GPU pieces (nes_dist.cu)
 int dist_plan_tiles(int m, int nbo, int nranks, int rank, std::vector<int2>& tiles,
                     std::vector<int>& tile_first);

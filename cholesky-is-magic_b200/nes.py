@@ -105,6 +105,11 @@ def _prototypes(lib):
     fn("nes_affine_one_iteration", C.c_int, _vp, C.c_int, _dp, _vp)
     fn("nes_affine_solve", C.c_int, _vp, C.c_int, _ip, _dp, _dp, _vp)
     fn("nes_affine_get", C.c_int, _vp, C.c_int, _dp, _vp)
+    fn("nes_batch_create", _vp, _dp, C.c_int, C.c_int, C.c_int, *([_dp] * 5), _vp)
+    fn("nes_batch_free", C.c_int, _vpp, _vp)
+    fn("nes_batch_normal_solve", C.c_int, _vp, _dp, _dp, _dp, _ip, _vp)
+    fn("nes_batch_affine_solve", C.c_int, _vp, C.c_int, _ip, _dp, _dp, _vp)
+    fn("nes_batch_get_x", C.c_int, _vp, _dp, _vp)
     fn("nes_timing_enable", C.c_int, _vp, C.c_int)
     fn("nes_timing_reset", C.c_int, _vp)
     fn("nes_timing_get", C.c_int, _vp, C.c_int, _dp, C.POINTER(C.c_longlong))

@@ -200,6 +200,25 @@ int nes_affine_one_iteration(nes_affine* st, int centering, double out[4], nes_c
 int nes_affine_solve(nes_affine* st, int max_iter, int* iters, double* obj, double* resnorm, nes_ctx* c);
 int nes_affine_get(nes_affine* st, int which, double* out, nes_ctx* c);  /* 'x','g','r','s' */
 
+/* ---- batched small dense LPs (BASELINE config 5: 1024 x (m = 256) via affine scaling) -------------
+ * The reference would call affine-scaling once per LP; here the LPs advance together and every kernel
+ * (formation, potrf, trsm, trsv, GEMV, reductions) covers the whole batch. */
+typedef struct nes_batch nes_batch;
+/* A_all: B matrices m x n, column-major each, back to back; vectors: B slices of length n (c, l, u, x)
+ * or m (b), back to back.  c_all..x_all may be NULL when only nes_batch_normal_solve is used. */
+nes_batch* nes_batch_create(const double* A_all, int B, int m, int n, const double* c_all,
+                            const double* b_all, const double* l_all, const double* u_all,
+                            const double* x_all, nes_ctx* c);
+int nes_batch_free(nes_batch** bt, nes_ctx* c);
+/* batched solve-dense (sparse-cholesky.lisp:409-431): (A_b diag s_b)(A_b diag s_b)' x_b = rhs_b for every
+ * b; s_all (B x n) may be NULL; status[b] = 0 or NES_NOT_POSDEF. */
+int nes_batch_normal_solve(nes_batch* bt, const double* s_all, const double* rhs_all, double* x_all,
+                           int* status, nes_ctx* c);
+/* batched affine-scaling (affine-scaling.lisp:265-297): iters[b] (negative: Cholesky failed in a repair
+ * step), obj[b] = c'x, res[b] = |b - Ax|_2. */
+int nes_batch_affine_solve(nes_batch* bt, int max_iter, int* iters, double* obj, double* res, nes_ctx* c);
+int nes_batch_get_x(nes_batch* bt, double* x_all, nes_ctx* c);
+
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink/NVSwitch --------------------------------
  * The reference has no distributed code at all; these calls are additions.  M and L are distributed
  * block-cyclically by outer block columns over the ranks (1 x Q grid); each finished panel is

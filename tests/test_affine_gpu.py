@@ -37,6 +37,19 @@ def test_affine_scaling_dense_matches_oracle(common, m, n, ub):
     assert st.counters["lnz"] == m * (m + 1) / 2
 
 
+@pytest.mark.parametrize("m,n,seed", [(24, 60, 2), (24, 60, 4), (200, 500, 0)])
+def test_affine_first_iterations_match_oracle(common, m, n, seed):
+    """Fixed-iteration parity (robust, unlike the noise-driven stop): iterate after k steps."""
+    sf = lpgen.dense_lp(m, n, seed)
+    for k in (2, 9):
+        ost = oa.make_affine_state(sf.nvars, sf.ncons, sf.c_dense(), sf.A_dense, sf.b, sf.l, sf.u)
+        oa.affine_scaling(ost, k)
+        st = affine_scaling.make_affine_state(sf)
+        obj, x, res, it = affine_scaling.affine_scaling(st, k, native_loop=True)
+        assert it == k
+        np.testing.assert_allclose(x, ost.x, rtol=1e-6, atol=1e-8)
+
+
 def test_affine_native_loop_equals_stepwise(common):
     sf = lpgen.dense_lp(48, 120, 4)
     a = affine_scaling.affine_scaling(affine_scaling.make_affine_state(sf), 2000)
