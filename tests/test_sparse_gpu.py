@@ -140,3 +140,19 @@ def test_sparse_pdas_matches_oracle(common, m, n):
     obj, gap, it = pdas.pdas(st, 400, native_loop=True)
     assert it == oit
     assert abs(obj - oobj) <= 1e-8 * abs(oobj)
+
+
+def test_config4_flow_mps_to_pdas(common, tmp_path):
+    """BASELINE config 4 end to end at test size: generator -> MPS file -> read-mps -> to-standard-form
+    -> make-pdas -> pdas with the sparse Newton solve on the GPU, against the oracle on the same file."""
+    from cholesky_is_magic_b200 import read_mps
+    m, n = 120, 300
+    sf0 = lpgen.sparse_lp(m, n, nnz_per_col=5, bandwidth=16, seed=7)
+    path = tmp_path / "config4.mps"
+    read_mps.write_mps(path, sf0)
+    sf = read_mps.to_standard_form(read_mps.read_mps_file(path))
+    A = sp.csc_matrix((sf.A.value, (sf.A.row, sf.A.col)), shape=(sf.ncons, sf.nvars))
+    ost = opdas.make_pdas(sf.nvars, sf.ncons, sf.c_dense(), A, sf.b, sf.l, sf.u)
+    oobj, ogap, oit = opdas.pdas(ost, 400)
+    obj, gap, it = pdas.pdas(pdas.make_pdas(sf), 400)
+    assert it == oit and abs(obj - oobj) <= 1e-8 * abs(oobj)
