@@ -125,6 +125,10 @@ trsm_panel_kernel(double* __restrict__ M, long long ld, int j0, int m, const dou
     }
 }
 
+constexpr int TI_SMEM_FWD = (CH_NB * 129 + CH_NB) * 8;
+__global__ void trtri_diag_kernel(const double* __restrict__ M, long long ld, int m,
+                                  const double* __restrict__ dinv_g, double* __restrict__ Winv);
+
 static int chol_configure(nes_ctx* c) {
     static bool done = false;
     if (done) return 0;
@@ -132,6 +136,8 @@ static int chol_configure(nes_ctx* c) {
                                      CH_DIAG_SMEM));
     NES_CUDA(c, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      TR_SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(trtri_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     TI_SMEM_FWD));
     done = true;
     return 0;
 }
@@ -228,6 +234,52 @@ static int chol_update(nes_ctx* c, nes_factor* L, int r0, int c0, int nrows, int
 // panels (narrow DMMA update, diagonal block, TRSM), then one wide trailing update with K = NBO.
 // A larger K halves (NBO=256) or quarters (512) the number of passes over the trailing matrix and
 // the epilogue share of each tile.
+// Inverses of the 128x128 diagonal blocks of L, one CTA per block, thread j = column j of W = L_ii^-1
+// by forward substitution.  They serve the SOLVE phase only (dataflow TRSV): there a block solve is on
+// the critical path of every block row, and a triangular matvec with W is ~10x shorter than a
+// substitution.  The error it adds, cond(L_ii) eps, is far below the cond(M) eps of the solve itself;
+// the factorization (TRSM) never uses inverses, so the ||LL' - M|| gate is untouched.
+constexpr int TI_P = 129;
+constexpr int TI_SMEM = (CH_NB * TI_P + CH_NB) * 8;
+
+__global__ void __launch_bounds__(CH_NB)
+trtri_diag_kernel(const double* __restrict__ M, long long ld, int m, const double* __restrict__ dinv_g,
+                  double* __restrict__ Winv) {
+    // one shared array holds both triangles: L strictly below the diagonal at S[r + c*P] (r > c) and
+    // W' on and above it, W(r, j) at S[j + r*P] (r >= j), so thread j walks its column with unit stride
+    extern __shared__ double S[];
+    double* dv = S + CH_NB * TI_P;
+    const int j = threadIdx.x;
+    const int j0 = blockIdx.x * CH_NB;
+    const int jb = min(CH_NB, m - j0);
+    for (int idx = j; idx < jb * jb; idx += CH_NB) {
+        const int cc = idx / jb, r = idx - cc * jb;
+        if (r > cc) S[r + cc * TI_P] = M[(j0 + r) + (long long)(j0 + cc) * ld];
+    }
+    dv[j] = (j < jb) ? dinv_g[j0 + j] : 1.0;
+    __syncthreads();
+    if (j < jb) {
+        double* w = S + j;  // w[c] = w[c * TI_P]
+        w[j * TI_P] = dv[j];
+        for (int r = j + 1; r < jb; ++r) {
+            double s0 = 0.0, s1 = 0.0;
+            int cc = j;
+            for (; cc + 1 < r; cc += 2) {
+                s0 = fma(S[r + cc * TI_P], w[cc * TI_P], s0);
+                s1 = fma(S[r + (cc + 1) * TI_P], w[(cc + 1) * TI_P], s1);
+            }
+            if (cc < r) s0 = fma(S[r + cc * TI_P], w[cc * TI_P], s0);
+            w[r * TI_P] = -(s0 + s1) * dv[r];
+        }
+    }
+    __syncthreads();
+    double* Wg = Winv + (size_t)blockIdx.x * CH_NB * CH_NB;  // column-major 128 x 128, zero upper part
+    for (int idx = j; idx < CH_NB * CH_NB; idx += CH_NB) {
+        const int cc = idx >> 7, r = idx & 127;
+        Wg[idx] = (r >= cc && r < jb && cc < jb) ? S[cc + r * TI_P] : 0.0;
+    }
+}
+
 __global__ void info_to_minor_kernel(int* info) {
     // info = {status, minor}  ->  {status, status ? minor : INT_MAX} so MIN over ranks finds the first
     if (threadIdx.x == 0 && info[0] == 0) info[1] = 0x7fffffff;
@@ -311,6 +363,11 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
         }
         const int r0 = j0 + jbo;
         if (r0 < m) NES_TRY(chol_update(c, L, r0, r0, m - r0, m - r0, j0, jbo, 1));
+    }
+    if (L->d_Winv) {  // block inverses for the solve phase (off the factorization's critical path)
+        trtri_diag_kernel<<<(m + CH_NB - 1) / CH_NB, CH_NB, TI_SMEM, c->stream>>>(L->d_M, ld, m, L->d_dinv,
+                                                                                  L->d_Winv);
+        NES_CHECK_LAUNCH(c);
     }
     if (P > 1) {  // a failed pivot is only seen by the owner of its panel: agree on {status, first minor}
         info_to_minor_kernel<<<1, 32, 0, c->stream>>>(L->d_info);

@@ -149,6 +149,167 @@ trsv_update_bwd_kernel(const double* __restrict__ M, long long ld, int j0, int j
     if (lane == 0) x[cc] -= acc;
 }
 
+// ---- dataflow TRSV: one cooperative launch per sweep ---------------------------------------------
+// CTA c owns block rows c, c+G, ... (128 rows each).  For block row i it streams the blocks L(i,k)
+// (forward; L(k,i)' backward) in dependency order, spinning on a per-block-row "ready" flag until the
+// CTA that owns block k has published its piece of the solution, and finally solves the diagonal
+// block and publishes its own piece.  The critical path per block row is one 128x128 block product
+// plus the diagonal solve plus one flag hand-off instead of two kernel launches.  Flags carry an
+// epoch number, so they never need resetting.  Co-residency of all CTAs is guaranteed by
+// cudaLaunchCooperativeKernel (grid <= SM count).
+constexpr int DF_Q = 4;                       // each block row is worked on by 4 x 128 threads
+constexpr int DF_W = SV_NB / DF_Q;            // columns (rows) of a block handled per thread: 32
+constexpr int DF_THREADS = DF_Q * SV_NB;      // 512
+constexpr int DF_SMEM = (2 + DF_Q) * SV_NB * 8;
+
+__device__ __forceinline__ void df_wait(volatile int* flag, int epoch) {
+    if (threadIdx.x == 0) {
+        while (*flag != epoch) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(DF_THREADS, 1)
+trsv_dataflow_kernel(const double* __restrict__ M, long long ld, int m, const double* __restrict__ Winv,
+                     double* __restrict__ x, int* __restrict__ flags, int epoch, int transposed) {
+    extern __shared__ __align__(16) double S[];
+    double* xs = S;                      // right-hand side of the diagonal block
+    double* yk = xs + SV_NB;             // the published piece of block k
+    double* part = yk + SV_NB;           // part[q][t]: partial sums of the thread quarters
+    const int tid = threadIdx.x, t = tid & 127, qd = tid >> 7;
+    const int nblk = (m + SV_NB - 1) / SV_NB;
+    auto combine = [&](double v) {       // sum over the four quarters, valid in quarter 0
+        part[qd * SV_NB + t] = v;
+        __syncthreads();
+        double s = 0.0;
+        if (qd == 0) s = (part[t] + part[SV_NB + t]) + (part[2 * SV_NB + t] + part[3 * SV_NB + t]);
+        return s;
+    };
+    for (int q = blockIdx.x; q < nblk; q += gridDim.x) {
+        const int i = transposed ? nblk - 1 - q : q;   // backward sweep walks the block rows downwards
+        const int j0 = i * SV_NB;
+        const int jb = min(SV_NB, m - j0);
+        // this thread's quarter of row t (forward) / column t (backward) of W = L_ii^-1, fetched while the
+        // dependencies are still in flight
+        double wreg[DF_W];
+        {
+            const double* Wb = Winv + (size_t)i * SV_NB * SV_NB;
+            if (!transposed) {
+#pragma unroll
+                for (int cc = 0; cc < DF_W; ++cc) wreg[cc] = Wb[t + (qd * DF_W + cc) * SV_NB];
+            } else {
+#pragma unroll
+                for (int r = 0; r < DF_W; ++r) wreg[r] = Wb[(qd * DF_W + r) + t * SV_NB];
+            }
+        }
+        __syncthreads();
+        double acc = 0.0;
+        // Each thread streams its quarter (32 values) of every 128x128 block.  The values of the NEXT
+        // block are fetched into registers before spinning on that block's flag, so the DRAM/L2 latency
+        // of L overlaps the wait and only 32 FMAs remain on the critical path after a flag flips.
+        double lreg[DF_W];
+        if (!transposed) {
+            const double* Lr = M + j0 + t;  // row of this thread
+            auto preload = [&](int k) {
+                if (t < jb) {
+                    const double* Lb = Lr + (long long)(k * SV_NB + qd * DF_W) * ld;
+#pragma unroll
+                    for (int cc = 0; cc < DF_W; ++cc) lreg[cc] = Lb[(long long)cc * ld];
+                }
+            };
+            if (i > 0) preload(0);
+            for (int k = 0; k < i; ++k) {
+                df_wait(flags + k, epoch);
+                if (tid < SV_NB) yk[tid] = __ldcg(x + k * SV_NB + tid);
+                __syncthreads();
+                if (t < jb) {
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int cc = 0; cc < DF_W; cc += 2) {
+                        a0 = fma(lreg[cc], yk[qd * DF_W + cc], a0);
+                        a1 = fma(lreg[cc + 1], yk[qd * DF_W + cc + 1], a1);
+                    }
+                    acc += a0 + a1;
+                }
+                if (k + 1 < i) preload(k + 1);
+                __syncthreads();
+            }
+        } else {
+            const double* Lc = M + (long long)(j0 + t) * ld;  // column of this thread
+            auto preload = [&](int k) {
+                if (t < jb) {
+                    const int kb = min(SV_NB, m - k * SV_NB);
+                    const double* Lb = Lc + k * SV_NB + qd * DF_W;
+                    const int r_hi = min(DF_W, kb - qd * DF_W);
+#pragma unroll
+                    for (int r = 0; r < DF_W; ++r) lreg[r] = (r < r_hi) ? Lb[r] : 0.0;
+                }
+            };
+            if (i < nblk - 1) preload(nblk - 1);
+            for (int k = nblk - 1; k > i; --k) {
+                df_wait(flags + k, epoch);
+                const int kb = min(SV_NB, m - k * SV_NB);
+                if (tid < SV_NB) yk[tid] = (tid < kb) ? __ldcg(x + k * SV_NB + tid) : 0.0;
+                __syncthreads();
+                if (t < jb) {
+                    double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                    for (int r = 0; r < DF_W; r += 2) {
+                        a0 = fma(lreg[r], yk[qd * DF_W + r], a0);
+                        a1 = fma(lreg[r + 1], yk[qd * DF_W + r + 1], a1);
+                    }
+                    acc += a0 + a1;
+                }
+                if (k - 1 > i) preload(k - 1);
+                __syncthreads();
+            }
+        }
+        // right-hand side of the diagonal block, then y_i = W r (forward) or W' r (backward): a triangular
+        // matvec, 32 FMAs per thread, instead of a 128-step substitution on the critical path
+        const double tot = combine(acc);
+        if (qd == 0) xs[t] = (t < jb) ? x[j0 + t] - tot : 0.0;
+        __syncthreads();
+        double v;
+        {
+            double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+            for (int cc = 0; cc < DF_W; cc += 2) {
+                a0 = fma(wreg[cc], xs[qd * DF_W + cc], a0);
+                a1 = fma(wreg[cc + 1], xs[qd * DF_W + cc + 1], a1);
+            }
+            v = a0 + a1;
+        }
+        v = combine(v);
+        if (qd == 0 && t < jb) x[j0 + t] = v;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile int*>(flags + i) = epoch;
+    }
+}
+
+static int dense_trsv_dataflow(nes_ctx* c, const double* M, long long ld, int m, const double* Winv,
+                               double* d_x, int* d_flags, int* epoch) {
+    static bool configured = false;
+    if (!configured) {
+        NES_CUDA(c, cudaFuncSetAttribute(trsv_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         DF_SMEM));
+        configured = true;
+    }
+    const int nblk = (m + SV_NB - 1) / SV_NB;
+    const int grid = nblk < c->num_sms ? nblk : c->num_sms;
+    for (int transposed = 0; transposed < 2; ++transposed) {
+        int ep = ++(*epoch);
+        void* args[] = {(void*)&M, (void*)&ld, (void*)&m, (void*)&Winv, (void*)&d_x, (void*)&d_flags,
+                        (void*)&ep, (void*)&transposed};
+        NES_CUDA(c, cudaLaunchCooperativeKernel((const void*)trsv_dataflow_kernel, dim3(grid), dim3(DF_THREADS),
+                                                args, DF_SMEM, c->stream));
+        ++c->launches;
+    }
+    return 0;
+}
+
 // Both sweeps for `nbatch` stacked problems (brows = row stride between problems, also the stride of
 // the right-hand sides and of dinv).  nbatch = 1, brows = 0 is the single-matrix case.
 int dense_trsv_sweeps(nes_ctx* c, const double* M, long long ld, int m, const double* dinv, double* d_x,
@@ -189,6 +350,9 @@ int dense_trsv_sweeps(nes_ctx* c, const double* M, long long ld, int m, const do
 
 int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
     StageTimer timer(c, NES_STAGE_SOLVE);
+    if (L->d_flags && L->d_Winv)
+        return dense_trsv_dataflow(c, L->d_M, (long long)L->ld, (int)L->m, L->d_Winv, d_x, L->d_flags,
+                                   &L->flag_epoch);
     return dense_trsv_sweeps(c, L->d_M, (long long)L->ld, (int)L->m, L->d_dinv, d_x, 1, 0);
 }
 

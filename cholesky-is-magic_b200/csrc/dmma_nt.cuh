@@ -35,14 +35,20 @@ namespace nes {
 
 constexpr int NT_BM = 128;
 constexpr int NT_BN = 128;
-constexpr int NT_BK = 16;
+#ifndef NT_BK_OVERRIDE
+#define NT_BK_OVERRIDE 32
+#endif
+constexpr int NT_BK = NT_BK_OVERRIDE;
 constexpr int NT_PITCH = 132;  // smem row pitch in doubles (TMA box rows)
-constexpr int NT_STAGES = 5;
+#ifndef NT_STAGES_OVERRIDE
+#define NT_STAGES_OVERRIDE 3
+#endif
+constexpr int NT_STAGES = NT_STAGES_OVERRIDE;
 constexpr int NT_CONSUMER_WARPS = 8;
 constexpr int NT_THREADS = NT_CONSUMER_WARPS * 32;
 constexpr int NT_TILE_BYTES = NT_PITCH * NT_BK * 8;            // 16896
 constexpr int NT_STAGE_BYTES = 2 * NT_TILE_BYTES + NT_BK * 8;  // + scale slab
-constexpr int NT_SMEM_BYTES = NT_STAGES * NT_STAGE_BYTES + 2 * NT_STAGES * 8 + 128;
+constexpr int NT_SMEM_BYTES = NT_STAGES * NT_STAGE_BYTES + 2 * NT_STAGES * 8 + 16 + 128;
 
 struct NtArgs {
     double* C;            // origin of the output region (column-major)
@@ -77,7 +83,10 @@ struct NtArgs {
 // holds for all blocks), so consecutive tiles should form a squarish patch: the lower triangle is cut
 // into bands of NT_BAND tile rows, each band walked column by column (a wave then touches about
 // NT_BAND + 148/NT_BAND row blocks instead of ~64).
-constexpr int NT_BAND = 12;
+#ifndef NT_BAND_ROWS
+#define NT_BAND_ROWS 12
+#endif
+constexpr int NT_BAND = NT_BAND_ROWS;
 
 __device__ __forceinline__ void nt_tile_coords(const NtArgs& p, int t, int& bi, int& bj) {
     if (p.tile_list) {
@@ -152,12 +161,21 @@ template <bool kHasScale>
 __global__ void __launch_bounds__(NT_THREADS, 1)
 dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                const NtArgs p) {
+    // The kernel has no static __shared__, so the dynamic window starts at the CTA's shared base
+    // (128B-aligned for the TMA destinations) and `smem` stays a shared-typed pointer: the fragment
+    // loads compile to LDS instead of generic LD.
+#ifndef NT_SHARED_TYPED_SMEM
+    // measured on B200 (m=8192, n=16384): generic addressing of the staging buffers schedules better
+    // than a shared-typed pointer (LDS): 34.80 vs 35.33 ms; BK=32 x 3 stages beats 16 x 5 (34.24 ms)
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+#else
+    extern __shared__ __align__(128) uint8_t smem[];
+#endif
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NT_STAGES * NT_STAGE_BYTES);
     uint64_t* empty = full + NT_STAGES;
-    __shared__ int s_last;
+    int& s_last = *reinterpret_cast<int*>(empty + NT_STAGES);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;

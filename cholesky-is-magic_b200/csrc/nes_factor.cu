@@ -53,7 +53,10 @@ nes_factor* nes_analyze(nes_matrix* A, nes_ctx* c) {
     L->d_dinv = static_cast<double*>(dev_alloc(c, (m + 16) * sizeof(double)));
     L->d_rhs = static_cast<double*>(dev_alloc(c, (m + 16) * sizeof(double)));
     L->d_info = static_cast<int*>(dev_alloc(c, 4 * sizeof(int)));
-    if (!L->d_M || !L->d_dinv || !L->d_rhs || !L->d_info) {
+    L->d_flags = static_cast<int*>(dev_alloc(c, ((m + 127) / 128 + 1) * sizeof(int)));
+    if (L->d_flags) cudaMemsetAsync(L->d_flags, 0, ((m + 127) / 128 + 1) * sizeof(int), c->stream);
+    L->d_Winv = static_cast<double*>(dev_alloc(c, ((m + 127) / 128) * 128 * 128 * sizeof(double)));
+    if (!L->d_M || !L->d_dinv || !L->d_rhs || !L->d_info || !L->d_flags || !L->d_Winv) {
         nes_free_factor(&L, c);
         return nullptr;
     }
@@ -123,6 +126,8 @@ static void nes_free_factor_impl(nes_factor* L, nes_ctx* c) {
     dev_free(c, L->d_dinv);
     dev_free(c, L->d_rhs);
     dev_free(c, L->d_info);
+    dev_free(c, L->d_flags);
+    dev_free(c, L->d_Winv);
     dev_free(c, L->d_tile_list);
     dev_free(c, L->d_stage);
 }

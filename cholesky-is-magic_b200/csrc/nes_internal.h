@@ -168,6 +168,9 @@ struct nes_factor {
     double* d_dinv = nullptr;  // 1/L_jj
     double* d_rhs = nullptr;   // solve workspace (solve2's Y/E)
     int* d_info = nullptr;     // {status, minor}
+    int* d_flags = nullptr;    // per-block-row ready flags of the dataflow TRSV (epoch numbered)
+    double* d_Winv = nullptr;  // inverses of the 128x128 diagonal blocks of L (solve phase only)
+    int flag_epoch = 0;
     CUtensorMap mapM;    // 132 x 16 operand boxes (dmma_nt)
     CUtensorMap mapBlk;  // 128 x 128 block boxes (diagonal-block kernels)
     int factorized = 0;

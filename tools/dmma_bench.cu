@@ -154,6 +154,7 @@ int main(int argc, char** argv) {
     int sms = prop.multiProcessorCount;
     printf("device %s, %d SMs, clock %d kHz\n", prop.name, sms, prop.clockRate);
     double* out; CK(cudaMalloc(&out, (size_t)sms * 8 * 1024 * 8));
+#ifndef QUICK
     run_dmma<4>(4, 1, out, sms);
     run_dmma<8>(4, 1, out, sms);
     run_dmma<16>(4, 1, out, sms);
@@ -166,6 +167,7 @@ int main(int argc, char** argv) {
     run_dfma<8>(8, 1, out, sms);
     run_dfma<8>(16, 1, out, sms);
     run_dfma<8>(32, 2, out, sms);
+#endif
     syrk_case(200, 500, sms, true, 0);
     syrk_case(130, 37, sms, true, 0);
     syrk_case(517, 1001, sms, true, 0);
