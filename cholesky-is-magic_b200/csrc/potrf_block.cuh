@@ -1,111 +1,146 @@
 // In-shared-memory Cholesky of one diagonal block (<= 128 x 128, column-major pitch CH_P), shared by
 // the dense panel kernel (dense_chol.cu) and the supernode kernel (sparse_chol.cu).
-//   16-column sub-panels: the 16x16 pivot block is factored by ONE WARP with shuffles (lane = row),
-//   the rows below by one thread per row, the trailing rank-16 update on a 16x16 thread grid with
-//   interleaved 7x7 register tiles.  256 threads.  A non-positive (or NaN) pivot records
+//   8-column sub-panels: every row-owning thread factors the 8x8 pivot block redundantly in registers
+//   (the first version used one warp + shuffles on a 16x16 pivot: ~490 cycles per column measured;
+//   the register version's chain is rsqrt + mul + fma) and solves its own row; the trailing rank-8
+//   update runs on a 16x16 thread grid with interleaved 8x8 register tiles.  256 threads.  A non-positive (or NaN) pivot records
 //   info = {NES_NOT_POSDEF, col_base + column} once and continues with a unit pivot.
 #pragma once
 #include "../../include/nes.h"
 
 namespace nes {
 
+#ifdef POTRF_PROFILE
+__device__ long long potrf_prof[8];
+#endif
+
 constexpr int CH_NB = 128;
-constexpr int CH_W = 16;
 constexpr int CH_P = 128;  // smem pitch of the diagonal block (column-major, dense TMA box)
 
 __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb, double dbound,
                                                  int* __restrict__ info, int col_base) {
     const int tid = threadIdx.x;
-    const int j0 = col_base;
-    for (int c0 = 0; c0 < jb; c0 += CH_W) {
-        const int w = min(CH_W, jb - c0);
-        // (1) pivot block, one warp, lane = row
-        if (tid < 32) {
-            const int lane = tid;
-            double a[CH_W];
+    constexpr int W = 8;  // sub-panel width
+#ifdef POTRF_PROFILE
+    long long t_piv = 0, t_upd = 0, t0 = clock64();
+#endif
+    for (int c0 = 0; c0 < jb; c0 += W) {
+        const int w = min(W, jb - c0);
+        // (1)+(2) every thread that owns a row >= c0 factors the w x w pivot block REDUNDANTLY in its own
+        // registers (no shuffles, no barrier between the pivot and the row solves: the per-column chain
+        // is rsqrt + mul + fma) and then solves its row against it.
+        const int r = c0 + tid;
+#ifdef POTRF_PROFILE
+        long long q0 = clock64(), q1 = q0, q2 = q0, q3 = q0;
+#endif
+        if (r < jb) {
+            double P[W][W];   // lower triangle of the pivot block, then of its factor
+            double ri[W];
+            double x[W];
+            if (w == W) {  // full sub-panel: unconditional broadcast loads
 #pragma unroll
-            for (int cc = 0; cc < CH_W; ++cc)
-                a[cc] = (lane < w && cc <= lane) ? S[(c0 + lane) + (c0 + cc) * CH_P] : 0.0;
+                for (int cc = 0; cc < W; ++cc)
 #pragma unroll
-            for (int cc = 0; cc < CH_W; ++cc) {
-                if (cc < w) {
-                    double d = __shfl_sync(0xffffffffu, a[cc], cc);
-                    // CHOLMOD dbound for LL': L_jj is not allowed below dbound (0 = off)
-                    if (dbound > 0.0 && d < dbound * dbound) d = dbound * dbound;
-                    if (!(d > 0.0)) {  // also catches NaN
-                        if (lane == 0 && info[0] == 0) {
-                            info[0] = NES_NOT_POSDEF;
-                            info[1] = j0 + c0 + cc;
-                        }
-                        d = 1.0;
-                    }
-                    // rsqrt is the latency floor of the pivot chain (66 cycles on B200); it is good to
-                    // 1 ulp, so L_jj = d * rsqrt(d) is within 2 ulp of sqrt(d)
-                    const double ri = rsqrt(d);
-                    a[cc] = (lane == cc) ? d * ri : a[cc] * ri;
+                    for (int rr = cc; rr < W; ++rr) P[rr][cc] = S[(c0 + rr) + (c0 + cc) * CH_P];
 #pragma unroll
-                    for (int c2 = cc + 1; c2 < CH_W; ++c2) {
-                        const double l = __shfl_sync(0xffffffffu, a[cc], c2);
-                        a[c2] = fma(-a[cc], l, a[c2]);
-                    }
-                    if (lane == 0) dinv[c0 + cc] = ri;
-                }
+                for (int cc = 0; cc < W; ++cc) x[cc] = S[r + (c0 + cc) * CH_P];
+            } else {
+#pragma unroll
+                for (int cc = 0; cc < W; ++cc)
+#pragma unroll
+                    for (int rr = cc; rr < W; ++rr)
+                        P[rr][cc] = (rr < w && cc < w) ? S[(c0 + rr) + (c0 + cc) * CH_P] : (rr == cc ? 1.0 : 0.0);
+#pragma unroll
+                for (int cc = 0; cc < W; ++cc) x[cc] = (cc < w) ? S[r + (c0 + cc) * CH_P] : 0.0;
             }
+#ifdef POTRF_PROFILE
+            q1 = clock64();
+#endif
 #pragma unroll
-            for (int cc = 0; cc < CH_W; ++cc)
-                if (lane < w && cc <= lane) S[(c0 + lane) + (c0 + cc) * CH_P] = a[cc];
+            for (int cc = 0; cc < W; ++cc) {
+                double d = P[cc][cc];
+                // CHOLMOD dbound for LL': L_jj is not allowed below dbound (0 = off)
+                if (dbound > 0.0 && d < dbound * dbound) d = dbound * dbound;
+                if (!(d > 0.0)) {  // also catches NaN
+                    if (tid == 0 && cc < w && info[0] == 0) {
+                        info[0] = NES_NOT_POSDEF;
+                        info[1] = col_base + c0 + cc;
+                    }
+                    d = 1.0;
+                }
+                // rsqrt is the latency floor of the pivot chain (66 cycles on B200); it is good to 1 ulp,
+                // so L_jj = d * rsqrt(d) is within 2 ulp of sqrt(d)
+                ri[cc] = rsqrt(d);
+                P[cc][cc] = d * ri[cc];
+#pragma unroll
+                for (int rr = cc + 1; rr < W; ++rr) P[rr][cc] *= ri[cc];
+#pragma unroll
+                for (int c2 = cc + 1; c2 < W; ++c2)
+#pragma unroll
+                    for (int rr = c2; rr < W; ++rr) P[rr][c2] = fma(-P[rr][cc], P[c2][cc], P[rr][c2]);
+            }
+#ifdef POTRF_PROFILE
+            q2 = clock64();
+#endif
+            // x L_p' = a.  For a row INSIDE the pivot block the same recurrence yields row tid of the
+            // factor in x[0..tid] (entries past the diagonal are junk and not stored), so every thread
+            // takes one path: no divergence in warp 0.
+#pragma unroll
+            for (int cc = 0; cc < W; ++cc) {
+                double acc = x[cc];
+#pragma unroll
+                for (int p = 0; p < cc; ++p) acc = fma(-x[p], P[cc][p], acc);
+                x[cc] = acc * ri[cc];
+            }
+            const int last = (tid < w) ? tid : w - 1;
+#pragma unroll
+            for (int cc = 0; cc < W; ++cc)
+                if (cc <= last) S[r + (c0 + cc) * CH_P] = x[cc];
+            if (tid == 0) {
+#pragma unroll
+                for (int cc = 0; cc < W; ++cc)
+                    if (cc < w) dinv[c0 + cc] = ri[cc];
+            }
         }
+#ifdef POTRF_PROFILE
+        q3 = clock64();
+        if (tid == 0 && c0 == 0) { potrf_prof[2] = q1 - q0; potrf_prof[3] = q2 - q1; potrf_prof[4] = q3 - q2; }
+        if (tid == 96 && c0 == 0) { potrf_prof[6] = q3 - q0; }
+        if (tid == 255 && c0 == 0) { potrf_prof[7] = q3 - q0; }
+#endif
         __syncthreads();
+#ifdef POTRF_PROFILE
+        { long long t1 = clock64(); t_piv += t1 - t0; t0 = t1; if (tid == 0 && c0 == 0) potrf_prof[5] = t_piv; }
+#endif
         const int base = c0 + w;
         const int T = jb - base;
         if (T <= 0) break;
-        // (2) rows below the pivot block: x L_d' = a, one thread per row
-        if (tid < T) {
-            const int r = base + tid;
-            double x[CH_W];
-#pragma unroll
-            for (int cc = 0; cc < CH_W; ++cc) x[cc] = (cc < w) ? S[r + (c0 + cc) * CH_P] : 0.0;
-#pragma unroll
-            for (int cc = 0; cc < CH_W; ++cc) {
-                if (cc < w) {
-                    double acc = x[cc];
-#pragma unroll
-                    for (int p = 0; p < cc; ++p)
-                        acc = fma(-x[p], S[(c0 + cc) + (c0 + p) * CH_P], acc);
-                    x[cc] = acc * dinv[c0 + cc];
-                }
-            }
-#pragma unroll
-            for (int cc = 0; cc < CH_W; ++cc)
-                if (cc < w) S[r + (c0 + cc) * CH_P] = x[cc];
-        }
-        __syncthreads();
-        // (3) trailing rank-w update of the lower triangle, 16x16 thread grid, interleaved 7x7 tiles.
+        // (3) trailing rank-w update of the lower triangle, 16x16 thread grid, interleaved 8x8 tiles.
         // Loads are unconditional: rows past T alias the top of the next column (finite, and the
         // products land in accumulators that are never stored).
         {
             const int ti = tid & 15, tj = tid >> 4;
-            double acc[7][7];
+            double acc[8][8];
 #pragma unroll
-            for (int a_ = 0; a_ < 7; ++a_)
+            for (int a_ = 0; a_ < 8; ++a_)
 #pragma unroll
-                for (int b_ = 0; b_ < 7; ++b_) acc[a_][b_] = 0.0;
+                for (int b_ = 0; b_ < 8; ++b_) acc[a_][b_] = 0.0;
             const double* colbase = S + c0 * CH_P + base;
             const int na = (T + 15) >> 4;  // 16-row groups in the trailing block (uniform)
-            if (w == CH_W) {
-#pragma unroll 4
-                for (int p = 0; p < CH_W; ++p) {
-                    const double* col = colbase + p * CH_P;
-                    double xi[7], xj[7];
+            if (w == W) {
 #pragma unroll
-                    for (int a_ = 0; a_ < 7; ++a_) {
+                for (int p = 0; p < W; ++p) {
+                    const double* col = colbase + p * CH_P;
+                    double xi[8], xj[8];
+#pragma unroll
+                    for (int a_ = 0; a_ < 8; ++a_) {
                         if (a_ < na) {
                             xi[a_] = col[ti + 16 * a_];
                             xj[a_] = col[tj + 16 * a_];
                         }
                     }
 #pragma unroll
-                    for (int a_ = 0; a_ < 7; ++a_) {
+                    for (int a_ = 0; a_ < 8; ++a_) {
                         if (a_ < na) {
 #pragma unroll
                             for (int b_ = 0; b_ <= a_; ++b_)
@@ -117,7 +152,7 @@ __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb
                 for (int p = 0; p < w; ++p) {
                     const double* col = colbase + p * CH_P;
 #pragma unroll
-                    for (int a_ = 0; a_ < 7; ++a_) {
+                    for (int a_ = 0; a_ < 8; ++a_) {
                         if (a_ < na) {
                             const double xa = col[ti + 16 * a_];
 #pragma unroll
@@ -128,7 +163,7 @@ __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb
                 }
             }
 #pragma unroll
-            for (int a_ = 0; a_ < 7; ++a_) {
+            for (int a_ = 0; a_ < 8; ++a_) {
                 if (a_ < na) {
 #pragma unroll
                     for (int b_ = 0; b_ <= a_; ++b_) {
@@ -139,8 +174,13 @@ __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb
             }
         }
         __syncthreads();
+#ifdef POTRF_PROFILE
+        { long long t1 = clock64(); t_upd += t1 - t0; t0 = t1; }
+#endif
     }
-
+#ifdef POTRF_PROFILE
+    if (tid == 0) { potrf_prof[0] = t_piv; potrf_prof[1] = t_upd; }
+#endif
 }
 
 }  // namespace nes
