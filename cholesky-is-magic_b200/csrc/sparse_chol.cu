@@ -57,6 +57,22 @@ struct SparseFactor {
     long long* d_edest = nullptr;
     double* d_x = nullptr;        // permuted right-hand side / solution workspace
     int* d_info = nullptr;
+    // dataflow solve (one cooperative launch per sweep)
+    int* d_first = nullptr;       // nsuper+1
+    int* d_nr = nullptr;          // nsuper
+    long long* d_off = nullptr;   // nsuper+1
+    int* d_rowptr = nullptr;      // nsuper+1
+    long long* d_woff = nullptr;  // nsuper+1: offsets of the inverted diagonal blocks (nc x nc each)
+    double* d_W = nullptr;
+    int* d_inptr = nullptr;       // nsuper+1: incoming segments of each target supernode, ascending source
+    int* d_in_s = nullptr;
+    int* d_in_j0 = nullptr;
+    int* d_in_j1 = nullptr;
+    int* d_segptr = nullptr;      // nsuper+1 (device copy of segptr)
+    int* d_seg_tid = nullptr;     // target supernode id of each outgoing segment
+    int* d_flags = nullptr;
+    int flag_epoch = 0;
+    long long wsize = 0;
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -254,7 +270,7 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
 
     // ---- update segments + relative maps -------------------------------------------------------
     std::vector<long long> seg_toff;
-    std::vector<int> seg_tnr, seg_tcol0, seg_j0, seg_j1, seg_relptr, rel;
+    std::vector<int> seg_tnr, seg_tcol0, seg_j0, seg_j1, seg_relptr, rel, seg_tid, seg_src;
     sf->segptr.assign(nsuper + 1, 0);
     for (int s = 0; s < nsuper; ++s) {
         const int nc = first[s + 1] - first[s];
@@ -266,6 +282,8 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
             int j1 = j;
             while (j1 < rb && col2sn[R[nc + j1]] == t) ++j1;
             seg_toff.push_back(sf->off[t]);
+            seg_tid.push_back(t);
+            seg_src.push_back(s);
             seg_tnr.push_back(sf->nr[t]);
             seg_tcol0.push_back(first[t]);
             seg_j0.push_back(j);
@@ -288,6 +306,25 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
         sf->segptr[s + 1] = (int)seg_toff.size();
     }
     sf->nseg = (int)seg_toff.size();
+    // incoming segments per target (sources ascending because segments are generated in source order)
+    std::vector<int> inptr(nsuper + 1, 0), in_s(sf->nseg), in_j0(sf->nseg), in_j1(sf->nseg);
+    for (int q = 0; q < sf->nseg; ++q) inptr[seg_tid[q] + 1]++;
+    for (int t = 0; t < nsuper; ++t) inptr[t + 1] += inptr[t];
+    {
+        std::vector<int> next(inptr.begin(), inptr.end() - 1);
+        for (int q = 0; q < sf->nseg; ++q) {
+            const int p = next[seg_tid[q]]++;
+            in_s[p] = seg_src[q];
+            in_j0[p] = seg_j0[q];
+            in_j1[p] = seg_j1[q];
+        }
+    }
+    std::vector<long long> woff(nsuper + 1, 0);
+    for (int t = 0; t < nsuper; ++t) {
+        const long long nc = first[t + 1] - first[t];
+        woff[t + 1] = woff[t] + nc * nc;
+    }
+    sf->wsize = woff[nsuper];
 
     // ---- assembly map: every entry (i >= j) of tril(P M P') -> position in the supernodal storage
     std::vector<int> ei, ej;
@@ -334,14 +371,21 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
     bool ok = up_i(&sf->d_rows, rows) && up_l(&sf->d_seg_toff, seg_toff) && up_i(&sf->d_seg_tnr, seg_tnr) &&
               up_i(&sf->d_seg_tcol0, seg_tcol0) && up_i(&sf->d_seg_j0, seg_j0) && up_i(&sf->d_seg_j1, seg_j1) &&
               up_i(&sf->d_seg_relptr, seg_relptr) && up_i(&sf->d_rel, rel) && up_i(&sf->d_perm, perm) &&
-              up_i(&sf->d_ei, ei) && up_i(&sf->d_ej, ej) && up_l(&sf->d_edest, edest);
+              up_i(&sf->d_ei, ei) && up_i(&sf->d_ej, ej) && up_l(&sf->d_edest, edest) &&
+              up_i(&sf->d_first, first) && up_i(&sf->d_nr, sf->nr) && up_l(&sf->d_off, sf->off) &&
+              up_i(&sf->d_rowptr, sf->rowptr) && up_l(&sf->d_woff, woff) && up_i(&sf->d_inptr, inptr) &&
+              up_i(&sf->d_in_s, in_s) && up_i(&sf->d_in_j0, in_j0) && up_i(&sf->d_in_j1, in_j1) &&
+              up_i(&sf->d_segptr, sf->segptr) && up_i(&sf->d_seg_tid, seg_tid);
     if (ok) {
         sf->d_L = static_cast<double*>(dev_alloc(c, (size_t)(sf->lsize + 16) * sizeof(double)));
         sf->d_dinv = static_cast<double*>(dev_alloc(c, (size_t)(m + 16) * sizeof(double)));
         sf->d_x = static_cast<double*>(dev_alloc(c, (size_t)(m + 16) * sizeof(double)));
         sf->d_info = static_cast<int*>(dev_alloc(c, 4 * sizeof(int)));
+        sf->d_W = static_cast<double*>(dev_alloc(c, (size_t)(sf->wsize + 16) * sizeof(double)));
+        sf->d_flags = static_cast<int*>(dev_alloc(c, (size_t)(nsuper + 1) * sizeof(int)));
         L->d_rhs = static_cast<double*>(dev_alloc(c, (size_t)(m + 16) * sizeof(double)));
-        ok = sf->d_L && sf->d_dinv && sf->d_x && sf->d_info && L->d_rhs;
+        ok = sf->d_L && sf->d_dinv && sf->d_x && sf->d_info && L->d_rhs && sf->d_W && sf->d_flags;
+        if (ok) cudaMemsetAsync(sf->d_flags, 0, (size_t)(nsuper + 1) * sizeof(int), c->stream);
     }
     if (!ok) return c->status < 0 ? c->status : NES_ERR_OUT_OF_MEMORY;
     c->anz = (double)sf->anz;
@@ -357,7 +401,9 @@ void sparse_free(nes_ctx* c, nes_factor* L) {
     if (!sf) return;
     void* ptrs[] = {sf->d_L, sf->d_dinv, sf->d_rows, sf->d_seg_toff, sf->d_seg_tnr, sf->d_seg_tcol0,
                     sf->d_seg_j0, sf->d_seg_j1, sf->d_seg_relptr, sf->d_rel, sf->d_perm, sf->d_ei,
-                    sf->d_ej, sf->d_edest, sf->d_x, sf->d_info};
+                    sf->d_ej, sf->d_edest, sf->d_x, sf->d_info, sf->d_first, sf->d_nr, sf->d_off, sf->d_rowptr,
+                    sf->d_woff, sf->d_W, sf->d_inptr, sf->d_in_s, sf->d_in_j0, sf->d_in_j1, sf->d_segptr,
+                    sf->d_seg_tid, sf->d_flags};
     for (void* p : ptrs) dev_free(c, p);
     delete sf;
     L->sparse = nullptr;
@@ -688,12 +734,224 @@ snode_bwd_kernel(const double* __restrict__ Lv, long long off, int nr, int nc, i
     if (tid < nc) x[col0 + tid] = v;
 }
 
+// ---- dataflow supernodal solve: one cooperative launch per sweep -------------------------------
+// CTAs take supernodes round-robin in elimination order.  Forward (owner computes): supernode t waits,
+// source by source, for the descendants s that have rows inside t's columns, subtracts
+// B_s[rows in t, :] y_s from its right-hand side in shared memory (fixed source order => bitwise
+// reproducible, no atomics), multiplies by W_t = L_tt^-1 and publishes y_t with an epoch-numbered flag.
+// Backward: supernode s waits for the supernodes that own its below-diagonal rows, forms
+// y_s - B_s' z[rows], multiplies by W_s' and publishes.  Replaces 2 * nsuper single-CTA launches.
+constexpr int SD_THREADS = 256;
+constexpr int SD_SMEM = (CH_NB * 129 + 4 * CH_NB) * 8;
+
+// W_s = L_ss^-1 for every supernode, one CTA per supernode, thread j = column j (forward substitution).
+__global__ void __launch_bounds__(CH_NB)
+snode_trtri_kernel(const double* __restrict__ Lv, const long long* __restrict__ off,
+                   const int* __restrict__ first, const int* __restrict__ nrs,
+                   const double* __restrict__ dinv_g, const long long* __restrict__ woff,
+                   double* __restrict__ W) {
+    constexpr int P = 129;
+    extern __shared__ double S[];   // L strictly below the diagonal at S[r + c*P]; W' on/above it
+    double* dv = S + CH_NB * P;
+    const int s = blockIdx.x, j = threadIdx.x;
+    const int col0 = first[s], nc = first[s + 1] - col0, nr = nrs[s];
+    const double* blk = Lv + off[s];
+    for (int idx = j; idx < nc * nc; idx += CH_NB) {
+        const int cc = idx / nc, r = idx - cc * nc;
+        if (r > cc) S[r + cc * P] = blk[r + (long long)cc * nr];
+    }
+    dv[j] = (j < nc) ? dinv_g[col0 + j] : 1.0;
+    __syncthreads();
+    if (j < nc) {
+        double* w = S + j;
+        w[j * P] = dv[j];
+        for (int r = j + 1; r < nc; ++r) {
+            double s0 = 0.0, s1 = 0.0;
+            int cc = j;
+            for (; cc + 1 < r; cc += 2) {
+                s0 = fma(S[r + cc * P], w[cc * P], s0);
+                s1 = fma(S[r + (cc + 1) * P], w[(cc + 1) * P], s1);
+            }
+            if (cc < r) s0 = fma(S[r + cc * P], w[cc * P], s0);
+            w[r * P] = -(s0 + s1) * dv[r];
+        }
+    }
+    __syncthreads();
+    double* Wg = W + woff[s];   // column-major nc x nc, zero above the diagonal
+    for (int idx = j; idx < nc * nc; idx += CH_NB) {
+        const int cc = idx / nc, r = idx - cc * nc;
+        Wg[idx] = (r >= cc) ? S[cc + r * P] : 0.0;
+    }
+}
+
+__device__ __forceinline__ void sd_wait(volatile int* flag, int epoch) {
+    if (threadIdx.x == 0) {
+        while (*flag != epoch) {
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+struct SolveDesc {
+    const double* Lv;
+    const double* W;
+    const long long* off;
+    const long long* woff;
+    const int* first;
+    const int* nr;
+    const int* rowptr;
+    const int* rows;
+    const int* inptr;
+    const int* in_s;
+    const int* in_j0;
+    const int* in_j1;
+    const int* segptr;
+    const int* seg_tid;
+    int nsuper;
+};
+
+constexpr int SD_WP = 129;  // pitch of the staged W block
+
+__global__ void __launch_bounds__(SD_THREADS)
+snode_solve_dataflow_kernel(SolveDesc d, double* __restrict__ x, int* __restrict__ flags, int epoch,
+                            int transposed) {
+    extern __shared__ double sm[];
+    double* Ws = sm;                          // W_s staged as Ws[r + c*SD_WP]
+    double* rhs = Ws + CH_NB * SD_WP;         // right-hand side of this supernode's columns (nc)
+    double* ys = rhs + CH_NB;                 // the published piece of another supernode
+    double* part = ys + CH_NB;                // 2 x 128 partial sums
+    const int tid = threadIdx.x, t = tid & 127, half = tid >> 7;
+    for (int q = blockIdx.x; q < d.nsuper; q += gridDim.x) {
+        const int s = transposed ? d.nsuper - 1 - q : q;
+        const int col0 = d.first[s], nc = d.first[s + 1] - col0, nr = d.nr[s];
+        const double* Wb = d.W + d.woff[s];
+        __syncthreads();
+        // stage W_s and the right-hand side while the dependencies are still in flight
+        for (int idx = tid; idx < nc * nc; idx += SD_THREADS) {
+            const int cc = idx / nc, r = idx - cc * nc;
+            Ws[r + cc * SD_WP] = Wb[idx];
+        }
+        if (tid < CH_NB) rhs[tid] = (tid < nc) ? x[col0 + tid] : 0.0;
+        __syncthreads();
+        if (!transposed) {
+            for (int e = d.inptr[s]; e < d.inptr[s + 1]; ++e) {
+                const int src = d.in_s[e], j0 = d.in_j0[e], j1 = d.in_j1[e];
+                const int scol0 = d.first[src], snc = d.first[src + 1] - scol0, snr = d.nr[src];
+                const double* B = d.Lv + d.off[src] + snc;      // B(j, c) = B[j + c*snr]
+                const int* srows = d.rows + d.rowptr[src] + snc;
+                const int nj = j1 - j0;                         // <= 128 rows of src land in my columns
+                const int c_lo = half * ((snc + 1) / 2), c_hi = half ? snc : (snc + 1) / 2;
+                // fetch my slice of B before spinning on the source's flag
+                double breg[64];
+#pragma unroll
+                for (int cc = 0; cc < 64; ++cc)
+                    breg[cc] = (t < nj && c_lo + cc < c_hi) ? B[(j0 + t) + (long long)(c_lo + cc) * snr] : 0.0;
+                sd_wait(flags + src, epoch);
+                if (tid < CH_NB) ys[tid] = (tid < snc) ? __ldcg(x + scol0 + tid) : 0.0;
+                __syncthreads();
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int cc = 0; cc < 64; cc += 2) {
+                    a0 = fma(breg[cc], ys[min(c_lo + cc, CH_NB - 1)], a0);
+                    a1 = fma(breg[cc + 1], ys[min(c_lo + cc + 1, CH_NB - 1)], a1);
+                }
+                part[half * CH_NB + t] = a0 + a1;
+                __syncthreads();
+                if (tid < nj) rhs[srows[j0 + tid] - col0] -= part[tid] + part[CH_NB + tid];
+                __syncthreads();
+            }
+            // y_s = W rhs  (lower triangular matvec from shared memory, two halves of the columns)
+            {
+                const int c_lo = half * 64, c_hi = min(nc, c_lo + 64);
+                double a0 = 0.0, a1 = 0.0;
+                if (t < nc) {
+                    int cc = c_lo;
+                    for (; cc + 1 < c_hi; cc += 2) {
+                        a0 = fma(Ws[t + cc * SD_WP], rhs[cc], a0);
+                        a1 = fma(Ws[t + (cc + 1) * SD_WP], rhs[cc + 1], a1);
+                    }
+                    if (cc < c_hi) a0 = fma(Ws[t + cc * SD_WP], rhs[cc], a0);
+                }
+                part[half * CH_NB + t] = a0 + a1;
+            }
+            __syncthreads();
+            if (tid < nc) x[col0 + tid] = part[tid] + part[CH_NB + tid];
+        } else {
+            // y_s - B_s' z, one outgoing segment (= one ancestor) at a time, farthest ancestor first:
+            // thread t owns column t; its slice of the segment's rows is fetched before the wait
+            const double* blk = d.Lv + d.off[s] + nc;           // B(j, c) = blk[j + c*nr]
+            const int* R = d.rows + d.rowptr[s] + nc;
+            for (int e = d.segptr[s + 1] - 1; e >= d.segptr[s]; --e) {
+                const int tgt = d.seg_tid[e];
+                // segment bounds were stored per source in seg_j0/seg_j1; recover them from the rows:
+                // rows of this segment are those owned by tgt
+                const int tcol0 = d.first[tgt], tcol1 = d.first[tgt + 1];
+                // binary search is avoided: in_j0/in_j1 of (tgt <- s) are the same numbers, but indexed by
+                // target; the outgoing copy lives in d.in_* only per target, so scan (segments are short)
+                int j0 = 0, j1 = 0;
+                {
+                    const int rb = nr - nc;
+                    int lo = 0;
+                    while (lo < rb && R[lo] < tcol0) ++lo;
+                    int hi = lo;
+                    while (hi < rb && R[hi] < tcol1) ++hi;
+                    j0 = lo;
+                    j1 = hi;
+                }
+                const int nj = j1 - j0;
+                const int r_lo = half * ((nj + 1) / 2), r_hi = half ? nj : (nj + 1) / 2;
+                double breg[64];
+#pragma unroll
+                for (int rr = 0; rr < 64; ++rr)
+                    breg[rr] = (t < nc && r_lo + rr < r_hi) ? blk[(j0 + r_lo + rr) + (long long)t * nr] : 0.0;
+                sd_wait(flags + tgt, epoch);
+                if (tid < CH_NB) ys[tid] = (tid < nj) ? __ldcg(x + R[j0 + tid]) : 0.0;
+                __syncthreads();
+                double a0 = 0.0, a1 = 0.0;
+#pragma unroll
+                for (int rr = 0; rr < 64; rr += 2) {
+                    a0 = fma(breg[rr], ys[min(r_lo + rr, CH_NB - 1)], a0);
+                    a1 = fma(breg[rr + 1], ys[min(r_lo + rr + 1, CH_NB - 1)], a1);
+                }
+                part[half * CH_NB + t] = a0 + a1;
+                __syncthreads();
+                if (tid < nc) rhs[tid] -= part[tid] + part[CH_NB + tid];
+                __syncthreads();
+            }
+            // z_s = W' rhs
+            {
+                const int c_lo = half * 64, c_hi = min(nc, c_lo + 64);
+                double a0 = 0.0, a1 = 0.0;
+                if (t < nc) {
+                    int cc = c_lo;
+                    for (; cc + 1 < c_hi; cc += 2) {
+                        a0 = fma(Ws[cc + t * SD_WP], rhs[cc], a0);
+                        a1 = fma(Ws[(cc + 1) + t * SD_WP], rhs[cc + 1], a1);
+                    }
+                    if (cc < c_hi) a0 = fma(Ws[cc + t * SD_WP], rhs[cc], a0);
+                }
+                part[half * CH_NB + t] = a0 + a1;
+            }
+            __syncthreads();
+            if (tid < nc) x[col0 + tid] = part[tid] + part[CH_NB + tid];
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) *reinterpret_cast<volatile int*>(flags + s) = epoch;
+    }
+}
+
 static int sparse_configure(nes_ctx* c) {
     static bool done = false;
     if (done) return 0;
     NES_CUDA(c, cudaFuncSetAttribute(snode_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_DIAG_SMEM));
     NES_CUDA(c, cudaFuncSetAttribute(snode_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_TR_SMEM));
     NES_CUDA(c, cudaFuncSetAttribute(snode_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_UP_SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(snode_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (CH_NB * 129 + CH_NB) * 8));
+    NES_CUDA(c, cudaFuncSetAttribute(snode_solve_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SD_SMEM));
     NES_CUDA(c, cudaFuncSetAttribute(snode_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_SOLVE_SMEM));
     NES_CUDA(c, cudaFuncSetAttribute(snode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_SOLVE_SMEM));
     done = true;
@@ -749,6 +1007,12 @@ int sparse_factorize(nes_ctx* c, nes_matrix* A, nes_factor* L) {
     }
     c->minor = sf->m;
     L->factorized = 1;
+    {   // block inverses for the dataflow solve (all supernodes in one launch)
+        StageTimer t(c, NES_STAGE_FACTOR);
+        snode_trtri_kernel<<<sf->nsuper, CH_NB, (CH_NB * 129 + CH_NB) * 8, c->stream>>>(
+            sf->d_L, sf->d_off, sf->d_first, sf->d_nr, sf->d_dinv, sf->d_woff, sf->d_W);
+        NES_CHECK_LAUNCH(c);
+    }
     return 0;
 }
 
@@ -758,6 +1022,23 @@ int sparse_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
     const int m = sf->m;
     gather_perm_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(m, sf->d_perm, d_x, sf->d_x, 0);
     NES_CHECK_LAUNCH(c);
+    if (sf->d_W && sf->d_flags) {
+        SolveDesc d{sf->d_L, sf->d_W, sf->d_off, sf->d_woff, sf->d_first, sf->d_nr, sf->d_rowptr, sf->d_rows,
+                    sf->d_inptr, sf->d_in_s, sf->d_in_j0, sf->d_in_j1, sf->d_segptr, sf->d_seg_tid, sf->nsuper};
+        const int grid = sf->nsuper < c->num_sms ? sf->nsuper : c->num_sms;
+        double* xp = sf->d_x;
+        int* fl = sf->d_flags;
+        for (int transposed = 0; transposed < 2; ++transposed) {
+            int ep = ++sf->flag_epoch;
+            void* args[] = {(void*)&d, (void*)&xp, (void*)&fl, (void*)&ep, (void*)&transposed};
+            NES_CUDA(c, cudaLaunchCooperativeKernel((const void*)snode_solve_dataflow_kernel, dim3(grid),
+                                                    dim3(SD_THREADS), args, SD_SMEM, c->stream));
+            ++c->launches;
+        }
+        gather_perm_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(m, sf->d_perm, sf->d_x, d_x, 1);
+        NES_CHECK_LAUNCH(c);
+        return 0;
+    }
     for (int s = 0; s < sf->nsuper; ++s) {
         const int col0 = sf->first[s], nc = sf->first[s + 1] - col0;
         snode_fwd_kernel<<<1, 256, SN_SOLVE_SMEM, c->stream>>>(sf->d_L, sf->off[s], sf->nr[s], nc, col0,
