@@ -32,7 +32,7 @@ struct nes_batch {
     double *c, *l, *u, *x, *slack, *sc, *g, *theta;  // B*np
     double *b, *r, *t;                               // B*mp
     double* d_scal = nullptr;                        // B*8
-    CUtensorMap mapA, mapM, mapBlk;
+    CUtensorMap mapA, mapM, mapBlk, mapSlab;
 };
 
 enum { BM_SKIP = 0, BM_REPAIR = 1, BM_OPT = 2, BM_CENTER = 3 };
@@ -238,8 +238,7 @@ static int batch_factor(nes_ctx* c, nes_batch* bt) {
     NES_CUDA(c, cudaMemsetAsync(bt->d_info, 0, 2 * B * sizeof(int), c->stream));
     for (int i0 = 0; i0 < m; i0 += 128) {
         const int ib = (m - i0 < 128) ? m - i0 : 128;
-        NES_TRY(chol_panel_launch(c, bt->mapBlk, bt->d_M, (long long)bt->ld, i0, ib, m, bt->d_dinv, bt->d_info,
-                                  B, mp));
+        NES_TRY(chol_panel_launch(c, bt->mapBlk, bt->mapSlab, i0, ib, m, bt->d_dinv, bt->d_info, B, mp));
         const int rest = m - i0 - ib;
         if (rest > 0) {
             const int tr = (rest + NT_BM - 1) / NT_BM;
@@ -330,7 +329,8 @@ nes_batch* nes_batch_create(const double* A_all, int B, int m, int n, const doub
     dev_free(c, stage);
     ok = ok && make_operand_map(&bt->mapA, bt->d_A, (long long)bt->ld, n, (long long)bt->ld) == 0 &&
          make_operand_map(&bt->mapM, bt->d_M, (long long)bt->ld, bt->mp, (long long)bt->ld) == 0 &&
-         make_operand_map(&bt->mapBlk, bt->d_M, (long long)bt->ld, bt->mp, (long long)bt->ld, 128, 128) == 0;
+         make_operand_map(&bt->mapBlk, bt->d_M, (long long)bt->ld, bt->mp, (long long)bt->ld, 128, 128) == 0 &&
+         make_operand_map(&bt->mapSlab, bt->d_M, (long long)bt->ld, bt->mp, (long long)bt->ld, 64, 128) == 0;
     if (!ok) {
         fail(c, NES_ERR_CUDA, "nes_batch_create: setup failed");
         nes_batch_free(&bt, c);

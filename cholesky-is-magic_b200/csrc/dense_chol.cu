@@ -59,69 +59,45 @@ potrf_diag_kernel(const __grid_constant__ CUtensorMap mapBlk, int j0, int jb,
 
 // X L' = B for a 64-row slab of the panel below a full 128x128 diagonal block.
 constexpr int TR_ROWS = 64;
-constexpr int TR_SMEM = (CH_NB * CH_NB + TR_ROWS * CH_NB + CH_NB) * 8;
+constexpr int TR_SMEM = (CH_NB * CH_NB + TR_ROWS * CH_NB + CH_NB) * 8 + 16;
 
-constexpr int TR_THREADS = 256;  // all threads stage L and the slab; threads 0..63 substitute
+constexpr int TR_THREADS = 256;  // 4 threads per row (trsm_slab_smem)
 
+// Operands arrive by TMA: the 128x128 diagonal block (dense box = the Ls layout, upper triangle never
+// read) and the 64x128 slab of the panel (box lands as Xs[p*64 + row], rows past the matrix edge are
+// zero-filled); the solved slab leaves by one TMA store (clipped at the edge).  Thread-issued staging of
+// these 192 KB cost ~12 us per CTA, more than the substitution itself.
 __global__ void __launch_bounds__(TR_THREADS)
-trsm_panel_kernel(double* __restrict__ M, long long ld, int j0, int m, const double* __restrict__ dinv_g,
-                  int brows) {
-    extern __shared__ double sm[];
-    M += blockIdx.y * brows;      // batched mode: this problem's rows
-    dinv_g += blockIdx.y * brows;
+trsm_panel_kernel(const __grid_constant__ CUtensorMap mapBlk, const __grid_constant__ CUtensorMap mapSlab,
+                  int j0, int m, const double* __restrict__ dinv_g, int brows) {
+    extern __shared__ __align__(128) double sm[];
     double* Ls = sm;                       // Ls[c + p*128] = L[c][p]
     double* Xs = Ls + CH_NB * CH_NB;       // Xs[p*64 + row]
     double* dv = Xs + TR_ROWS * CH_NB;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dv + CH_NB);
     const int tid = threadIdx.x;
+    const int brow = blockIdx.y * brows;   // batched mode: this problem's rows
     const int row0 = j0 + CH_NB + blockIdx.x * TR_ROWS;
     const int nrows = min(TR_ROWS, m - row0);
-    const double* Lg = M + j0 + (long long)j0 * ld;
-#pragma unroll 8
-    for (int idx = tid; idx < CH_NB * CH_NB; idx += TR_THREADS) {
-        const int p = idx >> 7, cc = idx & 127;
-        Ls[idx] = (cc >= p) ? Lg[cc + (long long)p * ld] : 0.0;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar, (CH_NB * CH_NB + TR_ROWS * CH_NB) * 8);
+        tma_load_2d(Ls, &mapBlk, brow + j0, j0, bar);
+        tma_load_2d(Xs, &mapSlab, brow + row0, j0, bar);
     }
-    if (tid < CH_NB) dv[tid] = dinv_g[j0 + tid];
-    double* Bg = M + row0 + (long long)j0 * ld;
-#pragma unroll 8
-    for (int idx = tid; idx < TR_ROWS * CH_NB; idx += TR_THREADS) {
-        const int p = idx >> 6, rr = idx & 63;
-        if (rr < nrows) Xs[idx] = Bg[rr + (long long)p * ld];
-    }
+    if (tid < CH_NB) dv[tid] = dinv_g[brow + j0 + tid];
     __syncthreads();
-
-    if (tid < nrows) {
-        for (int cb = 0; cb < CH_NB; cb += 32) {
-            double b[32];
-#pragma unroll
-            for (int cc = 0; cc < 32; ++cc) b[cc] = Xs[(cb + cc) * TR_ROWS + tid];
-            for (int p = 0; p < cb; ++p) {
-                const double xp = Xs[p * TR_ROWS + tid];
-                const double2* lrow = reinterpret_cast<const double2*>(Ls + cb + p * CH_NB);
-#pragma unroll
-                for (int cc = 0; cc < 16; ++cc) {
-                    const double2 l2 = lrow[cc];
-                    b[2 * cc] = fma(-xp, l2.x, b[2 * cc]);
-                    b[2 * cc + 1] = fma(-xp, l2.y, b[2 * cc + 1]);
-                }
-            }
-#pragma unroll
-            for (int cc = 0; cc < 32; ++cc) {
-                const double x = b[cc] * dv[cb + cc];
-                b[cc] = x;
-#pragma unroll
-                for (int c2 = cc + 1; c2 < 32; ++c2)
-                    b[c2] = fma(-x, Ls[(cb + c2) + (cb + cc) * CH_NB], b[c2]);
-            }
-#pragma unroll
-            for (int cc = 0; cc < 32; ++cc) Xs[(cb + cc) * TR_ROWS + tid] = b[cc];
-        }
-    }
+    mbar_wait(bar, 0);
+    trsm_slab_smem(Ls, Xs, dv, CH_NB, nrows);
+    fence_proxy_async();
     __syncthreads();
-#pragma unroll 8
-    for (int idx = tid; idx < TR_ROWS * CH_NB; idx += TR_THREADS) {
-        const int p = idx >> 6, rr = idx & 63;
-        if (rr < nrows) Bg[rr + (long long)p * ld] = Xs[idx];
+    if (tid == 0) {
+        // rows of the slab past the matrix edge are clipped by the tensor map; in batched mode a slab
+        // never crosses into the next problem (row stride is a multiple of 128) and the problem's own
+        // padding rows are stored back unchanged
+        tma_store_2d(&mapSlab, brow + row0, j0, Xs);
+        tma_store_commit_and_wait();
     }
 }
 
@@ -191,7 +167,7 @@ int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L) {
 
 // Diagonal block + TRSM of one 128-column inner panel for `nbatch` stacked problems (brows = row
 // stride between problems; nbatch = 1, brows = 0 for a single matrix).  Used by batch.cu.
-int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, double* M, long long ld, int i0, int ib,
+int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, const CUtensorMap& mapSlab, int i0, int ib,
                       int m, double* dinv, int* info, int nbatch, int brows) {
     NES_TRY(chol_configure(c));
     potrf_diag_kernel<<<dim3(1, nbatch), 256, CH_DIAG_SMEM, c->stream>>>(mapBlk, i0, ib, dinv, c->dbound,
@@ -200,7 +176,7 @@ int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, double* M, long lon
     const int rest = m - i0 - ib;
     if (rest > 0) {
         trsm_panel_kernel<<<dim3((rest + TR_ROWS - 1) / TR_ROWS, nbatch), TR_THREADS, TR_SMEM, c->stream>>>(
-            M, ld, i0, m, dinv, brows);
+            mapBlk, mapSlab, i0, m, dinv, brows);
         NES_CHECK_LAUNCH(c);
     }
     return 0;
@@ -310,7 +286,7 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
                     const int rest = m - i0 - ib;
                     if (rest > 0) {
                         trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM,
-                                            c->stream>>>(L->d_M, ld, i0, m, L->d_dinv, 0);
+                                            c->stream>>>(L->mapBlk, L->mapSlab, i0, m, L->d_dinv, 0);
                         NES_CHECK_LAUNCH(c);
                     }
                 }
@@ -357,7 +333,7 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
             const int rest = m - i0 - ib;
             if (rest > 0) {
                 trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM, c->stream>>>(
-                    L->d_M, ld, i0, m, L->d_dinv, 0);
+                    L->mapBlk, L->mapSlab, i0, m, L->d_dinv, 0);
                 NES_CHECK_LAUNCH(c);
             }
         }

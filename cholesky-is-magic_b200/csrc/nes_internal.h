@@ -173,6 +173,7 @@ struct nes_factor {
     int flag_epoch = 0;
     CUtensorMap mapM;    // 132 x 16 operand boxes (dmma_nt)
     CUtensorMap mapBlk;  // 128 x 128 block boxes (diagonal-block kernels)
+    CUtensorMap mapSlab; // 64 x 128 slabs of a panel (TRSM)
     int factorized = 0;
     nes_matrix* analyzed_for = nullptr;
     // distributed factorization (nranks > 1): tiles of the lower triangle owned by this rank, ordered by
@@ -197,7 +198,7 @@ int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x);
 int matvec(nes_ctx* c, const nes_matrix* A, int transpose, double alpha, const double* d_x,
            double beta, double* d_y);
 // batched building blocks (dense_chol.cu / dense_solve.cu), used by batch.cu
-int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, double* M, long long ld, int i0, int ib,
+int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, const CUtensorMap& mapSlab, int i0, int ib,
                       int m, double* dinv, int* info, int nbatch, int brows);
 int dense_trsv_sweeps(nes_ctx* c, const double* M, long long ld, int m, const double* dinv, double* d_x,
                       int nbatch, int brows);

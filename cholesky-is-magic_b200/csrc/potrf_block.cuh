@@ -183,4 +183,70 @@ __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb
 #endif
 }
 
+
+// X L' = B for a slab of up to 64 rows against a diagonal block of nc <= 128 columns, all operands in
+// shared memory:  Ls[c + p*128] = L(c, p) (zero above the diagonal), Xs[p*64 + row], dv[c] = 1/L(c, c).
+// 256 threads = 4 threads per row (q = tid >> 6): within every 32-column block each thread owns 8
+// columns; contributions of the columns already solved are applied by all four in parallel, the 8x8
+// triangular pieces are solved by their owner.  True substitution (no inverse): the factorization's
+// backward-error bound is untouched.  ~3.3x fewer FMAs on the per-row critical path than one thread
+// per row.
+__device__ __forceinline__ void trsm_slab_smem(const double* Ls, double* Xs, const double* dv, int nc,
+                                               int nrows) {
+    const int tid = threadIdx.x, r = tid & 63, q = tid >> 6;
+    const bool active = r < nrows;
+    for (int cb = 0; cb < nc; cb += 32) {
+        const int c0 = cb + 8 * q;  // my 8 columns of this block
+        double b8[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) b8[i] = (active && c0 + i < nc) ? Xs[(c0 + i) * 64 + r] : 0.0;
+        if (active) {
+            for (int p = 0; p < cb; ++p) {
+                const double xp = Xs[p * 64 + r];
+                const double2* l2 = reinterpret_cast<const double2*>(Ls + c0 + p * 128);
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const double2 lv = l2[i];
+                    b8[2 * i] = fma(-xp, lv.x, b8[2 * i]);
+                    b8[2 * i + 1] = fma(-xp, lv.y, b8[2 * i + 1]);
+                }
+            }
+        }
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+            const int s0 = cb + 8 * qq;  // first column of the sub-block being solved
+            if (q == qq && active) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const double xv = b8[i] * dv[min(s0 + i, 127)];
+                    b8[i] = xv;
+#pragma unroll
+                    for (int i2 = i + 1; i2 < 8; ++i2)
+                        b8[i2] = fma(-xv, Ls[min(s0 + i2, 127) + min(s0 + i, 127) * 128], b8[i2]);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (s0 + i < nc) Xs[(s0 + i) * 64 + r] = b8[i];
+            }
+            __syncthreads();
+            if (q > qq && active && s0 < nc) {
+#pragma unroll
+                for (int pp = 0; pp < 8; ++pp) {
+                    const int p = s0 + pp;
+                    if (p < nc) {
+                        const double xp = Xs[p * 64 + r];
+                        const double2* l2 = reinterpret_cast<const double2*>(Ls + c0 + p * 128);
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const double2 lv = l2[i];
+                            b8[2 * i] = fma(-xp, lv.x, b8[2 * i]);
+                            b8[2 * i + 1] = fma(-xp, lv.y, b8[2 * i + 1]);
+                        }
+                    }
+                }
+            }
+        }
+    }
+}
+
 }  // namespace nes

@@ -480,42 +480,13 @@ snode_trsm_kernel(double* __restrict__ Lv, long long off, int nr, int nc, int co
         const int p = idx >> 7, cc = idx & 127;
         Ls[idx] = (cc >= p && cc < nc) ? blk[cc + (long long)p * nr] : 0.0;
     }
-    if (tid < nc) dv[tid] = dinv_g[col0 + tid];
+    if (tid < CH_NB) dv[tid] = (tid < nc) ? dinv_g[col0 + tid] : 1.0;
     for (int idx = tid; idx < SN_TR_ROWS * nc; idx += 256) {
         const int p = idx >> 6, rr = idx & 63;
         if (rr < nrows) Xs[idx] = blk[row0 + rr + (long long)p * nr];
     }
     __syncthreads();
-    if (tid < nrows) {
-        for (int cb = 0; cb < nc; cb += 32) {
-            double b[32];
-#pragma unroll
-            for (int cc = 0; cc < 32; ++cc) b[cc] = (cb + cc < nc) ? Xs[(cb + cc) * SN_TR_ROWS + tid] : 0.0;
-            for (int p = 0; p < cb; ++p) {
-                const double xp = Xs[p * SN_TR_ROWS + tid];
-                const double2* lrow = reinterpret_cast<const double2*>(Ls + cb + p * CH_NB);
-#pragma unroll
-                for (int cc = 0; cc < 16; ++cc) {
-                    const double2 l2 = lrow[cc];
-                    b[2 * cc] = fma(-xp, l2.x, b[2 * cc]);
-                    b[2 * cc + 1] = fma(-xp, l2.y, b[2 * cc + 1]);
-                }
-            }
-#pragma unroll
-            for (int cc = 0; cc < 32; ++cc) {
-                if (cb + cc < nc) {
-                    const double x = b[cc] * dv[cb + cc];
-                    b[cc] = x;
-#pragma unroll
-                    for (int c2 = cc + 1; c2 < 32; ++c2)
-                        b[c2] = fma(-x, Ls[(cb + c2) + (cb + cc) * CH_NB], b[c2]);
-                }
-            }
-#pragma unroll
-            for (int cc = 0; cc < 32; ++cc)
-                if (cb + cc < nc) Xs[(cb + cc) * SN_TR_ROWS + tid] = b[cc];
-        }
-    }
+    trsm_slab_smem(Ls, Xs, dv, nc, nrows);
     __syncthreads();
     for (int idx = tid; idx < SN_TR_ROWS * nc; idx += 256) {
         const int p = idx >> 6, rr = idx & 63;
