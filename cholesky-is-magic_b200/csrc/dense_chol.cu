@@ -261,6 +261,98 @@ __global__ void info_to_minor_kernel(int* info) {
     if (threadIdx.x == 0 && info[0] == 0) info[1] = 0x7fffffff;
 }
 
+// ---- distributed factorization (1 x Q block-cyclic outer panels) with look-ahead ------------------
+// After panel J has arrived everywhere, the owner of panel J+1 first updates only its tiles of block
+// column J+1, factors that panel and starts its broadcast, and only then updates the rest of its
+// columns; the other ranks update all their columns with panel J and then join the broadcast.  The
+// panel factorization (latency-bound, one GPU) therefore overlaps the other ranks' trailing updates
+// instead of sitting between every two of them.  Collectives are issued in the same order on every
+// rank, on the one stream the kernels use.
+static int dist_factor_panel(nes_ctx* c, nes_factor* L, int J) {
+    const int m = (int)L->m, nbo = L->nbo, j0 = J * nbo;
+    const int jbo = (m - j0 < nbo) ? m - j0 : nbo;
+    const long long ld = (long long)L->ld;
+    for (int i0 = j0; i0 < j0 + jbo; i0 += CH_NB) {
+        const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
+        if (i0 > j0) NES_TRY(chol_update(c, L, i0, i0, m - i0, ib, j0, i0 - j0, 0));
+        potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->mapBlk, i0, ib, L->d_dinv, c->dbound,
+                                                              L->d_info, 0);
+        NES_CHECK_LAUNCH(c);
+        const int rest = m - i0 - ib;
+        if (rest > 0) {
+            trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM, c->stream>>>(
+                L->mapBlk, L->mapSlab, i0, m, L->d_dinv, 0);
+            NES_CHECK_LAUNCH(c);
+        }
+    }
+    const size_t rows = (size_t)(m - j0);
+    NES_CUDA(c, cudaMemcpy2DAsync(L->d_stage, rows * 8, L->d_M + j0 + (long long)j0 * ld, ld * 8, rows * 8, jbo,
+                                  cudaMemcpyDeviceToDevice, c->stream));
+    NES_CUDA(c, cudaMemcpyAsync(L->d_stage + rows * jbo, L->d_dinv + j0, jbo * sizeof(double),
+                                cudaMemcpyDeviceToDevice, c->stream));
+    return 0;
+}
+
+static int dist_exchange_panel(nes_ctx* c, nes_factor* L, int J) {
+    const int m = (int)L->m, nbo = L->nbo, j0 = J * nbo;
+    const int jbo = (m - j0 < nbo) ? m - j0 : nbo;
+    const long long ld = (long long)L->ld;
+    const size_t rows = (size_t)(m - j0);
+    const int owner = dist_owner(J, c->nranks);
+    NES_TRY(dist_broadcast(c, L->d_stage, rows * jbo + jbo, owner));
+    if (c->rank != owner) {
+        NES_CUDA(c, cudaMemcpy2DAsync(L->d_M + j0 + (long long)j0 * ld, ld * 8, L->d_stage, rows * 8, rows * 8,
+                                      jbo, cudaMemcpyDeviceToDevice, c->stream));
+        NES_CUDA(c, cudaMemcpyAsync(L->d_dinv + j0, L->d_stage + rows * jbo, jbo * sizeof(double),
+                                    cudaMemcpyDeviceToDevice, c->stream));
+    }
+    return 0;
+}
+
+// owned tiles [tile_begin, tile_end) -= panel J panel J'
+static int dist_update(nes_ctx* c, nes_factor* L, int J, int tile_begin, int tile_end) {
+    if (tile_begin >= tile_end) return 0;
+    const int m = (int)L->m, nbo = L->nbo, j0 = J * nbo;
+    NtArgs a{};
+    a.C = L->d_M;
+    a.ldc = (long long)L->ld;
+    a.M = a.N = m;
+    a.rowA0 = a.rowB0 = 0;
+    a.k0 = j0;
+    a.K = (m - j0 < nbo) ? m - j0 : nbo;
+    a.alpha = -1.0;
+    a.beta = 1.0;
+    a.same_operand = 1;
+    a.tile_list = L->d_tile_list + tile_begin;
+    a.ntiles = tile_end - tile_begin;
+    cudaError_t e = nt_launch(L->mapM, L->mapM, a, c->num_sms, c->stream);
+    ++c->launches;
+    if (e != cudaSuccess)
+        return fail(c, NES_ERR_CUDA, "distributed update launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L) {
+    const int m = (int)L->m, nbo = L->nbo, P = c->nranks;
+    const int nblk = (m + nbo - 1) / nbo;
+    if (c->rank == dist_owner(0, P)) NES_TRY(dist_factor_panel(c, L, 0));
+    NES_TRY(dist_exchange_panel(c, L, 0));
+    for (int J = 0; J + 1 < nblk; ++J) {
+        const int next = J + 1;
+        const int* tf = L->tile_first.data();
+        if (c->rank == dist_owner(next, P)) {
+            NES_TRY(dist_update(c, L, J, tf[next], tf[next + 1]));       // block column `next` only
+            NES_TRY(dist_factor_panel(c, L, next));
+            NES_TRY(dist_exchange_panel(c, L, next));                     // root of the broadcast
+            NES_TRY(dist_update(c, L, J, tf[next + 1], L->ntiles_owned)); // the rest of my columns
+        } else {
+            NES_TRY(dist_update(c, L, J, tf[next], L->ntiles_owned));
+            NES_TRY(dist_exchange_panel(c, L, next));
+        }
+    }
+    return 0;
+}
+
 int dense_cholesky(nes_ctx* c, nes_factor* L) {
     StageTimer timer(c, NES_STAGE_FACTOR);
     NES_TRY(chol_configure(c));
@@ -269,60 +361,9 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
     const int NBO = dense_outer_block(m);
     const int P = c->nranks;
     NES_CUDA(c, cudaMemsetAsync(L->d_info, 0, 2 * sizeof(int), c->stream));
-    for (int j0 = 0, J = 0; j0 < m; j0 += NBO, ++J) {
+    if (P > 1) NES_TRY(dense_cholesky_dist_steps(c, L));
+    for (int j0 = 0, J = 0; j0 < m && P == 1; j0 += NBO, ++J) {
         const int jbo = (m - j0 < NBO) ? m - j0 : NBO;
-        if (P > 1) {
-            // ---- distributed step: owner factors the panel, everyone receives it, everyone updates
-            // the block columns it owns.
-            const int owner = dist_owner(J, P);
-            const size_t rows = (size_t)(m - j0);
-            if (c->rank == owner) {
-                for (int i0 = j0; i0 < j0 + jbo; i0 += CH_NB) {
-                    const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
-                    if (i0 > j0) NES_TRY(chol_update(c, L, i0, i0, m - i0, ib, j0, i0 - j0, 0));
-                    potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->mapBlk, i0, ib, L->d_dinv,
-                                                                          c->dbound, L->d_info, 0);
-                    NES_CHECK_LAUNCH(c);
-                    const int rest = m - i0 - ib;
-                    if (rest > 0) {
-                        trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM,
-                                            c->stream>>>(L->mapBlk, L->mapSlab, i0, m, L->d_dinv, 0);
-                        NES_CHECK_LAUNCH(c);
-                    }
-                }
-                NES_CUDA(c, cudaMemcpy2DAsync(L->d_stage, rows * 8, L->d_M + j0 + (long long)j0 * ld,
-                                              ld * 8, rows * 8, jbo, cudaMemcpyDeviceToDevice, c->stream));
-                NES_CUDA(c, cudaMemcpyAsync(L->d_stage + rows * jbo, L->d_dinv + j0, jbo * sizeof(double),
-                                            cudaMemcpyDeviceToDevice, c->stream));
-            }
-            NES_TRY(dist_broadcast(c, L->d_stage, rows * jbo + jbo, owner));
-            if (c->rank != owner) {
-                NES_CUDA(c, cudaMemcpy2DAsync(L->d_M + j0 + (long long)j0 * ld, ld * 8, L->d_stage,
-                                              rows * 8, rows * 8, jbo, cudaMemcpyDeviceToDevice, c->stream));
-                NES_CUDA(c, cudaMemcpyAsync(L->d_dinv + j0, L->d_stage + rows * jbo, jbo * sizeof(double),
-                                            cudaMemcpyDeviceToDevice, c->stream));
-            }
-            const int first = L->tile_first[J + 1];
-            if (first < L->ntiles_owned) {
-                NtArgs a{};
-                a.C = L->d_M;
-                a.ldc = ld;
-                a.M = a.N = m;
-                a.rowA0 = a.rowB0 = 0;
-                a.k0 = j0;
-                a.K = jbo;
-                a.alpha = -1.0;
-                a.beta = 1.0;
-                a.same_operand = 1;
-                a.tile_list = L->d_tile_list + first;
-                a.ntiles = L->ntiles_owned - first;
-                cudaError_t e = nt_launch(L->mapM, L->mapM, a, c->num_sms, c->stream);
-                ++c->launches;
-                if (e != cudaSuccess)
-                    return fail(c, NES_ERR_CUDA, "distributed update launch failed: %s", cudaGetErrorString(e));
-            }
-            continue;
-        }
         for (int i0 = j0; i0 < j0 + jbo; i0 += CH_NB) {
             const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
             if (i0 > j0)  // bring block column i0 up to date with the inner panels already factored
