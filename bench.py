@@ -295,7 +295,12 @@ def main():
         ach = (float(m) * m * n) / world / (form_ms / form_cnt * 1e-3) / 1e12  # this rank's share
         roof = {"bound": "tensor", "kernel": "dmma_nt_kernel<true> (fused scale+SYRK)",
                 "achieved": ach, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": ach / FP64_DMMA_PEAK_TFLOPS, "traffic": None,
+                "frac": ach / FP64_DMMA_PEAK_TFLOPS,
+                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at m=8192, n=16384 from
+                # profiles/r01_ncu_full_formation_dmma_nt_m8192.details.txt (ncu --set full); algorithmic
+                # bytes are 8mn + 4m^2 = 1.34e9
+                "traffic": 6.81e9 if (m, n, world) == (8192, 16384, 1) else None,
+                "traffic_unit": "bytes per launch (DRAM read+write, ncu)",
                 "peak_source": "own DMMA issue-rate microbenchmark (tools/dmma_bench.cu, profiles/r01_dmma_peak_and_syrk_v0.log); "
                                "MEASURED_PEAKS.json has no FP64 figure",
                 "step_frac_of_peak": value / world / 1e3 / FP64_DMMA_PEAK_TFLOPS}
