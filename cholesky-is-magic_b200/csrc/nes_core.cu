@@ -333,6 +333,12 @@ int nes_timing_get(nes_ctx* c, int stage, double* ms, long long* count) {
 }
 
 long long nes_get_launch_count(const nes_ctx* c) { return c ? c->launches : 0; }
+int nes_set_ordering_leaf(nes_ctx* c, int leaf) {
+    if (!c) return 0;
+    const int old = c->nd_leaf;
+    c->nd_leaf = leaf < 0 ? 0 : leaf;
+    return old;
+}
 
 int nes_mark_begin(nes_ctx* c) {
     NES_ENTER(c);

@@ -103,6 +103,16 @@ int dist_allreduce_int(nes_ctx* c, int* d_buf, size_t count, int op_max_else_min
     return 0;
 }
 
+int dist_allreduce_sum(nes_ctx* c, double* d_buf, size_t count) {
+    NcclApi* api = nccl_api();
+    if (!api || !c->nccl_comm) return fail(c, NES_ERR_COMM, "NCCL communicator not initialised");
+    ncclResult_t r = api->AllReduce(d_buf, d_buf, count, ncclDouble, ncclSum,
+                                    static_cast<ncclComm_t>(c->nccl_comm), c->stream);
+    if (r != ncclSuccess)
+        return fail(c, NES_ERR_COMM, "ncclAllReduce failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
+    return 0;
+}
+
 }  // namespace nes
 
 using namespace nes;

@@ -28,6 +28,7 @@ struct nes_ctx {
     double rowfacfl = 0, aatfl = 0;
     int blas_ok = 1;
     int minor = -1;
+    int nd_leaf = 0;  // nested-dissection leaf size for sparse analysis (0 = default)
 
     // runtime
     int started = 0;

@@ -92,6 +92,13 @@ __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
 
+// A tensor map that lives in GLOBAL memory (written by a copy, i.e. through the generic proxy) must be
+// acquired by the tensormap proxy before cp.async.bulk.tensor may read it.
+__device__ __forceinline__ void fence_tensormap_acquire(const CUtensorMap* map) {
+    asm volatile("fence.proxy.tensormap::generic.acquire.gpu [%0], 128;" ::"l"(reinterpret_cast<uint64_t>(map))
+                 : "memory");
+}
+
 __device__ __forceinline__ void prefetch_l2(const void* p) {
     asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
 }

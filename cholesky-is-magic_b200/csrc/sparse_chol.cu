@@ -1,413 +1,130 @@
-// K3/K4/K5 for a sparse (CSC) constraint matrix: supernodal Cholesky of A diag(theta) A'.
+// K3/K4/K5 for a sparse (CSC) constraint matrix: supernodal MULTIFRONTAL Cholesky of A diag(theta) A'.
 //
 // Replaces what sparse-newton-solve.lisp / affine-scaling.lisp get from CHOLMOD:
-//   cholmod_analyze    (sparse-cholesky.lisp:509, affine-scaling.lisp:270-271)  -> sparse_analyze  (HOST)
+//   cholmod_analyze    (sparse-cholesky.lisp:509, affine-scaling.lisp:270-271)  -> sparse_analyze  (host: sparse_symbolic.cu)
 //   cholmod_factorize  (sparse-cholesky.lisp:512, 543)                          -> sparse_factorize (GPU)
 //   cholmod_solve/2    (sparse-cholesky.lisp:515, 546)                          -> sparse_solve_inplace
 // and the counters printed by the reference (anz, aatfl, lnz, fl; affine-scaling.lisp:273-279).
 //
-// Symbolic phase (host, once per pattern -- the pattern of A diag(theta) A' never changes):
-//   pattern of tril(A A'), ordering (dense rows last + reverse Cuthill-McKee; CHOLMOD would use AMD --
-//   the factor and the solution do not depend on it beyond rounding, only lnz/fl do), elimination
-//   tree and column structures, fundamental supernodes merged along etree chains with relaxed
-//   amalgamation (<=128 columns, <=15% explicit zeros), per-supernode row lists, relative-index maps for
-//   the updates, and the destination of every entry of tril(A A') in the supernodal storage.
-// Numeric phase (device): owner-computes assembly (one thread per entry of tril(M): merge-join of two
-//   rows of A, so no atomics and bitwise reproducible), then supernodes in ascending (= topological)
-//   order: diagonal block (potrf_block_smem), TRSM of the rows below, and the outer-product update
-//   scattered into the ancestors through the relative maps.
-// Storage: supernode s is a dense nr x nc column-major block (ld = nr) holding its columns of L.
+// Numeric phase.  The assembly tree is processed level by level (nested dissection makes the levels
+// wide: hundreds of independent supernodes at the bottom); every level is three launches over all of
+// its supernodes:
+//   mf_potrf_kernel   one CTA per supernode: diagonal block to shared memory, extend-add of the children's
+//                     update matrices into it, in-smem Cholesky (potrf_block.cuh), write back
+//   mf_trsm_kernel    one CTA per 64-row slab of the rows below: slab to shared memory, extend-add,
+//                     X L' = B by substitution, write back
+//   mf_syrk_kernel    persistent, one CTA per SM, 128 x 128 tiles of the update matrix
+//                     U_s = -L21 L21' on the FP64 tensor cores (DMMA m8n8k4, operands by TMA from a
+//                     per-supernode tensor map, 3-stage mbarrier pipeline), then the extend-add of the
+//                     children's update matrices into the tile
+// Extend-add is OWNER-COMPUTES: the CTA that owns a piece of the parent's front pulls the matching
+// sub-rectangle of every child's update matrix (children in ascending order, coalesced along the
+// child's columns, rows scattered through the parent-relative map), so there are no atomics and the
+// factor is bitwise reproducible.  Original entries of M are assembled straight into the supernode
+// blocks (one thread per entry of tril(M): merge-join of two CSR rows of A with theta).
+// Update matrices live in a pool whose slots are reused as soon as the parent has consumed them.
+//
+// Solves are multifrontal too and level-synchronous: forward, supernode s subtracts its children's update
+// VECTORS from its right-hand side, multiplies by W_s = L_ss^-1 (inverted once per factorization) and
+// leaves u_s = B_s y_s + (children's entries below its columns); backward, it gathers the solution at
+// its rows below, forms y_s - B_s' z and multiplies by W_s'.
+//
+// Multi-GPU (nranks > 1): the symbolic phase maps disjoint subtrees of the assembly tree to ranks
+// (heaviest-first, flops from the symbolic counts) and leaves the top of the tree to everybody.  A rank
+// factors its own subtrees (phase A), publishes the update matrices of its subtree roots with ONE
+// ncclBroadcast (they are contiguous in the pool), and every rank then factors the top redundantly
+// (phase B), so no further exchange is needed; the solves exchange the subtree roots' update vectors
+// the same way and finish with an all-reduce of the solution pieces.
+// Storage: supernode s is a dense nr x nc column-major block (ld = nr rounded up to 16) of L.
 #include <algorithm>
+#include <cstdlib>
 #include <numeric>
-#include <queue>
 
+#include "dmma_nt.cuh"
 #include "nes_internal.h"
 #include "potrf_block.cuh"
+#include "sparse_symbolic.h"
 
 namespace nes {
 
+int dist_allreduce_sum(nes_ctx* c, double* d_buf, size_t count);  // nes_dist.cu
+
+struct MfDesc {
+    double* Lv;
+    double* U;
+    double* dinv;
+    double* W;
+    double* uvec;
+    const long long* off;
+    const long long* uoff;
+    const long long* woff;
+    const long long* vptr;
+    const int* first;
+    const int* nr;
+    const int* ld;
+    const int* ldu;
+    const int* rowptr;
+    const int* rows;
+    const int* childptr;
+    const int* child;
+    const int* relptr;
+    const int* rel;
+    const int* cut;
+    const CUtensorMap* maps;
+    int* info;
+    double dbound;
+    int dbg;
+};
+
+// NES_SPARSE_SYNC=1: synchronise after every launch of the sparse path and name the kernel that failed
+static bool sparse_sync_debug() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("NES_SPARSE_SYNC");
+        v = (e && *e && *e != '0') ? 1 : 0;
+    }
+    return v == 1;
+}
+#define MF_LAUNCHED(c, name)                                                                         \
+    do {                                                                                             \
+        NES_CHECK_LAUNCH(c);                                                                         \
+        if (sparse_sync_debug()) {                                                                   \
+            cudaError_t e2__ = cudaStreamSynchronize((c)->stream);                                   \
+            if (e2__ != cudaSuccess)                                                                 \
+                return nes::fail((c), NES_ERR_CUDA, "%s failed: %s", name, cudaGetErrorString(e2__)); \
+        }                                                                                            \
+    } while (0)
+
+// launch schedule of one phase (A: the supernodes this rank owns, B: the replicated top)
+struct Phase {
+    std::vector<int> pptr, tptr, yptr;  // nlevels + 1 offsets into the task arrays
+    int* d_potrf = nullptr;             // supernode ids, level by level
+    int2* d_trsm = nullptr;             // (supernode, 64-row slab)
+    int4* d_syrk = nullptr;             // (supernode, tile row, tile column, nc)
+    int count = 0;
+};
+
 struct SparseFactor {
+    Symbolic S;
     int m = 0;
-    int nsuper = 0;
-    long long lsize = 0;  // doubles in the supernodal storage
-    // host copies needed to drive the launches
-    std::vector<int> first;       // nsuper+1
-    std::vector<int> nr;          // rows per supernode
-    std::vector<long long> off;   // nsuper+1
-    std::vector<int> rowptr;      // nsuper+1 into rows
-    std::vector<int> segptr;      // nsuper+1 into segments
-    int nseg = 0;
-    long long anz = 0;
-    // device
-    double* d_L = nullptr;
-    double* d_dinv = nullptr;
-    int* d_rows = nullptr;        // concatenated supernode row lists (permuted indices)
-    int* d_seg_t_off = nullptr;   // per segment: nothing but packed params below
-    long long* d_seg_toff = nullptr;  // offset of the target supernode block
-    int* d_seg_tnr = nullptr;     // ld of the target block
-    int* d_seg_tcol0 = nullptr;   // first column of the target supernode
-    int* d_seg_j0 = nullptr;      // below-row range [j0, j1) of s whose rows are columns of the target
-    int* d_seg_j1 = nullptr;
-    int* d_seg_relptr = nullptr;  // offset into d_rel of rel[i - j0], i >= j0
-    int* d_rel = nullptr;
-    int* d_perm = nullptr;        // perm[new] = old
-    // assembly: entry e of tril(P M P'): rows oi, oj of A (original numbering), destination in d_L
+    MfDesc d{};
+    Phase phase[2];
+    // device copies of the symbolic arrays
+    std::vector<void*> owned;  // everything to free
+    int* d_perm = nullptr;
     int* d_ei = nullptr;
     int* d_ej = nullptr;
     long long* d_edest = nullptr;
-    double* d_x = nullptr;        // permuted right-hand side / solution workspace
+    int* d_owner = nullptr;
+    int* d_all = nullptr;      // supernodes factored on this rank (phase A then phase B)
+    int nall = 0;
+    double* d_x = nullptr;
     int* d_info = nullptr;
-    // dataflow solve (one cooperative launch per sweep)
-    int* d_first = nullptr;       // nsuper+1
-    int* d_nr = nullptr;          // nsuper
-    long long* d_off = nullptr;   // nsuper+1
-    int* d_rowptr = nullptr;      // nsuper+1
-    long long* d_woff = nullptr;  // nsuper+1: offsets of the inverted diagonal blocks (nc x nc each)
-    double* d_W = nullptr;
-    int* d_inptr = nullptr;       // nsuper+1: incoming segments of each target supernode, ascending source
-    int* d_in_s = nullptr;
-    int* d_in_j0 = nullptr;
-    int* d_in_j1 = nullptr;
-    int* d_segptr = nullptr;      // nsuper+1 (device copy of segptr)
-    int* d_seg_tid = nullptr;     // target supernode id of each outgoing segment
-    int* d_flags = nullptr;
-    int flag_epoch = 0;
     long long wsize = 0;
+    cudaGraphExec_t graph = nullptr;  // captured factorization (replayed while the operands stay put)
+    const void* graph_theta = nullptr;
+    const void* graph_vals = nullptr;
 };
-
-// ------------------------------------------------------------------------------------------------
-// host: symbolic analysis
-// ------------------------------------------------------------------------------------------------
-static void csc_to_csr(int m, int n, const std::vector<int>& cp, const std::vector<int>& ri,
-                       std::vector<int>& rp, std::vector<int>& cj) {
-    rp.assign(m + 1, 0);
-    cj.resize(ri.size());
-    for (int r : ri) rp[r + 1]++;
-    for (int i = 0; i < m; ++i) rp[i + 1] += rp[i];
-    std::vector<int> next(rp.begin(), rp.end() - 1);
-    for (int j = 0; j < n; ++j)
-        for (int k = cp[j]; k < cp[j + 1]; ++k) cj[next[ri[k]]++] = j;
-}
-
-// full symmetric adjacency of A A' (without the diagonal), sorted per row
-static void aat_pattern(int m, const std::vector<int>& cp, const std::vector<int>& ri,
-                        const std::vector<int>& rp, const std::vector<int>& cj,
-                        std::vector<int>& ap, std::vector<int>& ai, double& aatfl) {
-    ap.assign(m + 1, 0);
-    ai.clear();
-    std::vector<int> mark(m, -1);
-    aatfl = 0;
-    for (size_t j = 0; j + 1 < cp.size(); ++j) {
-        const double c = cp[j + 1] - cp[j];
-        aatfl += c * c;
-    }
-    for (int i = 0; i < m; ++i) {
-        const size_t start = ai.size();
-        mark[i] = i;
-        for (int q = rp[i]; q < rp[i + 1]; ++q) {
-            const int k = cj[q];
-            for (int t = cp[k]; t < cp[k + 1]; ++t) {
-                const int r = ri[t];
-                if (mark[r] != i) {
-                    mark[r] = i;
-                    ai.push_back(r);
-                }
-            }
-        }
-        std::sort(ai.begin() + start, ai.end());
-        ap[i + 1] = (int)ai.size();
-    }
-}
-
-// perm[new] = old.  Rows whose degree exceeds 10 sqrt(m) (at least 16) go last; the rest is ordered by
-// reverse Cuthill-McKee, component by component, starting from a minimum-degree vertex.
-static void order_rcm(int m, const std::vector<int>& ap, const std::vector<int>& ai,
-                      std::vector<int>& perm) {
-    perm.clear();
-    perm.reserve(m);
-    const double thresh = std::max(16.0, 10.0 * std::sqrt((double)m));
-    std::vector<char> dense(m, 0), seen(m, 0);
-    std::vector<int> deg(m);
-    for (int i = 0; i < m; ++i) {
-        deg[i] = ap[i + 1] - ap[i];
-        if (deg[i] > thresh) dense[i] = 1;
-    }
-    std::vector<int> order;
-    order.reserve(m);
-    std::vector<int> byDeg(m);
-    std::iota(byDeg.begin(), byDeg.end(), 0);
-    std::stable_sort(byDeg.begin(), byDeg.end(), [&](int a, int b) { return deg[a] < deg[b]; });
-    std::vector<int> nbr;
-    for (int s : byDeg) {
-        if (seen[s] || dense[s]) continue;
-        size_t head = order.size();
-        order.push_back(s);
-        seen[s] = 1;
-        while (head < order.size()) {
-            const int v = order[head++];
-            nbr.clear();
-            for (int q = ap[v]; q < ap[v + 1]; ++q) {
-                const int u = ai[q];
-                if (!seen[u] && !dense[u]) {
-                    seen[u] = 1;
-                    nbr.push_back(u);
-                }
-            }
-            std::sort(nbr.begin(), nbr.end(), [&](int a, int b) { return deg[a] != deg[b] ? deg[a] < deg[b] : a < b; });
-            order.insert(order.end(), nbr.begin(), nbr.end());
-        }
-    }
-    for (auto it = order.rbegin(); it != order.rend(); ++it) perm.push_back(*it);
-    for (int i = 0; i < m; ++i)
-        if (dense[i]) perm.push_back(i);
-}
-
-int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
-    const MatrixBase* b = A->base;
-    const int m = (int)b->m, n = (int)b->n;
-    std::vector<int> rp, cj;
-    csc_to_csr(m, n, b->h_colptr, b->h_rowidx, rp, cj);
-    std::vector<int> ap, ai;
-    double aatfl = 0;
-    aat_pattern(m, b->h_colptr, b->h_rowidx, rp, cj, ap, ai, aatfl);
-    std::vector<int> perm, iperm(m);
-    order_rcm(m, ap, ai, perm);
-    for (int i = 0; i < m; ++i) iperm[perm[i]] = i;
-
-    // ---- column structures of L (permuted), elimination tree --------------------------------------
-    // below-diagonal pattern of column j of P M P': { iperm[r] : r adjacent to perm[j], iperm[r] > j };
-    // struct(L_j) = that pattern united with struct(L_child) \ {j} over the etree children of j.
-    std::vector<std::vector<int>> lstruct(m);  // below-diagonal rows of L(:, j), sorted
-    std::vector<int> parent(m, -1), colcount(m);
-    std::vector<std::vector<int>> children(m);
-    std::vector<int> mark(m, -1);
-    long long anz = m;
-    {
-        std::vector<int> tmp;
-        for (int j = 0; j < m; ++j) {
-            tmp.clear();
-            mark[j] = j;
-            const int oj = perm[j];
-            for (int q = ap[oj]; q < ap[oj + 1]; ++q) {
-                const int i = iperm[ai[q]];
-                if (i > j && mark[i] != j) {
-                    mark[i] = j;
-                    tmp.push_back(i);
-                }
-            }
-            anz += (long long)tmp.size();
-            for (int ch : children[j])
-                for (int i : lstruct[ch])
-                    if (i > j && mark[i] != j) {
-                        mark[i] = j;
-                        tmp.push_back(i);
-                    }
-            std::sort(tmp.begin(), tmp.end());
-            lstruct[j] = tmp;
-            colcount[j] = (int)tmp.size() + 1;
-            if (!tmp.empty()) {
-                parent[j] = tmp[0];
-                children[tmp[0]].push_back(j);
-            }
-        }
-    }
-    double lnz = 0, fl = 0;
-    for (int j = 0; j < m; ++j) {
-        lnz += colcount[j];
-        fl += (double)colcount[j] * colcount[j];
-    }
-
-    // ---- supernodes: chains parent(j) = j+1 with nested structure, relaxed amalgamation ---------
-    SparseFactor* sf = new SparseFactor();
-    sf->m = m;
-    std::vector<int> first;
-    first.push_back(0);
-    {
-        int f = 0;
-        long long zeros = 0;  // explicit zeros if [f..j] is one supernode with the row set of column j
-        for (int j = 0; j + 1 <= m; ++j) {
-            bool merge = false;
-            if (j + 1 < m && parent[j] == j + 1) {
-                const int width = j + 1 - f + 1;  // width after the merge
-                // rows of the merged supernode = own columns + below-structure of column j+1
-                const long long nrows = width + (long long)lstruct[j + 1].size();
-                long long z = 0;
-                for (int q = f; q <= j + 1; ++q) z += (nrows - (q - f)) - colcount[q];
-                const long long total = nrows * width - (long long)width * (width - 1) / 2;
-                if (width <= CH_NB && (width <= 4 || z <= 0.15 * total)) {
-                    merge = true;
-                    zeros = z;
-                }
-            }
-            if (!merge) {
-                first.push_back(j + 1);
-                f = j + 1;
-                zeros = 0;
-            }
-        }
-        (void)zeros;
-    }
-    const int nsuper = (int)first.size() - 1;
-    sf->nsuper = nsuper;
-    sf->first = first;
-    std::vector<int> col2sn(m);
-    sf->nr.resize(nsuper);
-    sf->off.assign(nsuper + 1, 0);
-    sf->rowptr.assign(nsuper + 1, 0);
-    std::vector<int> rows;
-    for (int s = 0; s < nsuper; ++s) {
-        const int f = first[s], l = first[s + 1] - 1;
-        for (int j = f; j <= l; ++j) {
-            col2sn[j] = s;
-            rows.push_back(j);
-        }
-        for (int i : lstruct[l]) rows.push_back(i);
-        sf->nr[s] = (l - f + 1) + (int)lstruct[l].size();
-        sf->rowptr[s + 1] = (int)rows.size();
-        sf->off[s + 1] = sf->off[s] + (long long)sf->nr[s] * (l - f + 1);
-    }
-    sf->lsize = sf->off[nsuper];
-
-    // ---- update segments + relative maps -------------------------------------------------------
-    std::vector<long long> seg_toff;
-    std::vector<int> seg_tnr, seg_tcol0, seg_j0, seg_j1, seg_relptr, rel, seg_tid, seg_src;
-    sf->segptr.assign(nsuper + 1, 0);
-    for (int s = 0; s < nsuper; ++s) {
-        const int nc = first[s + 1] - first[s];
-        const int* R = rows.data() + sf->rowptr[s];
-        const int rb = sf->nr[s] - nc;
-        int j = 0;
-        while (j < rb) {
-            const int t = col2sn[R[nc + j]];
-            int j1 = j;
-            while (j1 < rb && col2sn[R[nc + j1]] == t) ++j1;
-            seg_toff.push_back(sf->off[t]);
-            seg_tid.push_back(t);
-            seg_src.push_back(s);
-            seg_tnr.push_back(sf->nr[t]);
-            seg_tcol0.push_back(first[t]);
-            seg_j0.push_back(j);
-            seg_j1.push_back(j1);
-            seg_relptr.push_back((int)rel.size());
-            const int* Rt = rows.data() + sf->rowptr[t];
-            const int nrt = sf->nr[t];
-            int p = 0;
-            for (int i = j; i < rb; ++i) {
-                while (p < nrt && Rt[p] < R[nc + i]) ++p;
-                if (p >= nrt || Rt[p] != R[nc + i]) {
-                    delete sf;
-                    return fail(c, NES_ERR_INVALID, "symbolic analysis: row %d of supernode %d missing in ancestor %d",
-                                R[nc + i], s, t);
-                }
-                rel.push_back(p);
-            }
-            j = j1;
-        }
-        sf->segptr[s + 1] = (int)seg_toff.size();
-    }
-    sf->nseg = (int)seg_toff.size();
-    // incoming segments per target (sources ascending because segments are generated in source order)
-    std::vector<int> inptr(nsuper + 1, 0), in_s(sf->nseg), in_j0(sf->nseg), in_j1(sf->nseg);
-    for (int q = 0; q < sf->nseg; ++q) inptr[seg_tid[q] + 1]++;
-    for (int t = 0; t < nsuper; ++t) inptr[t + 1] += inptr[t];
-    {
-        std::vector<int> next(inptr.begin(), inptr.end() - 1);
-        for (int q = 0; q < sf->nseg; ++q) {
-            const int p = next[seg_tid[q]]++;
-            in_s[p] = seg_src[q];
-            in_j0[p] = seg_j0[q];
-            in_j1[p] = seg_j1[q];
-        }
-    }
-    std::vector<long long> woff(nsuper + 1, 0);
-    for (int t = 0; t < nsuper; ++t) {
-        const long long nc = first[t + 1] - first[t];
-        woff[t + 1] = woff[t] + nc * nc;
-    }
-    sf->wsize = woff[nsuper];
-
-    // ---- assembly map: every entry (i >= j) of tril(P M P') -> position in the supernodal storage
-    std::vector<int> ei, ej;
-    std::vector<long long> edest;
-    ei.reserve(anz);
-    ej.reserve(anz);
-    edest.reserve(anz);
-    {
-        std::vector<int> col;
-        for (int j = 0; j < m; ++j) {
-            const int s = col2sn[j];
-            const int* R = rows.data() + sf->rowptr[s];
-            const int nrs = sf->nr[s];
-            const long long base = sf->off[s] + (long long)(j - first[s]) * nrs;
-            col.clear();
-            col.push_back(j);
-            const int oj = perm[j];
-            for (int q = ap[oj]; q < ap[oj + 1]; ++q) {
-                const int i = iperm[ai[q]];
-                if (i > j) col.push_back(i);
-            }
-            std::sort(col.begin(), col.end());
-            int p = 0;
-            for (int i : col) {
-                while (p < nrs && R[p] < i) ++p;
-                ei.push_back(perm[i]);
-                ej.push_back(oj);
-                edest.push_back(base + p);
-            }
-        }
-    }
-    sf->anz = (long long)ei.size();
-
-    // ---- upload -------------------------------------------------------------------------------
-    auto up_i = [&](int** dst, const std::vector<int>& v) {
-        *dst = static_cast<int*>(dev_alloc(c, (v.size() + 1) * sizeof(int)));
-        return *dst && upload(c, *dst, v.data(), v.size() * sizeof(int)) == 0;
-    };
-    auto up_l = [&](long long** dst, const std::vector<long long>& v) {
-        *dst = static_cast<long long*>(dev_alloc(c, (v.size() + 1) * sizeof(long long)));
-        return *dst && upload(c, *dst, v.data(), v.size() * sizeof(long long)) == 0;
-    };
-    L->sparse = sf;
-    bool ok = up_i(&sf->d_rows, rows) && up_l(&sf->d_seg_toff, seg_toff) && up_i(&sf->d_seg_tnr, seg_tnr) &&
-              up_i(&sf->d_seg_tcol0, seg_tcol0) && up_i(&sf->d_seg_j0, seg_j0) && up_i(&sf->d_seg_j1, seg_j1) &&
-              up_i(&sf->d_seg_relptr, seg_relptr) && up_i(&sf->d_rel, rel) && up_i(&sf->d_perm, perm) &&
-              up_i(&sf->d_ei, ei) && up_i(&sf->d_ej, ej) && up_l(&sf->d_edest, edest) &&
-              up_i(&sf->d_first, first) && up_i(&sf->d_nr, sf->nr) && up_l(&sf->d_off, sf->off) &&
-              up_i(&sf->d_rowptr, sf->rowptr) && up_l(&sf->d_woff, woff) && up_i(&sf->d_inptr, inptr) &&
-              up_i(&sf->d_in_s, in_s) && up_i(&sf->d_in_j0, in_j0) && up_i(&sf->d_in_j1, in_j1) &&
-              up_i(&sf->d_segptr, sf->segptr) && up_i(&sf->d_seg_tid, seg_tid);
-    if (ok) {
-        sf->d_L = static_cast<double*>(dev_alloc(c, (size_t)(sf->lsize + 16) * sizeof(double)));
-        sf->d_dinv = static_cast<double*>(dev_alloc(c, (size_t)(m + 16) * sizeof(double)));
-        sf->d_x = static_cast<double*>(dev_alloc(c, (size_t)(m + 16) * sizeof(double)));
-        sf->d_info = static_cast<int*>(dev_alloc(c, 4 * sizeof(int)));
-        sf->d_W = static_cast<double*>(dev_alloc(c, (size_t)(sf->wsize + 16) * sizeof(double)));
-        sf->d_flags = static_cast<int*>(dev_alloc(c, (size_t)(nsuper + 1) * sizeof(int)));
-        L->d_rhs = static_cast<double*>(dev_alloc(c, (size_t)(m + 16) * sizeof(double)));
-        ok = sf->d_L && sf->d_dinv && sf->d_x && sf->d_info && L->d_rhs && sf->d_W && sf->d_flags;
-        if (ok) cudaMemsetAsync(sf->d_flags, 0, (size_t)(nsuper + 1) * sizeof(int), c->stream);
-    }
-    if (!ok) return c->status < 0 ? c->status : NES_ERR_OUT_OF_MEMORY;
-    c->anz = (double)sf->anz;
-    c->aatfl = aatfl;
-    c->lnz = lnz;
-    c->fl = fl;
-    c->status = 0;
-    return 0;
-}
-
-void sparse_free(nes_ctx* c, nes_factor* L) {
-    SparseFactor* sf = L->sparse;
-    if (!sf) return;
-    void* ptrs[] = {sf->d_L, sf->d_dinv, sf->d_rows, sf->d_seg_toff, sf->d_seg_tnr, sf->d_seg_tcol0,
-                    sf->d_seg_j0, sf->d_seg_j1, sf->d_seg_relptr, sf->d_rel, sf->d_perm, sf->d_ei,
-                    sf->d_ej, sf->d_edest, sf->d_x, sf->d_info, sf->d_first, sf->d_nr, sf->d_off, sf->d_rowptr,
-                    sf->d_woff, sf->d_W, sf->d_inptr, sf->d_in_s, sf->d_in_j0, sf->d_in_j1, sf->d_segptr,
-                    sf->d_seg_tid, sf->d_flags};
-    for (void* p : ptrs) dev_free(c, p);
-    delete sf;
-    L->sparse = nullptr;
-}
 
 // ------------------------------------------------------------------------------------------------
 // device: numeric factorization
@@ -439,299 +156,266 @@ __global__ void sparse_assemble_kernel(long long anz, const int* __restrict__ ei
     Lv[edest[e]] = acc;
 }
 
-constexpr int SN_DIAG_SMEM = (CH_NB * CH_P + CH_NB) * 8;
 
+__device__ __forceinline__ int lower_bound_dev(const int* __restrict__ a, int lo, int hi, int key) {
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (a[mid] < key) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
+constexpr int MF_DIAG_SMEM = (CH_NB * CH_P + CH_NB) * 8;
+
+// Diagonal block of every supernode of a level: load, extend-add, Cholesky, store.
 __global__ void __launch_bounds__(256)
-snode_potrf_kernel(double* __restrict__ Lv, long long off, int nr, int nc, int col0,
-                   double* __restrict__ dinv_out, double dbound, int* __restrict__ info) {
+mf_potrf_kernel(const MfDesc d, const int* __restrict__ list) {
     extern __shared__ __align__(128) double S[];
     double* dinv = S + CH_NB * CH_P;
     const int tid = threadIdx.x;
-    double* blk = Lv + off;
+    const int s = list[blockIdx.x];
+    const int col0 = d.first[s], nc = d.first[s + 1] - col0, ld = d.ld[s];
+    double* blk = d.Lv + d.off[s];
     for (int idx = tid; idx < nc * nc; idx += 256) {
         const int cc = idx / nc, r = idx - cc * nc;
-        if (r >= cc) S[r + cc * CH_P] = blk[r + (long long)cc * nr];
+        if (r >= cc) S[r + cc * CH_P] = blk[r + (long long)cc * ld];
     }
     __syncthreads();
-    potrf_block_smem(S, dinv, nc, dbound, info, col0);
+    for (int q = d.childptr[s]; q < d.childptr[s + 1]; ++q) {
+        const int c = d.child[q];
+        const int cutc = d.cut[c];
+        const double* Uc = d.U + d.uoff[c];
+        const int lduc = d.ldu[c];
+        const int* rl = d.rel + d.relptr[c];
+        for (int idx = tid; idx < cutc * cutc; idx += 256) {
+            const int j = idx / cutc, i = idx - j * cutc;
+            if (i >= j) S[rl[i] + rl[j] * CH_P] += Uc[i + (long long)j * lduc];
+        }
+        __syncthreads();
+    }
+    potrf_block_smem(S, dinv, nc, d.dbound, d.info, col0);
+    __syncthreads();
     for (int idx = tid; idx < nc * nc; idx += 256) {
         const int cc = idx / nc, r = idx - cc * nc;
-        if (r >= cc) blk[r + (long long)cc * nr] = S[r + cc * CH_P];
+        if (r >= cc) blk[r + (long long)cc * ld] = S[r + cc * CH_P];
     }
-    if (tid < nc) dinv_out[col0 + tid] = dinv[tid];
+    if (tid < nc) d.dinv[col0 + tid] = dinv[tid];
 }
 
-// X L' = B for the rows below the diagonal block of a supernode (nc <= 128 columns).
-constexpr int SN_TR_ROWS = 64;
-constexpr int SN_TR_SMEM = (CH_NB * CH_NB + SN_TR_ROWS * CH_NB + CH_NB) * 8;
+// Rows below the diagonal block, 64 at a time: load, extend-add, X L' = B, store.
+constexpr int MF_TR_ROWS = 64;
+constexpr int MF_TR_SMEM = (CH_NB * CH_NB + MF_TR_ROWS * CH_NB + CH_NB) * 8;
 
 __global__ void __launch_bounds__(256)
-snode_trsm_kernel(double* __restrict__ Lv, long long off, int nr, int nc, int col0,
-                  const double* __restrict__ dinv_g) {
+mf_trsm_kernel(const MfDesc d, const int2* __restrict__ tasks) {
     extern __shared__ double sm[];
     double* Ls = sm;                        // Ls[c + p*128] = L[c][p]
     double* Xs = Ls + CH_NB * CH_NB;        // Xs[p*64 + row]
-    double* dv = Xs + SN_TR_ROWS * CH_NB;
+    double* dv = Xs + MF_TR_ROWS * CH_NB;
     const int tid = threadIdx.x;
-    const int row0 = nc + blockIdx.x * SN_TR_ROWS;
-    const int nrows = min(SN_TR_ROWS, nr - row0);
-    double* blk = Lv + off;
+    const int s = tasks[blockIdx.x].x;
+    const int col0 = d.first[s], nc = d.first[s + 1] - col0, nr = d.nr[s], ld = d.ld[s];
+    const int row0 = nc + tasks[blockIdx.x].y * MF_TR_ROWS;
+    const int nrows = min(MF_TR_ROWS, nr - row0);
+    double* blk = d.Lv + d.off[s];
     for (int idx = tid; idx < nc * CH_NB; idx += 256) {
         const int p = idx >> 7, cc = idx & 127;
-        Ls[idx] = (cc >= p && cc < nc) ? blk[cc + (long long)p * nr] : 0.0;
+        Ls[idx] = (cc >= p && cc < nc) ? blk[cc + (long long)p * ld] : 0.0;
     }
-    if (tid < CH_NB) dv[tid] = (tid < nc) ? dinv_g[col0 + tid] : 1.0;
-    for (int idx = tid; idx < SN_TR_ROWS * nc; idx += 256) {
+    if (tid < CH_NB) dv[tid] = (tid < nc) ? d.dinv[col0 + tid] : 1.0;
+    for (int idx = tid; idx < MF_TR_ROWS * nc; idx += 256) {
         const int p = idx >> 6, rr = idx & 63;
-        if (rr < nrows) Xs[idx] = blk[row0 + rr + (long long)p * nr];
+        Xs[idx] = (rr < nrows) ? blk[row0 + rr + (long long)p * ld] : 0.0;
     }
     __syncthreads();
+    for (int q = d.childptr[s]; q < d.childptr[s + 1]; ++q) {
+        const int c = d.child[q];
+        const int cutc = d.cut[c];
+        const int nuc = d.nr[c] - (d.first[c + 1] - d.first[c]);
+        const int* rl = d.rel + d.relptr[c];
+        const int ilo = lower_bound_dev(rl, cutc, nuc, row0);
+        const int ihi = lower_bound_dev(rl, ilo, nuc, row0 + nrows);
+        const int ni = ihi - ilo;
+        if (ni <= 0) continue;  // uniform over the CTA
+        const double* Uc = d.U + d.uoff[c];
+        const int lduc = d.ldu[c];
+        for (int idx = tid; idx < ni * cutc; idx += 256) {
+            const int j = idx / ni, i = ilo + idx - j * ni;
+            Xs[rl[j] * MF_TR_ROWS + rl[i] - row0] += Uc[i + (long long)j * lduc];
+        }
+        __syncthreads();
+    }
     trsm_slab_smem(Ls, Xs, dv, nc, nrows);
     __syncthreads();
-    for (int idx = tid; idx < SN_TR_ROWS * nc; idx += 256) {
+    for (int idx = tid; idx < MF_TR_ROWS * nc; idx += 256) {
         const int p = idx >> 6, rr = idx & 63;
-        if (rr < nrows) blk[row0 + rr + (long long)p * nr] = Xs[idx];
+        if (rr < nrows) blk[row0 + rr + (long long)p * ld] = Xs[idx];
     }
 }
 
-// Outer-product update of the ancestors: for segment q of supernode s (rows j0..j1 of the below part
-// are columns of ancestor t), U(i, j) = sum_c B(i,c) B(j,c) for i >= j, j in [j0, j1), is subtracted
-// from L_t at (rel[i - j0], column R[j] - first[t]).  grid = (row tiles of 64, segments of s).
-// Each CTA stages the 64-row slab and the segment's rows of B in shared memory (k <= 128).
-constexpr int SN_UP_ROWS = 64;
-constexpr int SN_UP_SMEM = (SN_UP_ROWS * (CH_NB + 1) + CH_NB * (CH_NB + 1)) * 8;
-
-__global__ void __launch_bounds__(256)
-snode_update_kernel(double* __restrict__ Lv, long long off, int nr, int nc, const int* __restrict__ rows,
-                    int seg0, const long long* __restrict__ seg_toff, const int* __restrict__ seg_tnr,
-                    const int* __restrict__ seg_tcol0, const int* __restrict__ seg_j0,
-                    const int* __restrict__ seg_j1, const int* __restrict__ seg_relptr,
-                    const int* __restrict__ rel) {
-    extern __shared__ double sm[];
-    const int P = CH_NB + 1;
-    double* Bi = sm;                    // Bi[r * P + c], 64 rows of the slab
-    double* Bj = Bi + SN_UP_ROWS * P;   // Bj[j * P + c], the segment's rows (<= 128)
-    const int seg = seg0 + blockIdx.y;
-    const int j0 = seg_j0[seg], j1 = seg_j1[seg];
-    const int rb = nr - nc;
-    const int i0 = j0 + blockIdx.x * SN_UP_ROWS;
-    if (i0 >= rb) return;
-    const int ni = min(SN_UP_ROWS, rb - i0);
-    const int nj = j1 - j0;
-    const int tid = threadIdx.x;
-    const double* B = Lv + off + nc;  // B(i, c) = B[i + c*nr]
-    for (int idx = tid; idx < SN_UP_ROWS * nc; idx += 256) {
-        const int cc = idx >> 6, r = idx & 63;
-        Bi[r * P + cc] = (r < ni) ? B[i0 + r + (long long)cc * nr] : 0.0;
-    }
-    for (int idx = tid; idx < nj * nc; idx += 256) {
-        const int cc = idx / nj, j = idx - cc * nj;
-        Bj[j * P + cc] = B[j0 + j + (long long)cc * nr];
+// Update matrices of a level on the FP64 tensor cores.  Task = (supernode, tile row bi, tile column
+// bj <= bi, nc): U(bi, bj) = -L21[bi] L21[bj]' with K = nc <= 128, then the extend-add of the children.
+// Same pipeline as dmma_nt_kernel (thread 0 doubles as the TMA producer, 8 DMMA warps of 64 x 32, 132-row
+// boxes so the fragment loads are conflict-free); the tensor map of the supernode's block comes from
+// a device array, rows past the block and columns past nc are zero-filled by TMA.
+__global__ void __launch_bounds__(NT_THREADS, 1)
+mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(
+        (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NT_STAGES * NT_STAGE_BYTES);
+    uint64_t* empty = full + NT_STAGES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const bool is_producer = (threadIdx.x == 0);
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < NT_STAGES; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], NT_CONSUMER_WARPS);
+        }
+        fence_mbar_init();
     }
     __syncthreads();
-    // thread (ti, tj): rows ti + 16a (a < 4), cols tj + 16b (b < 8)
-    const int ti = tid & 15, tj = tid >> 4;
-    double acc[4][8];
-#pragma unroll
-    for (int a = 0; a < 4; ++a)
-#pragma unroll
-        for (int b2 = 0; b2 < 8; ++b2) acc[a][b2] = 0.0;
-    const int nb = (nj + 15) >> 4;
-    for (int cc = 0; cc < nc; ++cc) {
-        double xi[4];
-#pragma unroll
-        for (int a = 0; a < 4; ++a) xi[a] = Bi[(ti + 16 * a) * P + cc];
-#pragma unroll
-        for (int b2 = 0; b2 < 8; ++b2) {
-            if (b2 < nb) {
-                const double xj = Bj[min(tj + 16 * b2, CH_NB - 1) * P + cc];
-#pragma unroll
-                for (int a = 0; a < 4; ++a) acc[a][b2] = fma(xi[a], xj, acc[a][b2]);
+
+    int p_task = blockIdx.x, p_kc = 0, p_kch = 0;
+    int4 pt = make_int4(0, 0, 0, 0);
+    uint32_t p_it = 0;
+    bool p_valid = false;
+    if (is_producer && p_task < ntasks) {
+        pt = tasks[p_task];
+        p_kch = (pt.w + NT_BK - 1) / NT_BK;
+        p_valid = true;
+    }
+    auto produce = [&]() {
+        if (!p_valid) return;
+        const int st_i = p_it % NT_STAGES;
+        const uint32_t ph = (p_it / NT_STAGES) & 1;
+        mbar_wait(&empty[st_i], ph ^ 1);
+        const bool diag = (pt.y == pt.z);
+        uint8_t* st = smem + st_i * NT_STAGE_BYTES;
+        mbar_expect_tx(&full[st_i], diag ? NT_TILE_BYTES : 2 * NT_TILE_BYTES);
+        const CUtensorMap* mp = d.maps + pt.x;
+        if (p_kc == 0) fence_tensormap_acquire(mp);
+        // the box must start on a 16-byte boundary (an odd row coordinate of an 8-byte type is an illegal
+        // instruction, measured: tools/tma_gmem_probe.cu): start one row early when nc is odd and let the
+        // consumers skip that row (the box has 132 rows for 128 used)
+        const int r0 = pt.w & ~1;
+        tma_load_2d(st, mp, r0 + pt.y * NT_BM, p_kc * NT_BK, &full[st_i]);
+        if (!diag) tma_load_2d(st + NT_TILE_BYTES, mp, r0 + pt.z * NT_BN, p_kc * NT_BK, &full[st_i]);
+        ++p_it;
+        if (++p_kc >= p_kch) {
+            p_task += gridDim.x;
+            p_kc = 0;
+            p_valid = p_task < ntasks;
+            if (p_valid) {
+                pt = tasks[p_task];
+                p_kch = (pt.w + NT_BK - 1) / NT_BK;
             }
         }
-    }
-    double* T = Lv + seg_toff[seg];
-    const int tnr = seg_tnr[seg], tcol0 = seg_tcol0[seg];
-    const int* relp = rel + seg_relptr[seg];
+    };
+    if (is_producer && !(d.dbg & 4))
+        for (int i = 0; i < NT_STAGES - 1; ++i) produce();
+
+    const int g = lane >> 2, t4 = lane & 3;
+    const int wm = warp >> 2, wn = warp & 3;
+    const int a_off = t4 * NT_PITCH + wm * 64 + g;
+    const int b_off = t4 * NT_PITCH + wn * 32 + g;
+    uint32_t it = 0;
+    for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
+        const int4 tk = tasks[t];
+        const int s = tk.x, bi = tk.y, bj = tk.z, nc = tk.w;
+        const int kch = (nc + NT_BK - 1) / NT_BK;
+        const bool diag = (bi == bj);
+        double acc[8][4][2];
 #pragma unroll
-    for (int a = 0; a < 4; ++a) {
-        const int i = i0 + ti + 16 * a;  // below-row index of s
-        if (i >= rb) continue;
-        const int trow = relp[i - j0];
+        for (int i = 0; i < 8; ++i)
 #pragma unroll
-        for (int b2 = 0; b2 < 8; ++b2) {
-            const int j = j0 + tj + 16 * b2;
-            if (j < j1 && j <= i) {
-                const int tcol = rows[nc + j] - tcol0;
-                T[trow + (long long)tcol * tnr] -= acc[a][b2];
+            for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+        for (int kc = 0; kc < kch && !(d.dbg & 4); ++kc, ++it) {
+            if (is_producer) produce();
+            __syncwarp();
+            const int st_i = it % NT_STAGES;
+            const uint32_t ph = (it / NT_STAGES) & 1;
+            mbar_wait(&full[st_i], ph);
+            const double* sA = reinterpret_cast<const double*>(smem + st_i * NT_STAGE_BYTES);
+            const double* sB = diag ? sA : sA + NT_PITCH * NT_BK;
+            const double* ap = sA + a_off + (nc & 1);
+            const double* bp = sB + b_off + (nc & 1);
+#pragma unroll
+            for (int ks = 0; ks < NT_BK / 4; ++ks) {
+                double af[8], bf[4];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) af[i] = ap[ks * 4 * NT_PITCH + i * 8];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) bf[j] = bp[ks * 4 * NT_PITCH + j * 8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[st_i]);
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// device: triangular solves, one CTA per supernode
-// ------------------------------------------------------------------------------------------------
-__global__ void gather_perm_kernel(int m, const int* __restrict__ perm, const double* __restrict__ src,
-                                   double* __restrict__ dst, int inverse) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
-    if (!inverse) dst[i] = src[perm[i]];   // y = P b
-    else dst[perm[i]] = src[i];            // x = P' y
-}
-
-// Triangular solve with a diagonal block staged in shared memory (column-major, pitch SN_SP), 128
-// "unknown" threads (tid < 128 own v), four 32x32 sub-blocks: one warp per sub-block with shuffles
-// (lane = row), then a rank-32 update of the other unknowns.  Same scheme as trsv_diag_kernel.
-constexpr int SN_SP = 130;
-constexpr int SN_SOLVE_SMEM = (CH_NB * SN_SP + 2 * CH_NB) * 8;
-
-__device__ __forceinline__ double snode_tri_solve(const double* S, double* xs, double v, double di, int nc,
-                                                  bool transposed) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (!transposed) {
-        for (int sb = 0; sb < CH_NB / 32; ++sb) {
-            const int base = 32 * sb;
-            if (base >= nc) break;
-            if (warp == sb) {
-#pragma unroll 8
-                for (int cc = 0; cc < 32; ++cc) {
-                    const double xc = __shfl_sync(0xffffffffu, v * di, cc);
-                    if (lane == cc) v = xc;
-                    else if (lane > cc && base + lane < nc) v = fma(-S[(base + lane) + (base + cc) * SN_SP], xc, v);
+        // epilogue: U tile = -acc (whole tile inside the matrix; only i >= j is ever read)
+        const int nu = d.nr[s] - nc, ldu = d.ldu[s];
+        double* Us = d.U + d.uoff[s];
+        const int row_base = bi * NT_BM + wm * 64 + g;
+        const int col_base = bj * NT_BN + wn * 32 + 2 * t4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+#pragma unroll
+            for (int c2 = 0; c2 < 2; ++c2) {
+                const int col = col_base + j * 8 + c2;
+                if (col < nu && !(d.dbg & 2)) {
+                    double* cp = Us + (long long)col * ldu;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) {
+                        const int row = row_base + i * 8;
+                        if (row < nu) cp[row] = -acc[i][j][c2];
+                    }
                 }
-                xs[base + lane] = v;
+            }
+        const int q0 = d.childptr[s], q1 = d.childptr[s + 1];
+        if (q0 == q1 || (d.dbg & 1)) continue;
+        __syncthreads();  // the tile is complete (and visible to the whole CTA) before the children are added
+        const int r_lo = nc + bi * NT_BM, c_lo = nc + bj * NT_BN;
+        for (int q = q0; q < q1; ++q) {
+            const int c = d.child[q];
+            const int cutc = d.cut[c];
+            const int nuc = d.nr[c] - (d.first[c + 1] - d.first[c]);
+            const int* rl = d.rel + d.relptr[c];
+            const int jlo = lower_bound_dev(rl, cutc, nuc, c_lo);
+            const int jhi = lower_bound_dev(rl, jlo, nuc, c_lo + NT_BN);
+            const int ilo = diag ? jlo : lower_bound_dev(rl, jhi, nuc, r_lo);
+            const int ihi = diag ? jhi : lower_bound_dev(rl, ilo, nuc, r_lo + NT_BM);
+            const int ni = ihi - ilo, nj = jhi - jlo;
+            if (ni <= 0 || nj <= 0) continue;  // uniform over the CTA
+            const double* Uc = d.U + d.uoff[c];
+            const int lduc = d.ldu[c];
+            for (int idx = threadIdx.x; idx < ni * nj; idx += NT_THREADS) {
+                const int jj = idx / ni, i = ilo + idx - jj * ni, j = jlo + jj;
+                if (i >= j) Us[(rl[i] - nc) + (long long)(rl[j] - nc) * ldu] += Uc[i + (long long)j * lduc];
             }
             __syncthreads();
-            if (tid >= base + 32 && tid < nc) {
-                double acc = 0.0;
-#pragma unroll 8
-                for (int cc = 0; cc < 32; ++cc) acc = fma(S[tid + (base + cc) * SN_SP], xs[base + cc], acc);
-                v -= acc;
-            }
-        }
-    } else {
-        for (int sb = CH_NB / 32 - 1; sb >= 0; --sb) {
-            const int base = 32 * sb;
-            if (base >= nc) continue;
-            if (warp == sb) {
-#pragma unroll 8
-                for (int cc = 31; cc >= 0; --cc) {
-                    const double xc = __shfl_sync(0xffffffffu, v * di, cc);
-                    if (lane == cc) v = xc;
-                    else if (lane < cc && base + cc < nc)
-                        v = fma(-S[(base + cc) + (base + lane) * SN_SP], xc, v);
-                }
-                xs[base + lane] = v;
-            }
-            __syncthreads();
-            if (tid < base) {
-                double acc = 0.0;
-#pragma unroll 8
-                for (int cc = 0; cc < 32; ++cc)
-                    if (base + cc < nc) acc = fma(S[(base + cc) + tid * SN_SP], xs[base + cc], acc);
-                v -= acc;
-            }
         }
     }
-    return v;
 }
 
-// forward: x_s <- L_ss^-1 x_s ; x[rows below] -= B x_s.   One CTA (256 threads) per supernode.
-__global__ void __launch_bounds__(256)
-snode_fwd_kernel(const double* __restrict__ Lv, long long off, int nr, int nc, int col0,
-                 const int* __restrict__ rows, const double* __restrict__ dinv, double* __restrict__ x) {
-    extern __shared__ double sm[];
-    double* S = sm;
-    double* xs = S + CH_NB * SN_SP;
-    const int tid = threadIdx.x;
-    const double* blk = Lv + off;
-#pragma unroll 4
-    for (int idx = tid; idx < nc * nc; idx += 256) {
-        const int cc = idx / nc, r = idx - cc * nc;
-        if (r > cc) S[r + cc * SN_SP] = blk[r + (long long)cc * nr];
-    }
-    double v = 0.0, di = 1.0;
-    if (tid < nc) {
-        v = x[col0 + tid];
-        di = dinv[col0 + tid];
-    }
-    __syncthreads();
-    v = snode_tri_solve(S, xs, v, di, nc, false);  // all 256 threads walk the same barriers
-    if (tid < nc) {
-        x[col0 + tid] = v;
-        xs[CH_NB + tid] = v;
-    }
-    __syncthreads();
-    const double* xf = xs + CH_NB;
-    for (int i = nc + tid; i < nr; i += 256) {
-        double acc = 0.0;
-#pragma unroll 8
-        for (int cc = 0; cc < nc; ++cc) acc = fma(blk[i + (long long)cc * nr], xf[cc], acc);
-        x[rows[i]] -= acc;
-    }
-}
-
-// backward: x_s <- L_ss^-T (x_s - B' x[rows below]).
-__global__ void __launch_bounds__(256)
-snode_bwd_kernel(const double* __restrict__ Lv, long long off, int nr, int nc, int col0,
-                 const int* __restrict__ rows, const double* __restrict__ dinv, double* __restrict__ x) {
-    extern __shared__ double sm[];
-    double* S = sm;
-    double* xs = S + CH_NB * SN_SP;
-    double* dots = xs + CH_NB;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const double* blk = Lv + off;
-#pragma unroll 4
-    for (int idx = tid; idx < nc * nc; idx += 256) {
-        const int cc = idx / nc, r = idx - cc * nc;
-        if (r > cc) S[r + cc * SN_SP] = blk[r + (long long)cc * nr];
-    }
-    for (int cc = warp; cc < nc; cc += 8) {
-        double acc = 0.0;
-#pragma unroll 4
-        for (int i = nc + lane; i < nr; i += 32) acc = fma(blk[i + (long long)cc * nr], x[rows[i]], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) dots[cc] = acc;
-    }
-    __syncthreads();
-    double v = 0.0, di = 1.0;
-    if (tid < nc) {
-        v = x[col0 + tid] - dots[tid];
-        di = dinv[col0 + tid];
-    }
-    v = snode_tri_solve(S, xs, v, di, nc, true);
-    if (tid < nc) x[col0 + tid] = v;
-}
-
-// ---- dataflow supernodal solve: one cooperative launch per sweep -------------------------------
-// CTAs take supernodes round-robin in elimination order.  Forward (owner computes): supernode t waits,
-// source by source, for the descendants s that have rows inside t's columns, subtracts
-// B_s[rows in t, :] y_s from its right-hand side in shared memory (fixed source order => bitwise
-// reproducible, no atomics), multiplies by W_t = L_tt^-1 and publishes y_t with an epoch-numbered flag.
-// Backward: supernode s waits for the supernodes that own its below-diagonal rows, forms
-// y_s - B_s' z[rows], multiplies by W_s' and publishes.  Replaces 2 * nsuper single-CTA launches.
-constexpr int SD_THREADS = 256;
-constexpr int SD_SMEM = (CH_NB * 129 + 4 * CH_NB) * 8;
-
-// W_s = L_ss^-1 for every supernode, one CTA per supernode, thread j = column j (forward substitution).
+// W_s = L_ss^-1 for the listed supernodes, one CTA each, thread j = column j (forward substitution).
+constexpr int MF_TI_SMEM = (CH_NB * 129 + CH_NB) * 8;
 __global__ void __launch_bounds__(CH_NB)
-snode_trtri_kernel(const double* __restrict__ Lv, const long long* __restrict__ off,
-                   const int* __restrict__ first, const int* __restrict__ nrs,
-                   const double* __restrict__ dinv_g, const long long* __restrict__ woff,
-                   double* __restrict__ W) {
+mf_trtri_kernel(const MfDesc d, const int* __restrict__ list) {
     constexpr int P = 129;
     extern __shared__ double S[];   // L strictly below the diagonal at S[r + c*P]; W' on/above it
     double* dv = S + CH_NB * P;
-    const int s = blockIdx.x, j = threadIdx.x;
-    const int col0 = first[s], nc = first[s + 1] - col0, nr = nrs[s];
-    const double* blk = Lv + off[s];
+    const int s = list[blockIdx.x], j = threadIdx.x;
+    const int col0 = d.first[s], nc = d.first[s + 1] - col0, ld = d.ld[s];
+    const double* blk = d.Lv + d.off[s];
     for (int idx = j; idx < nc * nc; idx += CH_NB) {
         const int cc = idx / nc, r = idx - cc * nc;
-        if (r > cc) S[r + cc * P] = blk[r + (long long)cc * nr];
+        if (r > cc) S[r + cc * P] = blk[r + (long long)cc * ld];
     }
-    dv[j] = (j < nc) ? dinv_g[col0 + j] : 1.0;
+    dv[j] = (j < nc) ? d.dinv[col0 + j] : 1.0;
     __syncthreads();
     if (j < nc) {
         double* w = S + j;
@@ -748,184 +432,383 @@ snode_trtri_kernel(const double* __restrict__ Lv, const long long* __restrict__ 
         }
     }
     __syncthreads();
-    double* Wg = W + woff[s];   // column-major nc x nc, zero above the diagonal
+    double* Wg = d.W + d.woff[s];   // column-major nc x nc, zero above the diagonal
     for (int idx = j; idx < nc * nc; idx += CH_NB) {
         const int cc = idx / nc, r = idx - cc * nc;
         Wg[idx] = (r >= cc) ? S[cc + r * P] : 0.0;
     }
 }
 
-__device__ __forceinline__ void sd_wait(volatile int* flag, int epoch) {
-    if (threadIdx.x == 0) {
-        while (*flag != epoch) {
+// ------------------------------------------------------------------------------------------------
+// device: multifrontal triangular solves, one CTA per supernode, one launch per level
+// ------------------------------------------------------------------------------------------------
+constexpr int MS_THREADS = 256;
+constexpr int MS_WP = 129;
+constexpr int MS_CHUNK = 2048;
+constexpr int MS_SMEM = (CH_NB * MS_WP + 4 * CH_NB + MS_CHUNK) * 8;
+
+__device__ __forceinline__ void ms_stage_w(const MfDesc& d, int s, int nc, double* Ws) {
+    const double* Wb = d.W + d.woff[s];
+    for (int idx = threadIdx.x; idx < nc * nc; idx += MS_THREADS) {
+        const int cc = idx / nc, r = idx - cc * nc;
+        Ws[r + cc * MS_WP] = Wb[idx];
+    }
+}
+
+// forward: rhs_s = b_s - (children's update vectors inside my columns); y_s = W_s rhs_s;
+//          u_s = B_s y_s + (children's entries below my columns)
+__global__ void __launch_bounds__(MS_THREADS)
+mf_fwd_kernel(const MfDesc d, const int* __restrict__ list, double* __restrict__ x) {
+    extern __shared__ double sm[];
+    double* Ws = sm;
+    double* rhs = Ws + CH_NB * MS_WP;
+    double* ys = rhs + CH_NB;
+    double* part = ys + CH_NB;  // 2 x 128
+    const int tid = threadIdx.x, t = tid & 127, half = tid >> 7;
+    const int s = list[blockIdx.x];
+    const int col0 = d.first[s], nc = d.first[s + 1] - col0, nr = d.nr[s], ld = d.ld[s];
+    const int nu = nr - nc;
+    ms_stage_w(d, s, nc, Ws);
+    if (tid < CH_NB) rhs[tid] = (tid < nc) ? x[col0 + tid] : 0.0;
+    __syncthreads();
+    const int q0 = d.childptr[s], q1 = d.childptr[s + 1];
+    for (int q = q0; q < q1; ++q) {
+        const int c = d.child[q];
+        const int cutc = d.cut[c];
+        const double* uc = d.uvec + d.vptr[c];
+        const int* rl = d.rel + d.relptr[c];
+        for (int i = tid; i < cutc; i += MS_THREADS) rhs[rl[i]] -= uc[i];
+        __syncthreads();
+    }
+    {
+        const int c_lo = half * 64, c_hi = min(nc, c_lo + 64);
+        double a0 = 0.0, a1 = 0.0;
+        if (t < nc) {
+            int cc = c_lo;
+            for (; cc + 1 < c_hi; cc += 2) {
+                a0 = fma(Ws[t + cc * MS_WP], rhs[cc], a0);
+                a1 = fma(Ws[t + (cc + 1) * MS_WP], rhs[cc + 1], a1);
+            }
+            if (cc < c_hi) a0 = fma(Ws[t + cc * MS_WP], rhs[cc], a0);
         }
-        __threadfence();
+        part[half * CH_NB + t] = a0 + a1;
     }
     __syncthreads();
-}
-
-struct SolveDesc {
-    const double* Lv;
-    const double* W;
-    const long long* off;
-    const long long* woff;
-    const int* first;
-    const int* nr;
-    const int* rowptr;
-    const int* rows;
-    const int* inptr;
-    const int* in_s;
-    const int* in_j0;
-    const int* in_j1;
-    const int* segptr;
-    const int* seg_tid;
-    int nsuper;
-};
-
-constexpr int SD_WP = 129;  // pitch of the staged W block
-
-__global__ void __launch_bounds__(SD_THREADS)
-snode_solve_dataflow_kernel(SolveDesc d, double* __restrict__ x, int* __restrict__ flags, int epoch,
-                            int transposed) {
-    extern __shared__ double sm[];
-    double* Ws = sm;                          // W_s staged as Ws[r + c*SD_WP]
-    double* rhs = Ws + CH_NB * SD_WP;         // right-hand side of this supernode's columns (nc)
-    double* ys = rhs + CH_NB;                 // the published piece of another supernode
-    double* part = ys + CH_NB;                // 2 x 128 partial sums
-    const int tid = threadIdx.x, t = tid & 127, half = tid >> 7;
-    for (int q = blockIdx.x; q < d.nsuper; q += gridDim.x) {
-        const int s = transposed ? d.nsuper - 1 - q : q;
-        const int col0 = d.first[s], nc = d.first[s + 1] - col0, nr = d.nr[s];
-        const double* Wb = d.W + d.woff[s];
-        __syncthreads();
-        // stage W_s and the right-hand side while the dependencies are still in flight
-        for (int idx = tid; idx < nc * nc; idx += SD_THREADS) {
-            const int cc = idx / nc, r = idx - cc * nc;
-            Ws[r + cc * SD_WP] = Wb[idx];
+    if (tid < CH_NB) {
+        const double y = (tid < nc) ? part[tid] + part[CH_NB + tid] : 0.0;
+        ys[tid] = y;
+        if (tid < nc) x[col0 + tid] = y;
+    }
+    __syncthreads();
+    if (nu == 0) return;
+    double* us = d.uvec + d.vptr[s];
+    const double* B = d.Lv + d.off[s] + nc;
+    for (int i = tid; i < nu; i += MS_THREADS) {
+        double a0 = 0.0, a1 = 0.0;
+        int cc = 0;
+        for (; cc + 1 < nc; cc += 2) {
+            a0 = fma(B[i + (long long)cc * ld], ys[cc], a0);
+            a1 = fma(B[i + (long long)(cc + 1) * ld], ys[cc + 1], a1);
         }
-        if (tid < CH_NB) rhs[tid] = (tid < nc) ? x[col0 + tid] : 0.0;
+        if (cc < nc) a0 = fma(B[i + (long long)cc * ld], ys[cc], a0);
+        us[i] = a0 + a1;
+    }
+    for (int q = q0; q < q1; ++q) {
         __syncthreads();
-        if (!transposed) {
-            for (int e = d.inptr[s]; e < d.inptr[s + 1]; ++e) {
-                const int src = d.in_s[e], j0 = d.in_j0[e], j1 = d.in_j1[e];
-                const int scol0 = d.first[src], snc = d.first[src + 1] - scol0, snr = d.nr[src];
-                const double* B = d.Lv + d.off[src] + snc;      // B(j, c) = B[j + c*snr]
-                const int* srows = d.rows + d.rowptr[src] + snc;
-                const int nj = j1 - j0;                         // <= 128 rows of src land in my columns
-                const int c_lo = half * ((snc + 1) / 2), c_hi = half ? snc : (snc + 1) / 2;
-                // fetch my slice of B before spinning on the source's flag
-                double breg[64];
-#pragma unroll
-                for (int cc = 0; cc < 64; ++cc)
-                    breg[cc] = (t < nj && c_lo + cc < c_hi) ? B[(j0 + t) + (long long)(c_lo + cc) * snr] : 0.0;
-                sd_wait(flags + src, epoch);
-                if (tid < CH_NB) ys[tid] = (tid < snc) ? __ldcg(x + scol0 + tid) : 0.0;
-                __syncthreads();
-                double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                for (int cc = 0; cc < 64; cc += 2) {
-                    a0 = fma(breg[cc], ys[min(c_lo + cc, CH_NB - 1)], a0);
-                    a1 = fma(breg[cc + 1], ys[min(c_lo + cc + 1, CH_NB - 1)], a1);
-                }
-                part[half * CH_NB + t] = a0 + a1;
-                __syncthreads();
-                if (tid < nj) rhs[srows[j0 + tid] - col0] -= part[tid] + part[CH_NB + tid];
-                __syncthreads();
-            }
-            // y_s = W rhs  (lower triangular matvec from shared memory, two halves of the columns)
-            {
-                const int c_lo = half * 64, c_hi = min(nc, c_lo + 64);
-                double a0 = 0.0, a1 = 0.0;
-                if (t < nc) {
-                    int cc = c_lo;
-                    for (; cc + 1 < c_hi; cc += 2) {
-                        a0 = fma(Ws[t + cc * SD_WP], rhs[cc], a0);
-                        a1 = fma(Ws[t + (cc + 1) * SD_WP], rhs[cc + 1], a1);
-                    }
-                    if (cc < c_hi) a0 = fma(Ws[t + cc * SD_WP], rhs[cc], a0);
-                }
-                part[half * CH_NB + t] = a0 + a1;
-            }
-            __syncthreads();
-            if (tid < nc) x[col0 + tid] = part[tid] + part[CH_NB + tid];
-        } else {
-            // y_s - B_s' z, one outgoing segment (= one ancestor) at a time, farthest ancestor first:
-            // thread t owns column t; its slice of the segment's rows is fetched before the wait
-            const double* blk = d.Lv + d.off[s] + nc;           // B(j, c) = blk[j + c*nr]
-            const int* R = d.rows + d.rowptr[s] + nc;
-            for (int e = d.segptr[s + 1] - 1; e >= d.segptr[s]; --e) {
-                const int tgt = d.seg_tid[e];
-                // segment bounds were stored per source in seg_j0/seg_j1; recover them from the rows:
-                // rows of this segment are those owned by tgt
-                const int tcol0 = d.first[tgt], tcol1 = d.first[tgt + 1];
-                // binary search is avoided: in_j0/in_j1 of (tgt <- s) are the same numbers, but indexed by
-                // target; the outgoing copy lives in d.in_* only per target, so scan (segments are short)
-                int j0 = 0, j1 = 0;
-                {
-                    const int rb = nr - nc;
-                    int lo = 0;
-                    while (lo < rb && R[lo] < tcol0) ++lo;
-                    int hi = lo;
-                    while (hi < rb && R[hi] < tcol1) ++hi;
-                    j0 = lo;
-                    j1 = hi;
-                }
-                const int nj = j1 - j0;
-                const int r_lo = half * ((nj + 1) / 2), r_hi = half ? nj : (nj + 1) / 2;
-                double breg[64];
-#pragma unroll
-                for (int rr = 0; rr < 64; ++rr)
-                    breg[rr] = (t < nc && r_lo + rr < r_hi) ? blk[(j0 + r_lo + rr) + (long long)t * nr] : 0.0;
-                sd_wait(flags + tgt, epoch);
-                if (tid < CH_NB) ys[tid] = (tid < nj) ? __ldcg(x + R[j0 + tid]) : 0.0;
-                __syncthreads();
-                double a0 = 0.0, a1 = 0.0;
-#pragma unroll
-                for (int rr = 0; rr < 64; rr += 2) {
-                    a0 = fma(breg[rr], ys[min(r_lo + rr, CH_NB - 1)], a0);
-                    a1 = fma(breg[rr + 1], ys[min(r_lo + rr + 1, CH_NB - 1)], a1);
-                }
-                part[half * CH_NB + t] = a0 + a1;
-                __syncthreads();
-                if (tid < nc) rhs[tid] -= part[tid] + part[CH_NB + tid];
-                __syncthreads();
-            }
-            // z_s = W' rhs
-            {
-                const int c_lo = half * 64, c_hi = min(nc, c_lo + 64);
-                double a0 = 0.0, a1 = 0.0;
-                if (t < nc) {
-                    int cc = c_lo;
-                    for (; cc + 1 < c_hi; cc += 2) {
-                        a0 = fma(Ws[cc + t * SD_WP], rhs[cc], a0);
-                        a1 = fma(Ws[(cc + 1) + t * SD_WP], rhs[cc + 1], a1);
-                    }
-                    if (cc < c_hi) a0 = fma(Ws[cc + t * SD_WP], rhs[cc], a0);
-                }
-                part[half * CH_NB + t] = a0 + a1;
-            }
-            __syncthreads();
-            if (tid < nc) x[col0 + tid] = part[tid] + part[CH_NB + tid];
-        }
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) *reinterpret_cast<volatile int*>(flags + s) = epoch;
+        const int c = d.child[q];
+        const int cutc = d.cut[c];
+        const int nuc = d.nr[c] - (d.first[c + 1] - d.first[c]);
+        const double* uc = d.uvec + d.vptr[c];
+        const int* rl = d.rel + d.relptr[c];
+        for (int i = cutc + tid; i < nuc; i += MS_THREADS) us[rl[i] - nc] += uc[i];
     }
 }
 
+// backward: z_s = W_s' (y_s - B_s' z[rows below])
+__global__ void __launch_bounds__(MS_THREADS)
+mf_bwd_kernel(const MfDesc d, const int* __restrict__ list, double* __restrict__ x) {
+    extern __shared__ double sm[];
+    double* Ws = sm;
+    double* rhs = Ws + CH_NB * MS_WP;
+    double* dots = rhs + CH_NB;
+    double* part = dots + CH_NB;  // 2 x 128
+    double* zr = part + 2 * CH_NB;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = tid & 127, half = tid >> 7;
+    const int s = list[blockIdx.x];
+    const int col0 = d.first[s], nc = d.first[s + 1] - col0, nr = d.nr[s], ld = d.ld[s];
+    const int nu = nr - nc;
+    ms_stage_w(d, s, nc, Ws);
+    if (tid < CH_NB) rhs[tid] = (tid < nc) ? x[col0 + tid] : 0.0;
+    const double* B = d.Lv + d.off[s] + nc;
+    const int* R = d.rows + d.rowptr[s] + nc;
+    double acc[16];
+#pragma unroll
+    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    for (int base = 0; base < nu; base += MS_CHUNK) {
+        const int len = min(MS_CHUNK, nu - base);
+        __syncthreads();
+        for (int i = tid; i < len; i += MS_THREADS) zr[i] = x[R[base + i]];
+        __syncthreads();
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const int cc = warp + 8 * k;
+            if (cc < nc) {
+                const double* bc = B + base + (long long)cc * ld;
+                double a = 0.0;
+                for (int i = lane; i < len; i += 32) a = fma(bc[i], zr[i], a);
+                acc[k] += a;
+            }
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+        double a = acc[k];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
+        if (lane == 0) dots[warp + 8 * k] = a;
+    }
+    __syncthreads();
+    if (tid < CH_NB) rhs[tid] -= dots[tid];
+    __syncthreads();
+    {
+        const int c_lo = half * 64, c_hi = min(nc, c_lo + 64);
+        double a0 = 0.0, a1 = 0.0;
+        if (t < nc) {
+            int cc = c_lo;
+            for (; cc + 1 < c_hi; cc += 2) {
+                a0 = fma(Ws[cc + t * MS_WP], rhs[cc], a0);
+                a1 = fma(Ws[(cc + 1) + t * MS_WP], rhs[cc + 1], a1);
+            }
+            if (cc < c_hi) a0 = fma(Ws[cc + t * MS_WP], rhs[cc], a0);
+        }
+        part[half * CH_NB + t] = a0 + a1;
+    }
+    __syncthreads();
+    if (tid < nc) x[col0 + tid] = part[tid] + part[CH_NB + tid];
+}
+
+// multi-GPU: keep only the pieces of the solution this rank is responsible for (its own supernodes;
+// rank 0 also keeps the replicated top) so that an all-reduce assembles the whole vector
+__global__ void mf_mask_kernel(int nsuper, const int* __restrict__ first, const int* __restrict__ owner,
+                               int rank, double* __restrict__ x) {
+    const int s = blockIdx.x;
+    if (s >= nsuper) return;
+    const int o = owner[s];
+    if (o == rank || (o < 0 && rank == 0)) return;
+    for (int j = first[s] + threadIdx.x; j < first[s + 1]; j += blockDim.x) x[j] = 0.0;
+}
+
+__global__ void gather_perm_kernel(int m, const int* __restrict__ perm, const double* __restrict__ src,
+                                   double* __restrict__ dst, int inverse) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    if (!inverse) dst[i] = src[perm[i]];   // y = P b
+    else dst[perm[i]] = src[i];            // x = P' y
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// host: analysis (upload of the symbolic structure, tensor maps, launch schedule)
+// ------------------------------------------------------------------------------------------------
 static int sparse_configure(nes_ctx* c) {
     static bool done = false;
     if (done) return 0;
-    NES_CUDA(c, cudaFuncSetAttribute(snode_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_DIAG_SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(snode_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_TR_SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(snode_update_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_UP_SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(snode_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (CH_NB * 129 + CH_NB) * 8));
-    NES_CUDA(c, cudaFuncSetAttribute(snode_solve_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SD_SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(snode_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_SOLVE_SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(snode_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SN_SOLVE_SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_DIAG_SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_TR_SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM_BYTES));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_TI_SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
     done = true;
+    return 0;
+}
+
+template <typename T>
+static T* up_vec(nes_ctx* c, SparseFactor* sf, const std::vector<T>& v) {
+    T* p = static_cast<T*>(dev_alloc(c, (v.size() + 2) * sizeof(T)));
+    if (!p) return nullptr;
+    sf->owned.push_back(p);
+    if (!v.empty() && upload(c, p, v.data(), v.size() * sizeof(T)) != 0) return nullptr;
+    return p;
+}
+
+template <typename T>
+static T* dev_new(nes_ctx* c, SparseFactor* sf, size_t count) {
+    T* p = static_cast<T*>(dev_alloc(c, (count + 16) * sizeof(T)));
+    if (p) sf->owned.push_back(p);
+    return p;
+}
+
+int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
+    const MatrixBase* b = A->base;
+    const int m = (int)b->m, n = (int)b->n;
+    SparseFactor* sf = new SparseFactor();
+    L->sparse = sf;
+    sf->m = m;
+    Symbolic& S = sf->S;
+    SymbolicOptions opt;
+    opt.nranks = c->nranks;
+    opt.nd_leaf = c->nd_leaf;
+    char err[256] = {0};
+    if (symbolic_analyze(m, n, b->h_colptr.data(), b->h_rowidx.data(), opt, &S, err, sizeof(err)) != 0)
+        return fail(c, NES_ERR_INVALID, "%s", err);
+    const int ns = S.nsuper;
+
+    // launch schedule: phase A = supernodes of this rank's subtrees, phase B = the replicated top
+    std::vector<int> all;
+    for (int ph = 0; ph < 2; ++ph) {
+        Phase& P = sf->phase[ph];
+        std::vector<int> potrf;
+        std::vector<int2> trsm;
+        std::vector<int4> syrk;
+        P.pptr.assign(S.nlevels + 1, 0);
+        P.tptr.assign(S.nlevels + 1, 0);
+        P.yptr.assign(S.nlevels + 1, 0);
+        for (int l = 0; l < S.nlevels; ++l) {
+            for (int s = S.lvlptr[l]; s < S.lvlptr[l + 1]; ++s) {
+                const bool mine = (ph == 0) ? (S.owner[s] == c->rank) : (S.owner[s] < 0);
+                if (!mine) continue;
+                const int nc = S.first[s + 1] - S.first[s], nu = S.nr[s] - nc;
+                potrf.push_back(s);
+                for (int k = 0; k * MF_TR_ROWS < nu; ++k) trsm.push_back(make_int2(s, k));
+                const int tn = (nu + NT_BM - 1) / NT_BM;
+                for (int bi = 0; bi < tn; ++bi)
+                    for (int bj = 0; bj <= bi; ++bj) syrk.push_back(make_int4(s, bi, bj, nc));
+            }
+            P.pptr[l + 1] = (int)potrf.size();
+            P.tptr[l + 1] = (int)trsm.size();
+            P.yptr[l + 1] = (int)syrk.size();
+        }
+        P.count = (int)potrf.size();
+        all.insert(all.end(), potrf.begin(), potrf.end());
+        P.d_potrf = up_vec(c, sf, potrf);
+        P.d_trsm = up_vec(c, sf, trsm);
+        P.d_syrk = up_vec(c, sf, syrk);
+        if (!P.d_potrf || !P.d_trsm || !P.d_syrk) return c->status < 0 ? c->status : NES_ERR_OUT_OF_MEMORY;
+    }
+    sf->nall = (int)all.size();
+    sf->d_all = up_vec(c, sf, all);
+
+    std::vector<long long> woff(ns + 1, 0);
+    for (int t = 0; t < ns; ++t) {
+        const long long nc = S.first[t + 1] - S.first[t];
+        woff[t + 1] = woff[t] + nc * nc;
+    }
+    sf->wsize = woff[ns];
+
+    MfDesc& d = sf->d;
+    d.off = up_vec(c, sf, S.off);
+    d.uoff = up_vec(c, sf, S.uoff);
+    d.woff = up_vec(c, sf, woff);
+    d.vptr = up_vec(c, sf, S.vptr);
+    d.first = up_vec(c, sf, S.first);
+    d.nr = up_vec(c, sf, S.nr);
+    d.ld = up_vec(c, sf, S.ld);
+    d.ldu = up_vec(c, sf, S.ldu);
+    d.rowptr = up_vec(c, sf, S.rowptr);
+    d.rows = up_vec(c, sf, S.rows);
+    d.childptr = up_vec(c, sf, S.childptr);
+    d.child = up_vec(c, sf, S.child);
+    d.relptr = up_vec(c, sf, S.relptr);
+    d.rel = up_vec(c, sf, S.rel);
+    d.cut = up_vec(c, sf, S.cut);
+    sf->d_perm = up_vec(c, sf, S.perm);
+    sf->d_ei = up_vec(c, sf, S.ei);
+    sf->d_ej = up_vec(c, sf, S.ej);
+    sf->d_edest = up_vec(c, sf, S.edest);
+    sf->d_owner = up_vec(c, sf, S.owner);
+    d.Lv = dev_new<double>(c, sf, (size_t)S.lsize);
+    d.U = dev_new<double>(c, sf, (size_t)S.usize);
+    d.dinv = dev_new<double>(c, sf, (size_t)m);
+    d.W = dev_new<double>(c, sf, (size_t)sf->wsize);
+    d.uvec = dev_new<double>(c, sf, (size_t)S.vsize);
+    sf->d_x = dev_new<double>(c, sf, (size_t)m);
+    sf->d_info = dev_new<int>(c, sf, 4);
+    d.info = sf->d_info;
+    L->d_rhs = static_cast<double*>(dev_alloc(c, (size_t)(m + 16) * sizeof(double)));
+    const bool ok = d.off && d.uoff && d.woff && d.vptr && d.first && d.nr && d.ld && d.ldu && d.rowptr && d.rows &&
+                    d.childptr && d.child && d.relptr && d.rel && d.cut && sf->d_perm && sf->d_ei && sf->d_ej &&
+                    sf->d_edest && sf->d_owner && sf->d_all && d.Lv && d.U && d.dinv && d.W && d.uvec && sf->d_x &&
+                    sf->d_info && L->d_rhs;
+    if (!ok) return c->status < 0 ? c->status : NES_ERR_OUT_OF_MEMORY;
+    NES_CUDA(c, cudaMemsetAsync(d.dinv, 0, (size_t)m * sizeof(double), c->stream));
+    NES_CUDA(c, cudaMemsetAsync(d.uvec, 0, (size_t)(S.vsize + 16) * sizeof(double), c->stream));
+
+    // one tensor map per supernode block (132 x 32 boxes, OOB rows / columns read as zero)
+    {
+        std::vector<CUtensorMap> maps(ns);
+        for (int s = 0; s < ns; ++s) {
+            const int nc = S.first[s + 1] - S.first[s];
+            if (S.nr[s] == nc) {
+                memset(&maps[s], 0, sizeof(CUtensorMap));
+                continue;
+            }
+            if (make_operand_map(&maps[s], d.Lv + S.off[s], S.nr[s], nc, S.ld[s]) != 0)
+                return fail(c, NES_ERR_CUDA, "cuTensorMapEncodeTiled failed for supernode %d (%d x %d)", s, S.nr[s], nc);
+        }
+        CUtensorMap* dm = static_cast<CUtensorMap*>(dev_alloc(c, (size_t)(ns + 1) * sizeof(CUtensorMap)));
+        if (!dm) return c->status;
+        sf->owned.push_back(dm);
+        NES_TRY(upload(c, dm, maps.data(), (size_t)ns * sizeof(CUtensorMap)));
+        d.maps = dm;
+    }
+    c->anz = (double)S.anz;
+    c->aatfl = S.aatfl;
+    c->lnz = S.lnz;
+    c->fl = S.fl;
+    c->status = 0;
+    return 0;
+}
+
+void sparse_free(nes_ctx* c, nes_factor* L) {
+    SparseFactor* sf = L->sparse;
+    if (!sf) return;
+    if (sf->graph) cudaGraphExecDestroy(sf->graph);
+    for (void* p : sf->owned) dev_free(c, p);
+    delete sf;
+    L->sparse = nullptr;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: numeric factorization
+// ------------------------------------------------------------------------------------------------
+static int run_factor_phase(nes_ctx* c, SparseFactor* sf, int ph) {
+    const Phase& P = sf->phase[ph];
+    const Symbolic& S = sf->S;
+    for (int l = 0; l < S.nlevels; ++l) {
+        const int np = P.pptr[l + 1] - P.pptr[l];
+        if (np == 0) continue;
+        mf_potrf_kernel<<<np, 256, MF_DIAG_SMEM, c->stream>>>(sf->d, P.d_potrf + P.pptr[l]);
+        MF_LAUNCHED(c, "mf_potrf_kernel");
+        const int nt = P.tptr[l + 1] - P.tptr[l];
+        if (nt > 0) {
+            mf_trsm_kernel<<<nt, 256, MF_TR_SMEM, c->stream>>>(sf->d, P.d_trsm + P.tptr[l]);
+            MF_LAUNCHED(c, "mf_trsm_kernel");
+        }
+        const int ny = P.yptr[l + 1] - P.yptr[l];
+        if (ny > 0) {
+            const int grid = ny < c->num_sms ? ny : c->num_sms;
+            mf_syrk_kernel<<<grid, NT_THREADS, NT_SMEM_BYTES, c->stream>>>(sf->d, P.d_syrk + P.yptr[l], ny);
+            MF_LAUNCHED(c, "mf_syrk_kernel");
+        }
+    }
+    return 0;
+}
+
+__global__ void info_first_minor_kernel(int* info) {
+    if (threadIdx.x == 0 && info[0] == 0) info[1] = 0x7fffffff;
+}
+
+static int enqueue_factorization(nes_ctx* c, SparseFactor* sf, const MatrixBase* b, const double* d_theta) {
+    const Symbolic& S = sf->S;
+    NES_CUDA(c, cudaMemsetAsync(sf->d.Lv, 0, (size_t)S.lsize * sizeof(double), c->stream));
+    NES_CUDA(c, cudaMemsetAsync(sf->d_info, 0, 2 * sizeof(int), c->stream));
+    if (S.anz > 0) {
+        sparse_assemble_kernel<<<(unsigned)((S.anz + 255) / 256), 256, 0, c->stream>>>(
+            S.anz, sf->d_ei, sf->d_ej, sf->d_edest, b->d_rowptr, b->d_colidx, b->d_csr_val, d_theta, sf->d.Lv);
+        MF_LAUNCHED(c, "sparse_assemble_kernel");
+    }
+    NES_TRY(run_factor_phase(c, sf, 0));
     return 0;
 }
 
@@ -934,39 +817,30 @@ int sparse_factorize(nes_ctx* c, nes_matrix* A, nes_factor* L) {
     if (!sf) return fail(c, NES_ERR_INVALID, "sparse factor was not analyzed");
     NES_TRY(sparse_configure(c));
     const MatrixBase* b = A->base;
+    const Symbolic& S = sf->S;
     L->factorized = 0;
-    {
-        StageTimer t(c, NES_STAGE_FORM);
-        NES_CUDA(c, cudaMemsetAsync(sf->d_L, 0, (size_t)sf->lsize * sizeof(double), c->stream));
-        NES_CUDA(c, cudaMemsetAsync(sf->d_info, 0, 2 * sizeof(int), c->stream));
-        if (sf->anz > 0) {
-            sparse_assemble_kernel<<<(unsigned)((sf->anz + 255) / 256), 256, 0, c->stream>>>(
-                sf->anz, sf->d_ei, sf->d_ej, sf->d_edest, b->d_rowptr, b->d_colidx, b->d_csr_val,
-                A->d_theta, sf->d_L);
-            NES_CHECK_LAUNCH(c);
-        }
-    }
+    sf->d.dbound = c->dbound;
+    sf->d.dbg = getenv("NES_SPARSE_DBG") ? atoi(getenv("NES_SPARSE_DBG")) : 0;
     {
         StageTimer t(c, NES_STAGE_FACTOR);
-        for (int s = 0; s < sf->nsuper; ++s) {
-            const int col0 = sf->first[s], nc = sf->first[s + 1] - col0, nr = sf->nr[s];
-            const long long off = sf->off[s];
-            snode_potrf_kernel<<<1, 256, SN_DIAG_SMEM, c->stream>>>(sf->d_L, off, nr, nc, col0, sf->d_dinv,
-                                                                   c->dbound, sf->d_info);
-            NES_CHECK_LAUNCH(c);
-            const int rb = nr - nc;
-            if (rb <= 0) continue;
-            snode_trsm_kernel<<<(rb + SN_TR_ROWS - 1) / SN_TR_ROWS, 256, SN_TR_SMEM, c->stream>>>(
-                sf->d_L, off, nr, nc, col0, sf->d_dinv);
-            NES_CHECK_LAUNCH(c);
-            const int nseg = sf->segptr[s + 1] - sf->segptr[s];
-            if (nseg > 0) {
-                dim3 grid((rb + SN_UP_ROWS - 1) / SN_UP_ROWS, nseg);
-                snode_update_kernel<<<grid, 256, SN_UP_SMEM, c->stream>>>(
-                    sf->d_L, off, nr, nc, sf->d_rows + sf->rowptr[s], sf->segptr[s], sf->d_seg_toff,
-                    sf->d_seg_tnr, sf->d_seg_tcol0, sf->d_seg_j0, sf->d_seg_j1, sf->d_seg_relptr, sf->d_rel);
-                NES_CHECK_LAUNCH(c);
+        NES_TRY(enqueue_factorization(c, sf, b, A->d_theta));
+        if (c->nranks > 1) {
+            // publish the update matrices of my subtree roots: contiguous per owner, one broadcast each
+            for (int q = 0; q < c->nranks; ++q) {
+                const long long cnt = S.xu_off[q + 1] - S.xu_off[q];
+                if (cnt > 0) NES_TRY(dist_broadcast(c, sf->d.U + S.xu_off[q], (size_t)cnt, q));
             }
+        }
+        NES_TRY(run_factor_phase(c, sf, 1));
+        if (sf->nall > 0) {  // block inverses for the solves
+            mf_trtri_kernel<<<sf->nall, CH_NB, MF_TI_SMEM, c->stream>>>(sf->d, sf->d_all);
+            MF_LAUNCHED(c, "mf_trtri_kernel");
+        }
+        if (c->nranks > 1) {  // a failed pivot is seen by one rank only: agree on {status, first minor}
+            info_first_minor_kernel<<<1, 32, 0, c->stream>>>(sf->d_info);
+            NES_CHECK_LAUNCH(c);
+            NES_TRY(dist_allreduce_int(c, sf->d_info, 1, 1));
+            NES_TRY(dist_allreduce_int(c, sf->d_info + 1, 1, 0));
         }
     }
     int info[2] = {0, 0};
@@ -978,11 +852,22 @@ int sparse_factorize(nes_ctx* c, nes_matrix* A, nes_factor* L) {
     }
     c->minor = sf->m;
     L->factorized = 1;
-    {   // block inverses for the dataflow solve (all supernodes in one launch)
-        StageTimer t(c, NES_STAGE_FACTOR);
-        snode_trtri_kernel<<<sf->nsuper, CH_NB, (CH_NB * 129 + CH_NB) * 8, c->stream>>>(
-            sf->d_L, sf->d_off, sf->d_first, sf->d_nr, sf->d_dinv, sf->d_woff, sf->d_W);
-        NES_CHECK_LAUNCH(c);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// host: solves
+// ------------------------------------------------------------------------------------------------
+static int run_solve_phase(nes_ctx* c, SparseFactor* sf, int ph, bool backward) {
+    const Phase& P = sf->phase[ph];
+    const int nl = sf->S.nlevels;
+    for (int k = 0; k < nl; ++k) {
+        const int l = backward ? nl - 1 - k : k;
+        const int np = P.pptr[l + 1] - P.pptr[l];
+        if (np == 0) continue;
+        if (!backward) mf_fwd_kernel<<<np, MS_THREADS, MS_SMEM, c->stream>>>(sf->d, P.d_potrf + P.pptr[l], sf->d_x);
+        else mf_bwd_kernel<<<np, MS_THREADS, MS_SMEM, c->stream>>>(sf->d, P.d_potrf + P.pptr[l], sf->d_x);
+        MF_LAUNCHED(c, backward ? "mf_bwd_kernel" : "mf_fwd_kernel");
     }
     return 0;
 }
@@ -990,37 +875,24 @@ int sparse_factorize(nes_ctx* c, nes_matrix* A, nes_factor* L) {
 int sparse_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
     SparseFactor* sf = L->sparse;
     StageTimer t(c, NES_STAGE_SOLVE);
+    const Symbolic& S = sf->S;
     const int m = sf->m;
     gather_perm_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(m, sf->d_perm, d_x, sf->d_x, 0);
     NES_CHECK_LAUNCH(c);
-    if (sf->d_W && sf->d_flags) {
-        SolveDesc d{sf->d_L, sf->d_W, sf->d_off, sf->d_woff, sf->d_first, sf->d_nr, sf->d_rowptr, sf->d_rows,
-                    sf->d_inptr, sf->d_in_s, sf->d_in_j0, sf->d_in_j1, sf->d_segptr, sf->d_seg_tid, sf->nsuper};
-        const int grid = sf->nsuper < c->num_sms ? sf->nsuper : c->num_sms;
-        double* xp = sf->d_x;
-        int* fl = sf->d_flags;
-        for (int transposed = 0; transposed < 2; ++transposed) {
-            int ep = ++sf->flag_epoch;
-            void* args[] = {(void*)&d, (void*)&xp, (void*)&fl, (void*)&ep, (void*)&transposed};
-            NES_CUDA(c, cudaLaunchCooperativeKernel((const void*)snode_solve_dataflow_kernel, dim3(grid),
-                                                    dim3(SD_THREADS), args, SD_SMEM, c->stream));
-            ++c->launches;
+    NES_TRY(run_solve_phase(c, sf, 0, false));
+    if (c->nranks > 1) {
+        for (int q = 0; q < c->nranks; ++q) {
+            const long long cnt = S.xv_off[q + 1] - S.xv_off[q];
+            if (cnt > 0) NES_TRY(dist_broadcast(c, sf->d.uvec + S.xv_off[q], (size_t)cnt, q));
         }
-        gather_perm_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(m, sf->d_perm, sf->d_x, d_x, 1);
-        NES_CHECK_LAUNCH(c);
-        return 0;
     }
-    for (int s = 0; s < sf->nsuper; ++s) {
-        const int col0 = sf->first[s], nc = sf->first[s + 1] - col0;
-        snode_fwd_kernel<<<1, 256, SN_SOLVE_SMEM, c->stream>>>(sf->d_L, sf->off[s], sf->nr[s], nc, col0,
-                                                  sf->d_rows + sf->rowptr[s], sf->d_dinv, sf->d_x);
+    NES_TRY(run_solve_phase(c, sf, 1, false));
+    NES_TRY(run_solve_phase(c, sf, 1, true));
+    NES_TRY(run_solve_phase(c, sf, 0, true));
+    if (c->nranks > 1) {
+        mf_mask_kernel<<<S.nsuper, 128, 0, c->stream>>>(S.nsuper, sf->d.first, sf->d_owner, c->rank, sf->d_x);
         NES_CHECK_LAUNCH(c);
-    }
-    for (int s = sf->nsuper - 1; s >= 0; --s) {
-        const int col0 = sf->first[s], nc = sf->first[s + 1] - col0;
-        snode_bwd_kernel<<<1, 256, SN_SOLVE_SMEM, c->stream>>>(sf->d_L, sf->off[s], sf->nr[s], nc, col0,
-                                                  sf->d_rows + sf->rowptr[s], sf->d_dinv, sf->d_x);
-        NES_CHECK_LAUNCH(c);
+        NES_TRY(dist_allreduce_sum(c, sf->d_x, (size_t)m));
     }
     gather_perm_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(m, sf->d_perm, sf->d_x, d_x, 1);
     NES_CHECK_LAUNCH(c);
@@ -1028,24 +900,27 @@ int sparse_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
 }
 
 // expand the supernodal factor to a dense lower-triangular matrix (testing) + permutation
-int sparse_factor_to_dense(nes_ctx* c, nes_factor* L, double* Lout, size_t ld, int* perm_out) {
+int sparse_factor_to_dense(nes_ctx* c, nes_factor* L, double* Lout, size_t ldo, int* perm_out) {
     SparseFactor* sf = L->sparse;
-    std::vector<double> h((size_t)sf->lsize);
-    std::vector<int> rows(sf->rowptr[sf->nsuper]), perm(sf->m);
-    NES_TRY(download(c, h.data(), sf->d_L, h.size() * sizeof(double)));
-    NES_TRY(download(c, rows.data(), sf->d_rows, rows.size() * sizeof(int)));
-    NES_TRY(download(c, perm.data(), sf->d_perm, perm.size() * sizeof(int)));
+    const Symbolic& S = sf->S;
+    if (c->nranks > 1) {  // the blocks of a subtree live on its owner only: collect them (testing path)
+        for (int s = 0; s < S.nsuper; ++s)
+            if (S.owner[s] >= 0)
+                NES_TRY(dist_broadcast(c, sf->d.Lv + S.off[s], (size_t)(S.off[s + 1] - S.off[s]), S.owner[s]));
+    }
+    std::vector<double> h((size_t)S.lsize);
+    NES_TRY(download(c, h.data(), sf->d.Lv, h.size() * sizeof(double)));
     for (size_t j = 0; j < (size_t)sf->m; ++j)
-        for (size_t i = 0; i < (size_t)sf->m; ++i) Lout[i + j * ld] = 0.0;
-    for (int s = 0; s < sf->nsuper; ++s) {
-        const int col0 = sf->first[s], nc = sf->first[s + 1] - col0, nr = sf->nr[s];
-        const int* R = rows.data() + sf->rowptr[s];
+        for (size_t i = 0; i < (size_t)sf->m; ++i) Lout[i + j * ldo] = 0.0;
+    for (int s = 0; s < S.nsuper; ++s) {
+        const int col0 = S.first[s], nc = S.first[s + 1] - col0, nr = S.nr[s];
+        const int* R = S.rows.data() + S.rowptr[s];
         for (int cc = 0; cc < nc; ++cc)
             for (int r = cc; r < nr; ++r)
-                Lout[(size_t)R[r] + (size_t)(col0 + cc) * ld] = h[(size_t)sf->off[s] + r + (size_t)cc * nr];
+                Lout[(size_t)R[r] + (size_t)(col0 + cc) * ldo] = h[(size_t)S.off[s] + r + (size_t)cc * S.ld[s]];
     }
     if (perm_out)
-        for (int i = 0; i < sf->m; ++i) perm_out[i] = perm[i];
+        for (int i = 0; i < sf->m; ++i) perm_out[i] = S.perm[i];
     return 0;
 }
 

@@ -122,9 +122,47 @@ def _prototypes(lib):
     fn("nes_dist_plan", C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int)
     fn("nes_mark_begin", C.c_int, _vp)
     fn("nes_mark_end", C.c_int, _vp, _dp)
+    fn("nes_symbolic_create", _vp, C.c_int, C.c_int, _ip, _ip, C.c_int, C.c_int, C.c_char_p, C.c_size_t)
+    fn("nes_symbolic_ints", C.c_longlong, _vp, C.c_char_p, C.POINTER(_ip))
+    fn("nes_symbolic_longs", C.c_longlong, _vp, C.c_char_p, C.POINTER(C.POINTER(C.c_longlong)))
+    fn("nes_symbolic_scalar", C.c_double, _vp, C.c_char_p)
+    fn("nes_symbolic_free", None, _vp)
+    fn("nes_set_ordering_leaf", C.c_int, _vp, C.c_int)
 
 
 _lib = None
+
+_SYM_INTS = ("perm", "first", "nr", "ld", "rows", "rowptr", "sparent", "level", "lvlptr", "childptr", "child",
+             "relptr", "rel", "cut", "ldu", "owner", "ei", "ej", "segptr", "seg_tid", "inptr", "in_s")
+_SYM_LONGS = ("off", "uoff", "edest", "vptr", "xu_off", "xv_off")
+_SYM_SCALARS = ("anz", "aatfl", "lnz", "fl", "lsize", "usize", "nsuper", "nlevels")
+
+
+def symbolic_analyze(colptr, rowidx, m, n, nranks=1, nd_leaf=0):
+    """Host-only symbolic analysis (cholmod_analyze's role; csrc/sparse_symbolic.cu) as a dict of numpy
+    arrays / scalars.  Needs no GPU."""
+    lib = load_library()
+    cp = np.ascontiguousarray(colptr, dtype=np.int32)
+    ri = np.ascontiguousarray(rowidx, dtype=np.int32)
+    err = C.create_string_buffer(512)
+    h = lib.nes_symbolic_create(m, n, cp.ctypes.data_as(_ip), ri.ctypes.data_as(_ip), nranks, nd_leaf, err, 512)
+    if not h:
+        raise NesError("nes_symbolic_create failed: " + err.value.decode())
+    out = {}
+    try:
+        for name in _SYM_INTS:
+            p = _ip()
+            cnt = lib.nes_symbolic_ints(h, name.encode(), C.byref(p))
+            out[name] = np.ctypeslib.as_array(p, shape=(cnt,)).copy() if cnt > 0 else np.zeros(0, np.int32)
+        for name in _SYM_LONGS:
+            p = C.POINTER(C.c_longlong)()
+            cnt = lib.nes_symbolic_longs(h, name.encode(), C.byref(p))
+            out[name] = np.ctypeslib.as_array(p, shape=(cnt,)).copy() if cnt > 0 else np.zeros(0, np.int64)
+        for name in _SYM_SCALARS:
+            out[name] = lib.nes_symbolic_scalar(h, name.encode())
+    finally:
+        lib.nes_symbolic_free(h)
+    return out
 
 
 def load_library():

@@ -235,6 +235,25 @@ int nes_comm_nranks(const nes_ctx* c);
  * and fills up to `cap` (tile row, tile column) pairs. */
 int nes_dist_plan(int m, int nranks, int rank, int* tile_rows, int* tile_cols, int cap);
 
+/* ---- symbolic analysis on its own (host only, no device needed) ---------------------------------
+ * What nes_analyze computes for a sparse A before anything touches the GPU: the fill-reducing
+ * ordering (nested dissection + reverse Cuthill-McKee leaves), supernodes, assembly-tree levels, index
+ * maps and the subtree-to-rank mapping of a multi-GPU run.  Exposed so hosts and tests can inspect or
+ * cache the analysis; named int arrays ("perm", "first", "nr", "ld", "rows", "rowptr", "sparent", "level",
+ * "lvlptr", "childptr", "child", "relptr", "rel", "cut", "ldu", "owner", "ei", "ej"), long long arrays
+ * ("off", "uoff", "edest") and double scalars ("anz", "aatfl", "lnz", "fl", "lsize", "usize", "nsuper",
+ * "nlevels").  cholmod_analyze (sparse-cholesky.lisp:261, 509). */
+void* nes_symbolic_create(int nrow, int ncol, const int* colptr, const int* rowidx, int nranks,
+                          int nd_leaf, char* err, size_t errlen);
+/* returns the element count (or -1 for an unknown name) and stores the array's address in *data */
+long long nes_symbolic_ints(const void* sym, const char* name, const int** data);
+long long nes_symbolic_longs(const void* sym, const char* name, const long long** data);
+double nes_symbolic_scalar(const void* sym, const char* name);
+void nes_symbolic_free(void* sym);
+/* nested dissection stops at vertex sets of `leaf` rows (0 = default max(256, nrow/128)); applies to
+ * later nes_analyze calls on this context; returns the previous value */
+int nes_set_ordering_leaf(nes_ctx* c, int leaf);
+
 /* ---- instrumentation (bench.py / roofline): device time of the library's own stages ---------- */
 #define NES_STAGE_FORM 0      /* K1 fused scale+SYRK   */
 #define NES_STAGE_FACTOR 1    /* K2 Cholesky            */

@@ -1,0 +1,173 @@
+"""CPU tests of the host symbolic analysis behind nes_analyze for sparse A (csrc/sparse_symbolic.cu;
+cholmod_analyze's role, sparse-cholesky.lisp:261, 509): ordering, supernodes, assembly-tree levels, the
+multifrontal index maps and the subtree-to-rank mapping.  The maps are exercised by a NumPy emulation
+of the device's multifrontal numeric phase (same storage, same extend-add rules), whose factor must
+satisfy L L' = P M P'.  No GPU needed."""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from cholesky_is_magic_b200 import nes
+from oracle import newton_solve as ons
+
+
+def banded(rng, m, n, bw, per_col):
+    rows, cols, vals = [], [], []
+    for j in range(n):
+        c = j * m // n if j >= m else j
+        r = np.unique(np.clip(c + rng.integers(-bw, bw + 1, per_col - 1), 0, m - 1))
+        r = np.union1d(r, [c])
+        rows += r.tolist(); cols += [j] * len(r); vals += (1 + rng.random(len(r))).tolist()
+    return sp.csc_matrix((vals, (rows, cols)), shape=(m, n))
+
+
+def analyze(A, nranks=1, leaf=0):
+    A = sp.csc_matrix(A)
+    A.sort_indices()
+    return nes.symbolic_analyze(A.indptr, A.indices, A.shape[0], A.shape[1], nranks, leaf)
+
+
+def true_colcounts(pattern):
+    """Boolean right-looking elimination of a symmetric pattern (dense, small m)."""
+    m = pattern.shape[0]
+    F = np.tril(pattern | np.eye(m, dtype=bool))
+    for j in range(m):
+        below = np.nonzero(F[j + 1:, j])[0] + j + 1
+        if len(below):
+            F[np.ix_(below, below)] |= np.tril(np.ones((len(below), len(below)), dtype=bool))
+    return F.sum(axis=0), F
+
+
+def multifrontal_numeric(S, M):
+    """NumPy emulation of sparse_chol.cu's numeric phase on the symbolic structure S."""
+    ns = int(S["nsuper"])
+    first, nr, ld, rowptr, rows, off = S["first"], S["nr"], S["ld"], S["rowptr"], S["rows"], S["off"]
+    perm = S["perm"]
+    Lv = np.zeros(int(S["lsize"]))
+    U = np.full(int(S["usize"]), np.nan)       # pool with slot reuse
+    # assembly: entry e = M[ei, ej] -> edest
+    Lv[S["edest"]] = M[S["ei"], S["ej"]]
+    for lvl in range(int(S["nlevels"])):
+        for s in range(S["lvlptr"][lvl], S["lvlptr"][lvl + 1]):
+            nc = first[s + 1] - first[s]; nu = nr[s] - nc
+            blk = Lv[off[s]: off[s] + ld[s] * nc].reshape(nc, ld[s]).T          # view, column-major
+            Us = None
+            if nu:
+                Us = U[S["uoff"][s]: S["uoff"][s] + S["ldu"][s] * nu].reshape(nu, S["ldu"][s]).T
+                Us[:nu, :] = 0.0
+            for c in S["child"][S["childptr"][s]: S["childptr"][s + 1]]:        # extend-add, children ascending
+                cnc = first[c + 1] - first[c]; cnu = nr[c] - cnc
+                Uc = U[S["uoff"][c]: S["uoff"][c] + S["ldu"][c] * cnu].reshape(cnu, S["ldu"][c]).T
+                rel = S["rel"][S["relptr"][c]: S["relptr"][c + 1]]
+                assert np.array_equal(rows[rowptr[s]: rowptr[s + 1]][rel], rows[rowptr[c] + cnc: rowptr[c + 1]])
+                cut = S["cut"][c]
+                assert np.all(rel[:cut] < nc) and np.all(rel[cut:] >= nc)
+                for j in range(cnu):
+                    i = np.arange(j, cnu)
+                    if j < cut:
+                        blk[rel[i], rel[j]] += Uc[i, j]
+                    else:
+                        Us[rel[i] - nc, rel[j] - nc] += Uc[i, j]
+            D = np.tril(blk[:nc, :nc]); D = D + np.tril(D, -1).T
+            Ld = np.linalg.cholesky(D)
+            blk[:nc, :nc] = Ld
+            if nu:
+                blk[nc:nr[s], :] = np.linalg.solve(Ld, blk[nc:nr[s], :].T).T
+                Us[:nu, :nu] -= np.tril(blk[nc:nr[s], :] @ blk[nc:nr[s], :].T)
+    m = len(perm)
+    L = np.zeros((m, m))
+    for s in range(ns):
+        nc = first[s + 1] - first[s]
+        blk = Lv[off[s]: off[s] + ld[s] * nc].reshape(nc, ld[s]).T
+        R = rows[rowptr[s]: rowptr[s + 1]]
+        for cc in range(nc):
+            L[R[cc:], first[s] + cc] = blk[cc:nr[s], cc]
+    return L
+
+
+CASES = [("random", 1, 1, 0), ("random", 7, 12, 0), ("random", 40, 90, 0), ("random", 150, 400, 0),
+         ("banded", 300, 700, 0), ("banded", 600, 1500, 32), ("banded", 900, 2000, 48)]
+
+
+@pytest.mark.parametrize("kind,m,n,leaf", CASES)
+def test_symbolic_structure_and_multifrontal_maps(kind, m, n, leaf):
+    rng = np.random.default_rng(m)
+    A = ons.random_sparse_matrix(rng, m, n, 0.05 if m <= 60 else 0.02) if kind == "random" else banded(rng, m, n, 12, 5)
+    A = sp.csc_matrix(A)
+    S = analyze(A, leaf=leaf)
+    perm = S["perm"]
+    assert sorted(perm.tolist()) == list(range(m))
+    pat = ((abs(A) @ abs(A).T).toarray() != 0)
+    cc, F = true_colcounts(pat[np.ix_(perm, perm)])
+    assert S["anz"] == np.count_nonzero(np.tril(pat))
+    assert S["aatfl"] == float((np.diff(A.indptr).astype(float) ** 2).sum())
+    assert S["lnz"] == cc.sum() and S["fl"] == float((cc.astype(float) ** 2).sum())
+    ns = int(S["nsuper"])
+    first, nr, rowptr, rows = S["first"], S["nr"], S["rowptr"], S["rows"]
+    assert first[0] == 0 and first[ns] == m and np.all(np.diff(first) >= 1) and np.all(np.diff(first) <= 128)
+    for s in range(ns):
+        R = rows[rowptr[s]: rowptr[s + 1]]
+        assert np.array_equal(R[: first[s + 1] - first[s]], np.arange(first[s], first[s + 1]))
+        assert np.all(np.diff(R) > 0)
+        last = first[s + 1] - 1
+        assert np.array_equal(R[first[s + 1] - first[s]:], np.nonzero(F[last + 1:, last])[0] + last + 1)
+        for j in range(first[s], first[s + 1]):                      # relaxed supernodes only add zeros
+            assert set(np.nonzero(F[j:, j])[0] + j) <= set(R.tolist())
+        p = S["sparent"][s]
+        assert (p == -1) == (nr[s] == first[s + 1] - first[s])
+        if p >= 0:
+            assert S["level"][p] > S["level"][s] and p > s
+    lv = S["lvlptr"]
+    assert lv[0] == 0 and lv[-1] == ns
+    for l in range(int(S["nlevels"])):
+        assert np.all(S["level"][lv[l]: lv[l + 1]] == l)
+    assert np.all(S["off"] % 16 == 0) and np.all(S["ld"] % 16 == 0)
+    # numeric emulation on the maps
+    s_ = np.sqrt(0.1 + 10 * rng.random(n))
+    M = ons.normal_matrix(A, s_)
+    L = multifrontal_numeric(S, M)
+    Mp = M[np.ix_(perm, perm)]
+    assert np.linalg.norm(L @ L.T - Mp) / np.linalg.norm(Mp) <= 1e-12
+
+
+def test_nested_dissection_gives_parallel_levels_and_reuses_update_slots():
+    rng = np.random.default_rng(3)
+    m, n = 4000, 9000
+    A = banded(rng, m, n, 20, 6)
+    S_nd = analyze(A, leaf=250)
+    S_rcm = analyze(A, leaf=10 ** 9)          # no dissection: profile ordering, a chain
+    width_nd = np.diff(S_nd["lvlptr"]).max()
+    assert np.median(np.diff(S_rcm["lvlptr"])) == 1          # a chain
+    assert width_nd >= 8 and S_nd["nlevels"] < S_rcm["nlevels"] / 2
+    assert S_nd["lnz"] < 6 * S_rcm["lnz"]
+    total_u = sum(int(S_nd["ldu"][s]) * int(S_nd["nr"][s] - (S_nd["first"][s + 1] - S_nd["first"][s]))
+                  for s in range(int(S_nd["nsuper"])))
+    assert S_nd["usize"] < total_u             # slots are reused across levels
+
+
+@pytest.mark.parametrize("Q", [2, 4, 8])
+def test_subtree_to_rank_mapping(Q):
+    rng = np.random.default_rng(5)
+    m, n = 6000, 14000
+    A = banded(rng, m, n, 16, 6)
+    S = analyze(A, nranks=Q, leaf=150)
+    owner, par = S["owner"], S["sparent"]
+    ns = int(S["nsuper"])
+    assert owner.min() >= -1 and owner.max() < Q
+    assert set(owner[owner >= 0].tolist()) == set(range(Q))          # every rank owns something
+    for s in range(ns):
+        p = par[s]
+        if p >= 0:
+            if owner[s] == -1:
+                assert owner[p] == -1                                 # the top is closed under "parent"
+            else:
+                assert owner[p] in (-1, owner[s])                     # subtrees are not split across ranks
+    # the ordering / structure itself does not depend on the number of ranks
+    S1 = analyze(A, nranks=1, leaf=150)
+    for k in ("perm", "first", "rows", "level", "rel"):
+        assert np.array_equal(S[k], S1[k])
+    # load balance of the owned flops (nc * nr^2 model): no rank above 1.6x the mean
+    nc = np.diff(S["first"]).astype(float)
+    fl = nc * S["nr"].astype(float) ** 2
+    load = np.array([fl[owner == q].sum() for q in range(Q)])
+    assert load.max() <= 1.6 * load.mean()
