@@ -88,6 +88,13 @@ __device__ __forceinline__ void bulk_load_1d(void* dst, const void* src, uint32_
         : "memory");
 }
 
+// 1D bulk copy shared -> global (bulk async group; bytes multiple of 16, both sides 16B aligned).
+__device__ __forceinline__ void bulk_store_1d(void* dst, const void* src, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(reinterpret_cast<uint64_t>(dst)),
+                 "r"(smem_u32(src)), "r"(bytes)
+                 : "memory");
+}
+
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }

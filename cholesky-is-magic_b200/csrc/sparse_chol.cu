@@ -70,6 +70,9 @@ struct MfDesc {
     const int* relptr;
     const int* rel;
     const int* cut;
+    const int* nb0;
+    const int* tbptr;
+    const int* tb;
     const CUtensorMap* maps;
     int* info;
     double dbound;
@@ -98,9 +101,13 @@ static bool sparse_sync_debug() {
 // launch schedule of one phase (A: the supernodes this rank owns, B: the replicated top)
 struct Phase {
     std::vector<int> pptr, tptr, yptr;  // nlevels + 1 offsets into the task arrays
+    std::vector<int> psplit, tsplit;    // per level: tasks [ptr, split) have nc <= 64, [split, next) are wider
     int* d_potrf = nullptr;             // supernode ids, level by level
     int2* d_trsm = nullptr;             // (supernode, 64-row slab)
     int4* d_syrk = nullptr;             // (supernode, tile row, tile column, nc)
+    std::vector<int> fptr, bptr;        // nlevels + 1 offsets into the solve task arrays
+    int2* d_ftail = nullptr;            // forward sweep: (supernode, 512-row chunk of its rows below)
+    int2* d_bdots = nullptr;            // backward sweep: (supernode, group of 16 columns)
     int count = 0;
 };
 
@@ -119,6 +126,7 @@ struct SparseFactor {
     int* d_all = nullptr;      // supernodes factored on this rank (phase A then phase B)
     int nall = 0;
     double* d_x = nullptr;
+    double* d_dots = nullptr;  // backward sweep: B_s' z per column
     int* d_info = nullptr;
     long long wsize = 0;
     cudaGraphExec_t graph = nullptr;  // captured factorization (replayed while the operands stay put)
@@ -157,108 +165,174 @@ __global__ void sparse_assemble_kernel(long long anz, const int* __restrict__ ei
 }
 
 
-__device__ __forceinline__ int lower_bound_dev(const int* __restrict__ a, int lo, int hi, int key) {
-    while (lo < hi) {
-        const int mid = (lo + hi) >> 1;
-        if (a[mid] < key) lo = mid + 1;
-        else hi = mid;
-    }
-    return lo;
-}
+// Diagonal block of every supernode of a level: load, extend-add, Cholesky, store.  `ncmax` (64 or 128,
+// bounds nc over the launch) sizes the shared block, so narrow supernodes run several CTAs per SM.
+// The block moves by 1D bulk copies, one per column (columns start 128-byte aligned; nc rounded up
+// to even rows: the extra row is a zero pad row of the layout), all in flight at once.
+static inline int mf_diag_smem(int ncmax) { return (ncmax * CH_P + CH_NB) * 8 + 16; }
 
-constexpr int MF_DIAG_SMEM = (CH_NB * CH_P + CH_NB) * 8;
-
-// Diagonal block of every supernode of a level: load, extend-add, Cholesky, store.
 __global__ void __launch_bounds__(256)
-mf_potrf_kernel(const MfDesc d, const int* __restrict__ list) {
+mf_potrf_kernel(const MfDesc d, const int* __restrict__ list, int ncmax) {
     extern __shared__ __align__(128) double S[];
-    double* dinv = S + CH_NB * CH_P;
-    const int tid = threadIdx.x;
+    double* dinv = S + ncmax * CH_P;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dinv + CH_NB);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = list[blockIdx.x];
     const int col0 = d.first[s], nc = d.first[s + 1] - col0, ld = d.ld[s];
+    const int nc2 = (nc + 1) & ~1;
     double* blk = d.Lv + d.off[s];
-    for (int idx = tid; idx < nc * nc; idx += 256) {
-        const int cc = idx / nc, r = idx - cc * nc;
-        if (r >= cc) S[r + cc * CH_P] = blk[r + (long long)cc * ld];
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar, (uint32_t)(nc * nc2 * 8));
     }
     __syncthreads();
+    if (warp == 0)
+        for (int cc = lane; cc < nc; cc += 32) bulk_load_1d(S + cc * CH_P, blk + (long long)cc * ld, nc2 * 8, bar);
+    mbar_wait(bar, 0);
+    int* srl = reinterpret_cast<int*>(dinv);  // the child's parent-relative rows (dinv is written later)
     for (int q = d.childptr[s]; q < d.childptr[s + 1]; ++q) {
         const int c = d.child[q];
         const int cutc = d.cut[c];
         const double* Uc = d.U + d.uoff[c];
         const int lduc = d.ldu[c];
-        const int* rl = d.rel + d.relptr[c];
-        for (int idx = tid; idx < cutc * cutc; idx += 256) {
-            const int j = idx / cutc, i = idx - j * cutc;
-            if (i >= j) S[rl[i] + rl[j] * CH_P] += Uc[i + (long long)j * lduc];
+        if (tid < cutc) srl[tid] = d.rel[d.relptr[c] + tid];
+        __syncthreads();
+        // lane owns rows lane + 32k of the child's leading cutc x cutc triangle; two columns per step so
+        // that eight independent loads are in flight per lane
+        for (int j = warp; j < cutc; j += 16) {
+            const int j2 = j + 8;
+            const double* u1 = Uc + (long long)j * lduc;
+            const double* u2 = Uc + (long long)min(j2, cutc - 1) * lduc;
+            double v1[4], v2[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = lane + 32 * k;
+                v1[k] = (i >= j && i < cutc) ? u1[i] : 0.0;
+                v2[k] = (i >= j2 && i < cutc) ? u2[i] : 0.0;
+            }
+            const int t1 = srl[j] * CH_P, t2 = srl[min(j2, cutc - 1)] * CH_P;
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int i = lane + 32 * k;
+                if (i >= j && i < cutc) S[srl[i] + t1] += v1[k];
+            }
+            if (j2 < cutc) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const int i = lane + 32 * k;
+                    if (i >= j2 && i < cutc) S[srl[i] + t2] += v2[k];
+                }
+            }
         }
         __syncthreads();
     }
     potrf_block_smem(S, dinv, nc, d.dbound, d.info, col0);
-    __syncthreads();
-    for (int idx = tid; idx < nc * nc; idx += 256) {
-        const int cc = idx / nc, r = idx - cc * nc;
-        if (r >= cc) blk[r + (long long)cc * ld] = S[r + cc * CH_P];
-    }
     if (tid < nc) d.dinv[col0 + tid] = dinv[tid];
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+        for (int cc = lane; cc < nc; cc += 32) bulk_store_1d(blk + (long long)cc * ld, S + cc * CH_P, nc2 * 8);
+        tma_store_commit_and_wait();
+    }
 }
 
-// Rows below the diagonal block, 64 at a time: load, extend-add, X L' = B, store.
+// Rows below the diagonal block, 64 at a time: load, extend-add, X L' = B, store.  Shared memory is
+// sized by `ncmax` (64 or 128).  L's columns and the slab's columns arrive by bulk copies; the slab
+// leaves the same way (16-row granularity: the layout pads every block to 16 rows).
 constexpr int MF_TR_ROWS = 64;
-constexpr int MF_TR_SMEM = (CH_NB * CH_NB + MF_TR_ROWS * CH_NB + CH_NB) * 8;
+static inline int mf_tr_smem(int ncmax) { return (ncmax * CH_NB + MF_TR_ROWS * ncmax + CH_NB) * 8 + 16; }
 
 __global__ void __launch_bounds__(256)
-mf_trsm_kernel(const MfDesc d, const int2* __restrict__ tasks) {
-    extern __shared__ double sm[];
+mf_trsm_kernel(const MfDesc d, const int2* __restrict__ tasks, int ncmax) {
+    extern __shared__ __align__(128) double sm[];
     double* Ls = sm;                        // Ls[c + p*128] = L[c][p]
-    double* Xs = Ls + CH_NB * CH_NB;        // Xs[p*64 + row]
-    double* dv = Xs + MF_TR_ROWS * CH_NB;
-    const int tid = threadIdx.x;
-    const int s = tasks[blockIdx.x].x;
-    const int col0 = d.first[s], nc = d.first[s + 1] - col0, nr = d.nr[s], ld = d.ld[s];
-    const int row0 = nc + tasks[blockIdx.x].y * MF_TR_ROWS;
-    const int nrows = min(MF_TR_ROWS, nr - row0);
+    double* Xs = Ls + ncmax * CH_NB;        // Xs[p*64 + row]
+    double* dv = Xs + MF_TR_ROWS * ncmax;
+    uint64_t* bar = reinterpret_cast<uint64_t*>(dv + CH_NB);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = tasks[blockIdx.x].x, slab = tasks[blockIdx.x].y;
+    const int col0 = d.first[s], nc = d.first[s + 1] - col0, nr = d.nr[s], ld = d.ld[s], nb0 = d.nb0[s];
+    const int nu = nr - nc;
+    const int i0 = slab * MF_TR_ROWS;                 // first below-row of the slab
+    const int nrows = min(MF_TR_ROWS, nu - i0);
+    const int nrows16 = (nrows + 15) & ~15;           // rows moved (pad rows of the layout included)
     double* blk = d.Lv + d.off[s];
-    for (int idx = tid; idx < nc * CH_NB; idx += 256) {
-        const int p = idx >> 7, cc = idx & 127;
-        Ls[idx] = (cc >= p && cc < nc) ? blk[cc + (long long)p * ld] : 0.0;
-    }
-    if (tid < CH_NB) dv[tid] = (tid < nc) ? d.dinv[col0 + tid] : 1.0;
-    for (int idx = tid; idx < MF_TR_ROWS * nc; idx += 256) {
-        const int p = idx >> 6, rr = idx & 63;
-        Xs[idx] = (rr < nrows) ? blk[row0 + rr + (long long)p * ld] : 0.0;
+    double* slab_g = blk + nb0 + i0;
+    if (tid == 0) {
+        mbar_init(bar, 1);
+        fence_mbar_init();
+        mbar_expect_tx(bar, (uint32_t)(nc * (nb0 + nrows16) * 8));
     }
     __syncthreads();
+    if (warp == 0) {
+        for (int p = lane; p < nc; p += 32) {
+            bulk_load_1d(Ls + p * CH_NB, blk + (long long)p * ld, nb0 * 8, bar);   // rows nc..nb0-1 are zero pad
+            bulk_load_1d(Xs + p * MF_TR_ROWS, slab_g + (long long)p * ld, nrows16 * 8, bar);
+        }
+    }
+    // columns nc..nb0-1 of Ls (read by the 32-column blocking of trsm_slab_smem) are zero
+    for (int idx = tid; idx < (nb0 - nc) * CH_NB; idx += 256) Ls[nc * CH_NB + idx] = 0.0;
+    if (tid < CH_NB) dv[tid] = (tid < nc) ? d.dinv[col0 + tid] : 1.0;
+    mbar_wait(bar, 0);
+    __syncthreads();
+    __shared__ int srow[MF_TR_ROWS], scol[CH_NB];
     for (int q = d.childptr[s]; q < d.childptr[s + 1]; ++q) {
         const int c = d.child[q];
+        const int* tb = d.tb + d.tbptr[c];
+        const int ilo = tb[slab], ihi = tb[slab + 1];
+        if (ihi <= ilo) continue;  // uniform over the CTA
         const int cutc = d.cut[c];
-        const int nuc = d.nr[c] - (d.first[c + 1] - d.first[c]);
         const int* rl = d.rel + d.relptr[c];
-        const int ilo = lower_bound_dev(rl, cutc, nuc, row0);
-        const int ihi = lower_bound_dev(rl, ilo, nuc, row0 + nrows);
-        const int ni = ihi - ilo;
-        if (ni <= 0) continue;  // uniform over the CTA
         const double* Uc = d.U + d.uoff[c];
         const int lduc = d.ldu[c];
-        for (int idx = tid; idx < ni * cutc; idx += 256) {
-            const int j = idx / ni, i = ilo + idx - j * ni;
-            Xs[rl[j] * MF_TR_ROWS + rl[i] - row0] += Uc[i + (long long)j * lduc];
-        }
         __syncthreads();
+        if (tid < ihi - ilo) srow[tid] = rl[ilo + tid] - (nc + i0);   // slab-local row (ihi - ilo <= 64)
+        if (tid < cutc) scol[tid] = rl[tid] * MF_TR_ROWS;             // target column offset in Xs
+        __syncthreads();
+        const int ni = ihi - ilo;
+        // lane owns child rows ilo + lane, ilo + lane + 32; four child columns per step
+        for (int j = warp; j < cutc; j += 32) {
+            double v[4][2];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int jj = min(j + 8 * k, cutc - 1);
+                const double* ucol = Uc + (long long)jj * lduc + ilo;
+                v[k][0] = (lane < ni) ? ucol[lane] : 0.0;
+                v[k][1] = (lane + 32 < ni) ? ucol[lane + 32] : 0.0;
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int jj = j + 8 * k;
+                if (jj < cutc) {
+                    double* xcol = Xs + scol[jj];
+                    if (lane < ni) xcol[srow[lane]] += v[k][0];
+                    if (lane + 32 < ni) xcol[srow[lane + 32]] += v[k][1];
+                }
+            }
+        }
     }
-    trsm_slab_smem(Ls, Xs, dv, nc, nrows);
     __syncthreads();
-    for (int idx = tid; idx < MF_TR_ROWS * nc; idx += 256) {
-        const int p = idx >> 6, rr = idx & 63;
-        if (rr < nrows) blk[row0 + rr + (long long)p * ld] = Xs[idx];
+    trsm_slab_smem(Ls, Xs, dv, nc, nrows);
+    fence_proxy_async();
+    __syncthreads();
+    if (warp == 0) {
+        for (int p = lane; p < nc; p += 32) bulk_store_1d(slab_g + (long long)p * ld, Xs + p * MF_TR_ROWS, nrows16 * 8);
+        tma_store_commit_and_wait();
     }
 }
 
 // Update matrices of a level on the FP64 tensor cores.  Task = (supernode, tile row bi, tile column
-// bj <= bi, nc): U(bi, bj) = -L21[bi] L21[bj]' with K = nc <= 128, then the extend-add of the children.
+// bj <= bi, nc): U(bi, bj) = -L21[bi] L21[bj]' with K = nc <= 128, plus the children's contributions.
 // Same pipeline as dmma_nt_kernel (thread 0 doubles as the TMA producer, 8 DMMA warps of 64 x 32, 132-row
 // boxes so the fragment loads are conflict-free); the tensor map of the supernode's block comes from
 // a device array, rows past the block and columns past nc are zero-filled by TMA.
+// Extend-add happens IN REGISTERS: for every child the tile's 128 rows and 128 columns get an inverse
+// map in shared memory (tile row -> row of the child's update matrix, from the slab table of the
+// symbolic phase, no searching), and every lane gathers the child's entries that fall on its own
+// accumulator elements (independent loads, no read-modify-write of global memory, one store per element).
+constexpr int MF_SY_SMEM = NT_SMEM_BYTES + 2 * NT_BM * 4;
+
 __global__ void __launch_bounds__(NT_THREADS, 1)
 mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
     extern __shared__ uint8_t smem_raw[];
@@ -266,6 +340,8 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
         (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
     uint64_t* full = reinterpret_cast<uint64_t*>(smem + NT_STAGES * NT_STAGE_BYTES);
     uint64_t* empty = full + NT_STAGES;
+    int* inv_r = reinterpret_cast<int*>(empty + NT_STAGES + 2);
+    int* inv_c = inv_r + NT_BM;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool is_producer = (threadIdx.x == 0);
     if (threadIdx.x == 0) {
@@ -277,13 +353,14 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
     }
     __syncthreads();
 
-    int p_task = blockIdx.x, p_kc = 0, p_kch = 0;
+    int p_task = blockIdx.x, p_kc = 0, p_kch = 0, p_nb0 = 0;
     int4 pt = make_int4(0, 0, 0, 0);
     uint32_t p_it = 0;
     bool p_valid = false;
     if (is_producer && p_task < ntasks) {
         pt = tasks[p_task];
         p_kch = (pt.w + NT_BK - 1) / NT_BK;
+        p_nb0 = (pt.w + 31) & ~31;
         p_valid = true;
     }
     auto produce = [&]() {
@@ -296,12 +373,10 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
         mbar_expect_tx(&full[st_i], diag ? NT_TILE_BYTES : 2 * NT_TILE_BYTES);
         const CUtensorMap* mp = d.maps + pt.x;
         if (p_kc == 0) fence_tensormap_acquire(mp);
-        // the box must start on a 16-byte boundary (an odd row coordinate of an 8-byte type is an illegal
-        // instruction, measured: tools/tma_gmem_probe.cu): start one row early when nc is odd and let the
-        // consumers skip that row (the box has 132 rows for 128 used)
-        const int r0 = pt.w & ~1;
-        tma_load_2d(st, mp, r0 + pt.y * NT_BM, p_kc * NT_BK, &full[st_i]);
-        if (!diag) tma_load_2d(st + NT_TILE_BYTES, mp, r0 + pt.z * NT_BN, p_kc * NT_BK, &full[st_i]);
+        // (the box must start on a 16-byte boundary: an odd row coordinate of an 8-byte type is an illegal
+        // instruction, measured with tools/tma_gmem_probe.cu -- the layout keeps nb0 a multiple of 32)
+        tma_load_2d(st, mp, p_nb0 + pt.y * NT_BM, p_kc * NT_BK, &full[st_i]);
+        if (!diag) tma_load_2d(st + NT_TILE_BYTES, mp, p_nb0 + pt.z * NT_BN, p_kc * NT_BK, &full[st_i]);
         ++p_it;
         if (++p_kc >= p_kch) {
             p_task += gridDim.x;
@@ -310,10 +385,11 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
             if (p_valid) {
                 pt = tasks[p_task];
                 p_kch = (pt.w + NT_BK - 1) / NT_BK;
+                p_nb0 = (pt.w + 31) & ~31;
             }
         }
     };
-    if (is_producer && !(d.dbg & 4))
+    if (is_producer)
         for (int i = 0; i < NT_STAGES - 1; ++i) produce();
 
     const int g = lane >> 2, t4 = lane & 3;
@@ -331,7 +407,7 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
         for (int i = 0; i < 8; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-        for (int kc = 0; kc < kch && !(d.dbg & 4); ++kc, ++it) {
+        for (int kc = 0; kc < kch; ++kc, ++it) {
             if (is_producer) produce();
             __syncwarp();
             const int st_i = it % NT_STAGES;
@@ -339,8 +415,8 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
             mbar_wait(&full[st_i], ph);
             const double* sA = reinterpret_cast<const double*>(smem + st_i * NT_STAGE_BYTES);
             const double* sB = diag ? sA : sA + NT_PITCH * NT_BK;
-            const double* ap = sA + a_off + (nc & 1);
-            const double* bp = sB + b_off + (nc & 1);
+            const double* ap = sA + a_off;
+            const double* bp = sB + b_off;
 #pragma unroll
             for (int ks = 0; ks < NT_BK / 4; ++ks) {
                 double af[8], bf[4];
@@ -356,17 +432,53 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
             __syncwarp();
             if (lane == 0) mbar_arrive(&empty[st_i]);
         }
-        // epilogue: U tile = -acc (whole tile inside the matrix; only i >= j is ever read)
         const int nu = d.nr[s] - nc, ldu = d.ldu[s];
+        const int lr0 = wm * 64 + g;        // my rows inside the tile: lr0 + 8 i
+        const int lc0 = wn * 32 + 2 * t4;   // my columns: lc0 + 8 j + c2
+        // ---- extend-add in registers: acc holds +L21 L21', children are SUBTRACTED, the store negates
+        for (int q = d.childptr[s]; q < d.childptr[s + 1]; ++q) {
+            const int c = d.child[q];
+            const int* tb = d.tb + d.tbptr[c];
+            const int jlo = tb[2 * bj], jhi = tb[min(2 * bj + 2, (nu + 63) >> 6)];
+            const int ilo = tb[2 * bi], ihi = tb[min(2 * bi + 2, (nu + 63) >> 6)];
+            if (ihi <= ilo || jhi <= jlo) continue;  // uniform over the CTA
+            const int* rl = d.rel + d.relptr[c];
+            __syncthreads();  // the previous child's maps are no longer read
+            if (threadIdx.x < NT_BM) {
+                inv_r[threadIdx.x] = -1;
+                inv_c[threadIdx.x] = -1;
+            }
+            __syncthreads();
+            for (int i = ilo + (int)threadIdx.x; i < ihi; i += NT_THREADS) inv_r[rl[i] - nc - bi * NT_BM] = i;
+            for (int j = jlo + (int)threadIdx.x; j < jhi; j += NT_THREADS) inv_c[rl[j] - nc - bj * NT_BN] = j;
+            __syncthreads();
+            const double* Uc = d.U + d.uoff[c];
+            const int lduc = d.ldu[c];
+            int ci[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) ci[i] = inv_r[lr0 + 8 * i];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int c2 = 0; c2 < 2; ++c2) {
+                    const int cj = inv_c[lc0 + 8 * j + c2];
+                    if (cj < 0) continue;
+                    const double* ucol = Uc + (long long)cj * lduc;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        if (ci[i] >= cj) acc[i][j][c2] -= ucol[ci[i]];
+                }
+        }
+        // ---- store U tile = -acc (whole tile inside the matrix; only i >= j is ever read)
         double* Us = d.U + d.uoff[s];
-        const int row_base = bi * NT_BM + wm * 64 + g;
-        const int col_base = bj * NT_BN + wn * 32 + 2 * t4;
+        const int row_base = bi * NT_BM + lr0;
+        const int col_base = bj * NT_BN + lc0;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
             for (int c2 = 0; c2 < 2; ++c2) {
                 const int col = col_base + j * 8 + c2;
-                if (col < nu && !(d.dbg & 2)) {
+                if (col < nu) {
                     double* cp = Us + (long long)col * ldu;
 #pragma unroll
                     for (int i = 0; i < 8; ++i) {
@@ -375,29 +487,6 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
                     }
                 }
             }
-        const int q0 = d.childptr[s], q1 = d.childptr[s + 1];
-        if (q0 == q1 || (d.dbg & 1)) continue;
-        __syncthreads();  // the tile is complete (and visible to the whole CTA) before the children are added
-        const int r_lo = nc + bi * NT_BM, c_lo = nc + bj * NT_BN;
-        for (int q = q0; q < q1; ++q) {
-            const int c = d.child[q];
-            const int cutc = d.cut[c];
-            const int nuc = d.nr[c] - (d.first[c + 1] - d.first[c]);
-            const int* rl = d.rel + d.relptr[c];
-            const int jlo = lower_bound_dev(rl, cutc, nuc, c_lo);
-            const int jhi = lower_bound_dev(rl, jlo, nuc, c_lo + NT_BN);
-            const int ilo = diag ? jlo : lower_bound_dev(rl, jhi, nuc, r_lo);
-            const int ihi = diag ? jhi : lower_bound_dev(rl, ilo, nuc, r_lo + NT_BM);
-            const int ni = ihi - ilo, nj = jhi - jlo;
-            if (ni <= 0 || nj <= 0) continue;  // uniform over the CTA
-            const double* Uc = d.U + d.uoff[c];
-            const int lduc = d.ldu[c];
-            for (int idx = threadIdx.x; idx < ni * nj; idx += NT_THREADS) {
-                const int jj = idx / ni, i = ilo + idx - jj * ni, j = jlo + jj;
-                if (i >= j) Us[(rl[i] - nc) + (long long)(rl[j] - nc) * ldu] += Uc[i + (long long)j * lduc];
-            }
-            __syncthreads();
-        }
     }
 }
 
@@ -440,39 +529,26 @@ mf_trtri_kernel(const MfDesc d, const int* __restrict__ list) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// device: multifrontal triangular solves, one CTA per supernode, one launch per level
+// device: multifrontal triangular solves, two launches per level and sweep
 // ------------------------------------------------------------------------------------------------
+// W_s and B_s are read straight from global memory (every element is used once).  The long part of a
+// supernode -- the product with its nu x nc block B_s -- is cut into row chunks (forward) or column
+// groups (backward) that run on different SMs; a single CTA per supernode was latency-bound at ~10 GB/s.
 constexpr int MS_THREADS = 256;
-constexpr int MS_WP = 129;
 constexpr int MS_CHUNK = 2048;
-constexpr int MS_SMEM = (CH_NB * MS_WP + 4 * CH_NB + MS_CHUNK) * 8;
+constexpr int MS_FWD_ROWS = 256;   // rows of B_s per CTA in the forward sweep (multiple of 64)
+constexpr int MS_BWD_COLS = 16;    // columns of B_s per CTA in the backward sweep
 
-__device__ __forceinline__ void ms_stage_w(const MfDesc& d, int s, int nc, double* Ws) {
-    const double* Wb = d.W + d.woff[s];
-    for (int idx = threadIdx.x; idx < nc * nc; idx += MS_THREADS) {
-        const int cc = idx / nc, r = idx - cc * nc;
-        Ws[r + cc * MS_WP] = Wb[idx];
-    }
-}
-
-// forward: rhs_s = b_s - (children's update vectors inside my columns); y_s = W_s rhs_s;
-//          u_s = B_s y_s + (children's entries below my columns)
+// forward, head: rhs_s = b_s - (children's update vectors inside my columns); y_s = W_s rhs_s
 __global__ void __launch_bounds__(MS_THREADS)
-mf_fwd_kernel(const MfDesc d, const int* __restrict__ list, double* __restrict__ x) {
-    extern __shared__ double sm[];
-    double* Ws = sm;
-    double* rhs = Ws + CH_NB * MS_WP;
-    double* ys = rhs + CH_NB;
-    double* part = ys + CH_NB;  // 2 x 128
+mf_fwd_head_kernel(const MfDesc d, const int* __restrict__ list, double* __restrict__ x) {
+    __shared__ double rhs[CH_NB], part[2 * CH_NB];
     const int tid = threadIdx.x, t = tid & 127, half = tid >> 7;
     const int s = list[blockIdx.x];
-    const int col0 = d.first[s], nc = d.first[s + 1] - col0, nr = d.nr[s], ld = d.ld[s];
-    const int nu = nr - nc;
-    ms_stage_w(d, s, nc, Ws);
+    const int col0 = d.first[s], nc = d.first[s + 1] - col0;
     if (tid < CH_NB) rhs[tid] = (tid < nc) ? x[col0 + tid] : 0.0;
     __syncthreads();
-    const int q0 = d.childptr[s], q1 = d.childptr[s + 1];
-    for (int q = q0; q < q1; ++q) {
+    for (int q = d.childptr[s]; q < d.childptr[s + 1]; ++q) {
         const int c = d.child[q];
         const int cutc = d.cut[c];
         const double* uc = d.uvec + d.vptr[c];
@@ -480,111 +556,141 @@ mf_fwd_kernel(const MfDesc d, const int* __restrict__ list, double* __restrict__
         for (int i = tid; i < cutc; i += MS_THREADS) rhs[rl[i]] -= uc[i];
         __syncthreads();
     }
-    {
-        const int c_lo = half * 64, c_hi = min(nc, c_lo + 64);
-        double a0 = 0.0, a1 = 0.0;
-        if (t < nc) {
-            int cc = c_lo;
-            for (; cc + 1 < c_hi; cc += 2) {
-                a0 = fma(Ws[t + cc * MS_WP], rhs[cc], a0);
-                a1 = fma(Ws[t + (cc + 1) * MS_WP], rhs[cc + 1], a1);
-            }
-            if (cc < c_hi) a0 = fma(Ws[t + cc * MS_WP], rhs[cc], a0);
+    // y = W rhs, W lower triangular, column-major nc x nc: thread t owns row t, two halves of the columns
+    const double* Wb = d.W + d.woff[s];
+    const int c_lo = half * 64, c_hi = min(t + 1, min(nc, c_lo + 64));
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (t < nc) {
+        int cc = c_lo;
+        for (; cc + 3 < c_hi; cc += 4) {
+            a0 = fma(Wb[t + (cc + 0) * nc], rhs[cc + 0], a0);
+            a1 = fma(Wb[t + (cc + 1) * nc], rhs[cc + 1], a1);
+            a2 = fma(Wb[t + (cc + 2) * nc], rhs[cc + 2], a2);
+            a3 = fma(Wb[t + (cc + 3) * nc], rhs[cc + 3], a3);
         }
-        part[half * CH_NB + t] = a0 + a1;
+        for (; cc < c_hi; ++cc) a0 = fma(Wb[t + cc * nc], rhs[cc], a0);
     }
+    part[half * CH_NB + t] = (a0 + a1) + (a2 + a3);
     __syncthreads();
-    if (tid < CH_NB) {
-        const double y = (tid < nc) ? part[tid] + part[CH_NB + tid] : 0.0;
-        ys[tid] = y;
-        if (tid < nc) x[col0 + tid] = y;
+    if (tid < nc) x[col0 + tid] = part[tid] + part[CH_NB + tid];
+}
+
+// forward, tail: rows [256 k, 256 k + 256) of u_s = B_s y_s + (children's entries that land there).
+// Lane l of every warp owns rows l, l+32, ... (coalesced along the columns of B_s), warp w owns the
+// columns w, w+8, ...; the eight partial vectors are summed through shared memory in warp order.
+__global__ void __launch_bounds__(MS_THREADS)
+mf_fwd_tail_kernel(const MfDesc d, const int2* __restrict__ tasks, const double* __restrict__ x) {
+    __shared__ double ys[CH_NB];
+    __shared__ double part[8][MS_FWD_ROWS];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = tasks[blockIdx.x].x, chunk = tasks[blockIdx.x].y;
+    const int col0 = d.first[s], nc = d.first[s + 1] - col0, nr = d.nr[s], ld = d.ld[s];
+    const int nu = nr - nc;
+    const int i0 = chunk * MS_FWD_ROWS, i1 = min(nu, i0 + MS_FWD_ROWS);
+    if (tid < CH_NB) ys[tid] = (tid < nc) ? x[col0 + tid] : 0.0;
+    __syncthreads();
+    const double* B = d.Lv + d.off[s] + d.nb0[s] + i0;
+    double a[MS_FWD_ROWS / 32];
+#pragma unroll
+    for (int k = 0; k < MS_FWD_ROWS / 32; ++k) a[k] = 0.0;
+    for (int cc = warp; cc < nc; cc += 8) {
+        const double* bc = B + (long long)cc * ld;
+        const double y = ys[cc];
+#pragma unroll
+        for (int k = 0; k < MS_FWD_ROWS / 32; ++k) {
+            const int i = lane + 32 * k;
+            if (i0 + i < i1) a[k] = fma(bc[i], y, a[k]);
+        }
     }
+#pragma unroll
+    for (int k = 0; k < MS_FWD_ROWS / 32; ++k) part[warp][lane + 32 * k] = a[k];
     __syncthreads();
-    if (nu == 0) return;
     double* us = d.uvec + d.vptr[s];
-    const double* B = d.Lv + d.off[s] + nc;
-    for (int i = tid; i < nu; i += MS_THREADS) {
-        double a0 = 0.0, a1 = 0.0;
-        int cc = 0;
-        for (; cc + 1 < nc; cc += 2) {
-            a0 = fma(B[i + (long long)cc * ld], ys[cc], a0);
-            a1 = fma(B[i + (long long)(cc + 1) * ld], ys[cc + 1], a1);
-        }
-        if (cc < nc) a0 = fma(B[i + (long long)cc * ld], ys[cc], a0);
-        us[i] = a0 + a1;
+    for (int i = tid; i < i1 - i0; i += MS_THREADS) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += part[w][i];
+        us[i0 + i] = v;
     }
-    for (int q = q0; q < q1; ++q) {
+    const int nslab = (nu + 63) >> 6;
+    for (int q = d.childptr[s]; q < d.childptr[s + 1]; ++q) {
         __syncthreads();
         const int c = d.child[q];
-        const int cutc = d.cut[c];
-        const int nuc = d.nr[c] - (d.first[c + 1] - d.first[c]);
+        const int* tb = d.tb + d.tbptr[c];
+        const int ilo = tb[min(nslab, i0 >> 6)], ihi = tb[min(nslab, (i0 + MS_FWD_ROWS) >> 6)];
         const double* uc = d.uvec + d.vptr[c];
         const int* rl = d.rel + d.relptr[c];
-        for (int i = cutc + tid; i < nuc; i += MS_THREADS) us[rl[i] - nc] += uc[i];
+        for (int i = ilo + tid; i < ihi; i += MS_THREADS) us[rl[i] - nc] += uc[i];
     }
 }
 
-// backward: z_s = W_s' (y_s - B_s' z[rows below])
+// backward, dots: for 16 columns of B_s, dots[col] = B_s(:, col)' z[rows below]; warp w owns 2 columns
 __global__ void __launch_bounds__(MS_THREADS)
-mf_bwd_kernel(const MfDesc d, const int* __restrict__ list, double* __restrict__ x) {
-    extern __shared__ double sm[];
-    double* Ws = sm;
-    double* rhs = Ws + CH_NB * MS_WP;
-    double* dots = rhs + CH_NB;
-    double* part = dots + CH_NB;  // 2 x 128
-    double* zr = part + 2 * CH_NB;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, t = tid & 127, half = tid >> 7;
-    const int s = list[blockIdx.x];
+mf_bwd_dots_kernel(const MfDesc d, const int2* __restrict__ tasks, const double* __restrict__ x,
+                   double* __restrict__ dots) {
+    __shared__ double zr[MS_CHUNK];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = tasks[blockIdx.x].x, grp = tasks[blockIdx.x].y;
     const int col0 = d.first[s], nc = d.first[s + 1] - col0, nr = d.nr[s], ld = d.ld[s];
     const int nu = nr - nc;
-    ms_stage_w(d, s, nc, Ws);
-    if (tid < CH_NB) rhs[tid] = (tid < nc) ? x[col0 + tid] : 0.0;
-    const double* B = d.Lv + d.off[s] + nc;
+    const double* B = d.Lv + d.off[s] + d.nb0[s];
     const int* R = d.rows + d.rowptr[s] + nc;
-    double acc[16];
-#pragma unroll
-    for (int k = 0; k < 16; ++k) acc[k] = 0.0;
+    const int ca = grp * MS_BWD_COLS + warp, cb = ca + 8;
+    double acc_a = 0.0, acc_b = 0.0;
     for (int base = 0; base < nu; base += MS_CHUNK) {
         const int len = min(MS_CHUNK, nu - base);
         __syncthreads();
         for (int i = tid; i < len; i += MS_THREADS) zr[i] = x[R[base + i]];
         __syncthreads();
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const int cc = warp + 8 * k;
-            if (cc < nc) {
-                const double* bc = B + base + (long long)cc * ld;
-                double a = 0.0;
-                for (int i = lane; i < len; i += 32) a = fma(bc[i], zr[i], a);
-                acc[k] += a;
+        if (ca < nc) {
+            const double* bc = B + base + (long long)ca * ld;
+            const double* bd = B + base + (long long)min(cb, nc - 1) * ld;
+            double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
+            int i = lane;
+            for (; i + 32 < len; i += 64) {
+                a0 = fma(bc[i], zr[i], a0);
+                b0 = fma(bd[i], zr[i], b0);
+                a1 = fma(bc[i + 32], zr[i + 32], a1);
+                b1 = fma(bd[i + 32], zr[i + 32], b1);
             }
+            if (i < len) {
+                a0 = fma(bc[i], zr[i], a0);
+                b0 = fma(bd[i], zr[i], b0);
+            }
+            acc_a += a0 + a1;
+            acc_b += b0 + b1;
         }
     }
 #pragma unroll
-    for (int k = 0; k < 16; ++k) {
-        double a = acc[k];
+    for (int o = 16; o > 0; o >>= 1) {
+        acc_a += __shfl_xor_sync(0xffffffffu, acc_a, o);
+        acc_b += __shfl_xor_sync(0xffffffffu, acc_b, o);
+    }
+    if (lane == 0) {
+        if (ca < nc) dots[col0 + ca] = acc_a;
+        if (cb < nc) dots[col0 + cb] = acc_b;
+    }
+}
+
+// backward, finish: z_s = W_s' (y_s - dots); warp w owns columns w, w+8, ... of W_s
+__global__ void __launch_bounds__(MS_THREADS)
+mf_bwd_finish_kernel(const MfDesc d, const int* __restrict__ list, double* __restrict__ x,
+                     const double* __restrict__ dots) {
+    __shared__ double rhs[CH_NB];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int s = list[blockIdx.x];
+    const int col0 = d.first[s], nc = d.first[s + 1] - col0, nu = d.nr[s] - nc;
+    if (tid < CH_NB) rhs[tid] = (tid < nc) ? x[col0 + tid] - (nu > 0 ? dots[col0 + tid] : 0.0) : 0.0;
+    __syncthreads();
+    const double* Wb = d.W + d.woff[s];
+    for (int t = warp; t < nc; t += 8) {   // z_t = sum_{cc >= t} W(cc, t) rhs[cc]
+        const double* wc = Wb + (long long)t * nc;
+        double a = 0.0;
+        for (int cc = t + lane; cc < nc; cc += 32) a = fma(wc[cc], rhs[cc], a);
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) dots[warp + 8 * k] = a;
+        if (lane == 0) x[col0 + t] = a;
     }
-    __syncthreads();
-    if (tid < CH_NB) rhs[tid] -= dots[tid];
-    __syncthreads();
-    {
-        const int c_lo = half * 64, c_hi = min(nc, c_lo + 64);
-        double a0 = 0.0, a1 = 0.0;
-        if (t < nc) {
-            int cc = c_lo;
-            for (; cc + 1 < c_hi; cc += 2) {
-                a0 = fma(Ws[cc + t * MS_WP], rhs[cc], a0);
-                a1 = fma(Ws[(cc + 1) + t * MS_WP], rhs[cc + 1], a1);
-            }
-            if (cc < c_hi) a0 = fma(Ws[cc + t * MS_WP], rhs[cc], a0);
-        }
-        part[half * CH_NB + t] = a0 + a1;
-    }
-    __syncthreads();
-    if (tid < nc) x[col0 + tid] = part[tid] + part[CH_NB + tid];
 }
 
 // multi-GPU: keep only the pieces of the solution this rank is responsible for (its own supernodes;
@@ -613,12 +719,10 @@ __global__ void gather_perm_kernel(int m, const int* __restrict__ perm, const do
 static int sparse_configure(nes_ctx* c) {
     static bool done = false;
     if (done) return 0;
-    NES_CUDA(c, cudaFuncSetAttribute(mf_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_DIAG_SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(mf_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_TR_SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(mf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM_BYTES));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mf_diag_smem(CH_NB)));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mf_tr_smem(CH_NB)));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SY_SMEM));
     NES_CUDA(c, cudaFuncSetAttribute(mf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_TI_SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(mf_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(mf_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MS_SMEM));
     done = true;
     return 0;
 }
@@ -661,30 +765,48 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
         std::vector<int> potrf;
         std::vector<int2> trsm;
         std::vector<int4> syrk;
+        std::vector<int2> ftail, bdots;
+        P.fptr.assign(S.nlevels + 1, 0);
+        P.bptr.assign(S.nlevels + 1, 0);
         P.pptr.assign(S.nlevels + 1, 0);
         P.tptr.assign(S.nlevels + 1, 0);
         P.yptr.assign(S.nlevels + 1, 0);
+        P.psplit.assign(S.nlevels, 0);
+        P.tsplit.assign(S.nlevels, 0);
         for (int l = 0; l < S.nlevels; ++l) {
-            for (int s = S.lvlptr[l]; s < S.lvlptr[l + 1]; ++s) {
-                const bool mine = (ph == 0) ? (S.owner[s] == c->rank) : (S.owner[s] < 0);
-                if (!mine) continue;
-                const int nc = S.first[s + 1] - S.first[s], nu = S.nr[s] - nc;
-                potrf.push_back(s);
-                for (int k = 0; k * MF_TR_ROWS < nu; ++k) trsm.push_back(make_int2(s, k));
-                const int tn = (nu + NT_BM - 1) / NT_BM;
-                for (int bi = 0; bi < tn; ++bi)
-                    for (int bj = 0; bj <= bi; ++bj) syrk.push_back(make_int4(s, bi, bj, nc));
+            for (int wide = 0; wide < 2; ++wide) {  // narrow supernodes first: they launch with less smem
+                for (int s = S.lvlptr[l]; s < S.lvlptr[l + 1]; ++s) {
+                    const bool mine = (ph == 0) ? (S.owner[s] == c->rank) : (S.owner[s] < 0);
+                    const int nc = S.first[s + 1] - S.first[s], nu = S.nr[s] - nc;
+                    if (!mine || (nc > 64) != (wide == 1)) continue;
+                    potrf.push_back(s);
+                    for (int k = 0; k * MF_TR_ROWS < nu; ++k) trsm.push_back(make_int2(s, k));
+                    const int tn = (nu + NT_BM - 1) / NT_BM;
+                    for (int bi = 0; bi < tn; ++bi)
+                        for (int bj = 0; bj <= bi; ++bj) syrk.push_back(make_int4(s, bi, bj, nc));
+                    for (int k = 0; k * MS_FWD_ROWS < nu; ++k) ftail.push_back(make_int2(s, k));
+                    if (nu > 0)
+                        for (int k = 0; k * MS_BWD_COLS < nc; ++k) bdots.push_back(make_int2(s, k));
+                }
+                if (wide == 0) {
+                    P.psplit[l] = (int)potrf.size();
+                    P.tsplit[l] = (int)trsm.size();
+                }
             }
             P.pptr[l + 1] = (int)potrf.size();
             P.tptr[l + 1] = (int)trsm.size();
             P.yptr[l + 1] = (int)syrk.size();
+            P.fptr[l + 1] = (int)ftail.size();
+            P.bptr[l + 1] = (int)bdots.size();
         }
         P.count = (int)potrf.size();
         all.insert(all.end(), potrf.begin(), potrf.end());
         P.d_potrf = up_vec(c, sf, potrf);
         P.d_trsm = up_vec(c, sf, trsm);
         P.d_syrk = up_vec(c, sf, syrk);
-        if (!P.d_potrf || !P.d_trsm || !P.d_syrk) return c->status < 0 ? c->status : NES_ERR_OUT_OF_MEMORY;
+        P.d_ftail = up_vec(c, sf, ftail);
+        P.d_bdots = up_vec(c, sf, bdots);
+        if (!P.d_potrf || !P.d_trsm || !P.d_syrk || !P.d_ftail || !P.d_bdots) return c->status < 0 ? c->status : NES_ERR_OUT_OF_MEMORY;
     }
     sf->nall = (int)all.size();
     sf->d_all = up_vec(c, sf, all);
@@ -712,6 +834,10 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
     d.relptr = up_vec(c, sf, S.relptr);
     d.rel = up_vec(c, sf, S.rel);
     d.cut = up_vec(c, sf, S.cut);
+    d.nb0 = up_vec(c, sf, S.nb0);
+    d.tbptr = up_vec(c, sf, S.tbptr);
+    d.tb = up_vec(c, sf, S.tb);
+    sf->d_dots = dev_new<double>(c, sf, (size_t)m);
     sf->d_perm = up_vec(c, sf, S.perm);
     sf->d_ei = up_vec(c, sf, S.ei);
     sf->d_ej = up_vec(c, sf, S.ej);
@@ -727,7 +853,7 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
     d.info = sf->d_info;
     L->d_rhs = static_cast<double*>(dev_alloc(c, (size_t)(m + 16) * sizeof(double)));
     const bool ok = d.off && d.uoff && d.woff && d.vptr && d.first && d.nr && d.ld && d.ldu && d.rowptr && d.rows &&
-                    d.childptr && d.child && d.relptr && d.rel && d.cut && sf->d_perm && sf->d_ei && sf->d_ej &&
+                    d.childptr && d.child && d.relptr && d.rel && d.cut && d.nb0 && d.tbptr && d.tb && sf->d_dots && sf->d_perm && sf->d_ei && sf->d_ej &&
                     sf->d_edest && sf->d_owner && sf->d_all && d.Lv && d.U && d.dinv && d.W && d.uvec && sf->d_x &&
                     sf->d_info && L->d_rhs;
     if (!ok) return c->status < 0 ? c->status : NES_ERR_OUT_OF_MEMORY;
@@ -743,7 +869,7 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
                 memset(&maps[s], 0, sizeof(CUtensorMap));
                 continue;
             }
-            if (make_operand_map(&maps[s], d.Lv + S.off[s], S.nr[s], nc, S.ld[s]) != 0)
+            if (make_operand_map(&maps[s], d.Lv + S.off[s], S.nb0[s] + S.nr[s] - nc, nc, S.ld[s]) != 0)
                 return fail(c, NES_ERR_CUDA, "cuTensorMapEncodeTiled failed for supernode %d (%d x %d)", s, S.nr[s], nc);
         }
         CUtensorMap* dm = static_cast<CUtensorMap*>(dev_alloc(c, (size_t)(ns + 1) * sizeof(CUtensorMap)));
@@ -776,19 +902,25 @@ static int run_factor_phase(nes_ctx* c, SparseFactor* sf, int ph) {
     const Phase& P = sf->phase[ph];
     const Symbolic& S = sf->S;
     for (int l = 0; l < S.nlevels; ++l) {
-        const int np = P.pptr[l + 1] - P.pptr[l];
-        if (np == 0) continue;
-        mf_potrf_kernel<<<np, 256, MF_DIAG_SMEM, c->stream>>>(sf->d, P.d_potrf + P.pptr[l]);
-        MF_LAUNCHED(c, "mf_potrf_kernel");
-        const int nt = P.tptr[l + 1] - P.tptr[l];
-        if (nt > 0) {
-            mf_trsm_kernel<<<nt, 256, MF_TR_SMEM, c->stream>>>(sf->d, P.d_trsm + P.tptr[l]);
+        if (P.pptr[l + 1] == P.pptr[l]) continue;
+        for (int wide = 0; wide < 2; ++wide) {
+            const int a = wide ? P.psplit[l] : P.pptr[l], b = wide ? P.pptr[l + 1] : P.psplit[l];
+            if (b <= a) continue;
+            const int ncmax = wide ? CH_NB : 64;
+            mf_potrf_kernel<<<b - a, 256, mf_diag_smem(ncmax), c->stream>>>(sf->d, P.d_potrf + a, ncmax);
+            MF_LAUNCHED(c, "mf_potrf_kernel");
+        }
+        for (int wide = 0; wide < 2; ++wide) {
+            const int a = wide ? P.tsplit[l] : P.tptr[l], b = wide ? P.tptr[l + 1] : P.tsplit[l];
+            if (b <= a) continue;
+            const int ncmax = wide ? CH_NB : 64;
+            mf_trsm_kernel<<<b - a, 256, mf_tr_smem(ncmax), c->stream>>>(sf->d, P.d_trsm + a, ncmax);
             MF_LAUNCHED(c, "mf_trsm_kernel");
         }
         const int ny = P.yptr[l + 1] - P.yptr[l];
         if (ny > 0) {
             const int grid = ny < c->num_sms ? ny : c->num_sms;
-            mf_syrk_kernel<<<grid, NT_THREADS, NT_SMEM_BYTES, c->stream>>>(sf->d, P.d_syrk + P.yptr[l], ny);
+            mf_syrk_kernel<<<grid, NT_THREADS, MF_SY_SMEM, c->stream>>>(sf->d, P.d_syrk + P.yptr[l], ny);
             MF_LAUNCHED(c, "mf_syrk_kernel");
         }
     }
@@ -865,9 +997,23 @@ static int run_solve_phase(nes_ctx* c, SparseFactor* sf, int ph, bool backward) 
         const int l = backward ? nl - 1 - k : k;
         const int np = P.pptr[l + 1] - P.pptr[l];
         if (np == 0) continue;
-        if (!backward) mf_fwd_kernel<<<np, MS_THREADS, MS_SMEM, c->stream>>>(sf->d, P.d_potrf + P.pptr[l], sf->d_x);
-        else mf_bwd_kernel<<<np, MS_THREADS, MS_SMEM, c->stream>>>(sf->d, P.d_potrf + P.pptr[l], sf->d_x);
-        MF_LAUNCHED(c, backward ? "mf_bwd_kernel" : "mf_fwd_kernel");
+        if (!backward) {
+            mf_fwd_head_kernel<<<np, MS_THREADS, 0, c->stream>>>(sf->d, P.d_potrf + P.pptr[l], sf->d_x);
+            MF_LAUNCHED(c, "mf_fwd_head_kernel");
+            const int nt = P.fptr[l + 1] - P.fptr[l];
+            if (nt > 0) {
+                mf_fwd_tail_kernel<<<nt, MS_THREADS, 0, c->stream>>>(sf->d, P.d_ftail + P.fptr[l], sf->d_x);
+                MF_LAUNCHED(c, "mf_fwd_tail_kernel");
+            }
+        } else {
+            const int nt = P.bptr[l + 1] - P.bptr[l];
+            if (nt > 0) {
+                mf_bwd_dots_kernel<<<nt, MS_THREADS, 0, c->stream>>>(sf->d, P.d_bdots + P.bptr[l], sf->d_x, sf->d_dots);
+                MF_LAUNCHED(c, "mf_bwd_dots_kernel");
+            }
+            mf_bwd_finish_kernel<<<np, MS_THREADS, 0, c->stream>>>(sf->d, P.d_potrf + P.pptr[l], sf->d_x, sf->d_dots);
+            MF_LAUNCHED(c, "mf_bwd_finish_kernel");
+        }
     }
     return 0;
 }
@@ -917,7 +1063,8 @@ int sparse_factor_to_dense(nes_ctx* c, nes_factor* L, double* Lout, size_t ldo, 
         const int* R = S.rows.data() + S.rowptr[s];
         for (int cc = 0; cc < nc; ++cc)
             for (int r = cc; r < nr; ++r)
-                Lout[(size_t)R[r] + (size_t)(col0 + cc) * ldo] = h[(size_t)S.off[s] + r + (size_t)cc * S.ld[s]];
+                Lout[(size_t)R[r] + (size_t)(col0 + cc) * ldo] =
+                    h[(size_t)S.off[s] + (r < nc ? r : r - nc + S.nb0[s]) + (size_t)cc * S.ld[s]];
     }
     if (perm_out)
         for (int i = 0; i < sf->m; ++i) perm_out[i] = S.perm[i];

@@ -489,6 +489,7 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
     // rows(s) = columns of s, then { i > last(s) : i adjacent to a column of s, or i below a child of s }
     S->nr.resize(ns);
     S->ld.resize(ns);
+    S->nb0.resize(ns);
     S->rowptr.assign(ns + 1, 0);
     S->off.assign(ns + 1, 0);
     {
@@ -524,7 +525,8 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
             for (int j = f; j <= l; ++j) S->rows.push_back(j);
             S->rows.insert(S->rows.end(), tmp.begin(), tmp.end());
             S->nr[s] = nc + (int)tmp.size();
-            S->ld[s] = (S->nr[s] + 15) & ~15;
+            S->nb0[s] = (nc + 31) & ~31;
+            S->ld[s] = S->nb0[s] + (((int)tmp.size() + 15) & ~15);
             S->rowptr[s + 1] = (int)S->rows.size();
             S->off[s + 1] = S->off[s] + (long long)S->ld[s] * nc;
         }
@@ -559,6 +561,29 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
             if (R[i] <= plast) ++cut;
         }
         S->cut[s] = cut;
+    }
+    S->tbptr.assign(ns + 1, 0);
+    for (int s = 0; s < ns; ++s) {
+        const int p = S->sparent[s];
+        int cnt = 0;
+        if (p >= 0 && S->nr[s] > first[s + 1] - first[s]) {
+            const int nup = S->nr[p] - (first[p + 1] - first[p]);
+            cnt = (nup + 63) / 64 + 1;
+        }
+        S->tbptr[s + 1] = S->tbptr[s] + cnt;
+    }
+    S->tb.resize(S->tbptr[ns]);
+    for (int s = 0; s < ns; ++s) {
+        const int cnt = S->tbptr[s + 1] - S->tbptr[s];
+        if (cnt == 0) continue;
+        const int p = S->sparent[s];
+        const int ncp = first[p + 1] - first[p], nu = S->nr[s] - (first[s + 1] - first[s]);
+        const int* rl = S->rel.data() + S->relptr[s];
+        int i = S->cut[s];
+        for (int k = 0; k < cnt; ++k) {
+            while (i < nu && rl[i] < ncp + 64 * k) ++i;
+            S->tb[S->tbptr[s] + k] = i;
+        }
     }
 
     // ---- subtree-to-rank mapping ----------------------------------------------------------------------------
@@ -762,7 +787,7 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
                 if (p >= nrs) return set_err(err, errlen, "symbolic analysis: entry (%d, %d) outside its supernode", i, j);
                 S->ei.push_back(perm[i]);
                 S->ej.push_back(oj);
-                S->edest.push_back(base + p);
+                S->edest.push_back(base + (p < first[s + 1] - first[s] ? p : p + S->nb0[s] - (first[s + 1] - first[s])));
             }
         }
     }
@@ -804,6 +829,7 @@ long long nes_symbolic_ints(const void* sym, const char* name, const int** data)
     } tab[] = {{"perm", &S->perm},       {"first", &S->first},     {"nr", &S->nr},           {"ld", &S->ld},
                {"rows", &S->rows},       {"rowptr", &S->rowptr},   {"sparent", &S->sparent}, {"level", &S->level},
                {"lvlptr", &S->lvlptr},   {"childptr", &S->childptr}, {"child", &S->child},   {"relptr", &S->relptr},
+               {"nb0", &S->nb0},         {"tbptr", &S->tbptr},     {"tb", &S->tb},
                {"rel", &S->rel},         {"cut", &S->cut},         {"ldu", &S->ldu},         {"owner", &S->owner},
                {"ei", &S->ei},           {"ej", &S->ej},           {"segptr", &S->segptr},   {"seg_tid", &S->seg_tid},
                {"inptr", &S->inptr},     {"in_s", &S->in_s}};

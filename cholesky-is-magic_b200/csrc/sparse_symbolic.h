@@ -17,6 +17,10 @@ struct Symbolic {
     // assembly tree (leaves = level 0), so [lvlptr[l], lvlptr[l+1]) are independent of each other
     std::vector<int> first;         // nsuper + 1
     std::vector<int> nr, ld;        // rows of the supernode's block of L; its leading dimension (16-aligned)
+    // Block layout: rows 0..nc-1 are the diagonal block, the nu = nr - nc rows below it start at storage
+    // row nb0 = nc rounded up to 32 (the pad rows stay zero), so slabs and TMA boxes of the rows below
+    // start 128-byte aligned; ld = nb0 + nu rounded up to 16.
+    std::vector<int> nb0;
     std::vector<int> rowptr, rows;  // sorted row lists (permuted numbering); the first nc rows are the columns
     std::vector<long long> off;     // nsuper + 1: offset of the block in the L storage (doubles, 16-aligned)
     long long lsize = 0;
@@ -26,6 +30,10 @@ struct Symbolic {
     // multifrontal maps: below-row i of s (i < nu = nr - nc) is row rel[relptr[s] + i] of the parent's
     // row list; the first cut[s] of them are columns of the parent
     std::vector<int> relptr, rel, cut;
+    // tb[tbptr[s] + k] = first below-row i of s whose parent row rel[i] is >= nc_parent + 64 k
+    // (k = 0 .. ceil(nu_parent / 64)): the rows of s that land in each 64-row slab of the parent's rows
+    // below, precomputed so the extend-add kernels do not search
+    std::vector<int> tbptr, tb;
     // update matrices U_s (nu x nu, ld ldu, lower triangle): offsets in a pool whose slots are reused
     // once the parent has consumed them
     std::vector<int> ldu;

@@ -133,7 +133,7 @@ def _prototypes(lib):
 _lib = None
 
 _SYM_INTS = ("perm", "first", "nr", "ld", "rows", "rowptr", "sparent", "level", "lvlptr", "childptr", "child",
-             "relptr", "rel", "cut", "ldu", "owner", "ei", "ej", "segptr", "seg_tid", "inptr", "in_s")
+             "relptr", "rel", "cut", "ldu", "nb0", "tbptr", "tb", "owner", "ei", "ej", "segptr", "seg_tid", "inptr", "in_s")
 _SYM_LONGS = ("off", "uoff", "edest", "vptr", "xu_off", "xv_off")
 _SYM_SCALARS = ("anz", "aatfl", "lnz", "fl", "lsize", "usize", "nsuper", "nlevels")
 

@@ -42,6 +42,7 @@ def multifrontal_numeric(S, M):
     """NumPy emulation of sparse_chol.cu's numeric phase on the symbolic structure S."""
     ns = int(S["nsuper"])
     first, nr, ld, rowptr, rows, off = S["first"], S["nr"], S["ld"], S["rowptr"], S["rows"], S["off"]
+    nb0 = S["nb0"]
     perm = S["perm"]
     Lv = np.zeros(int(S["lsize"]))
     U = np.full(int(S["usize"]), np.nan)       # pool with slot reuse
@@ -50,7 +51,9 @@ def multifrontal_numeric(S, M):
     for lvl in range(int(S["nlevels"])):
         for s in range(S["lvlptr"][lvl], S["lvlptr"][lvl + 1]):
             nc = first[s + 1] - first[s]; nu = nr[s] - nc
-            blk = Lv[off[s]: off[s] + ld[s] * nc].reshape(nc, ld[s]).T          # view, column-major
+            full = Lv[off[s]: off[s] + ld[s] * nc].reshape(nc, ld[s]).T         # view, column-major
+            assert nb0[s] % 32 == 0 and nb0[s] >= nc and ld[s] >= nb0[s] + nu
+            blk = full[np.r_[0:nc, nb0[s]:nb0[s] + nu], :]                      # copy: diagonal block + rows below
             Us = None
             if nu:
                 Us = U[S["uoff"][s]: S["uoff"][s] + S["ldu"][s] * nu].reshape(nu, S["ldu"][s]).T
@@ -59,6 +62,10 @@ def multifrontal_numeric(S, M):
                 cnc = first[c + 1] - first[c]; cnu = nr[c] - cnc
                 Uc = U[S["uoff"][c]: S["uoff"][c] + S["ldu"][c] * cnu].reshape(cnu, S["ldu"][c]).T
                 rel = S["rel"][S["relptr"][c]: S["relptr"][c + 1]]
+                tb = S["tb"][S["tbptr"][c]: S["tbptr"][c + 1]]               # 64-row slab boundaries
+                assert len(tb) == (nu + 63) // 64 + 1 and tb[-1] == cnu
+                for k in range(len(tb)):
+                    assert tb[k] == S["cut"][c] + np.searchsorted(rel[S["cut"][c]:], nc + 64 * k)
                 assert np.array_equal(rows[rowptr[s]: rowptr[s + 1]][rel], rows[rowptr[c] + cnc: rowptr[c + 1]])
                 cut = S["cut"][c]
                 assert np.all(rel[:cut] < nc) and np.all(rel[cut:] >= nc)
@@ -74,11 +81,14 @@ def multifrontal_numeric(S, M):
             if nu:
                 blk[nc:nr[s], :] = np.linalg.solve(Ld, blk[nc:nr[s], :].T).T
                 Us[:nu, :nu] -= np.tril(blk[nc:nr[s], :] @ blk[nc:nr[s], :].T)
+            full[0:nc, :] = blk[:nc, :]
+            full[nb0[s]:nb0[s] + nu, :] = blk[nc:, :]
     m = len(perm)
     L = np.zeros((m, m))
     for s in range(ns):
         nc = first[s + 1] - first[s]
-        blk = Lv[off[s]: off[s] + ld[s] * nc].reshape(nc, ld[s]).T
+        full = Lv[off[s]: off[s] + ld[s] * nc].reshape(nc, ld[s]).T
+        blk = full[np.r_[0:nc, nb0[s]:nb0[s] + nr[s] - nc], :]
         R = rows[rowptr[s]: rowptr[s + 1]]
         for cc in range(nc):
             L[R[cc:], first[s] + cc] = blk[cc:nr[s], cc]
