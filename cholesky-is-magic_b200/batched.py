@@ -67,3 +67,41 @@ class Batch:
             h = C.c_void_p(self.ptr)
             assert com.lib.nes_batch_free(C.byref(h), com.ptr) != 0
             self.ptr = None
+
+
+# ---- multi-GPU: the batch index is split across ranks, no data-path collective ----
+def shard_range(nbatch, world, rank):
+    """Problems [lo, hi) of rank `rank`: contiguous, sizes differ by at most one."""
+    base, extra = divmod(nbatch, world)
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+class ShardedBatch:
+    """The LPs of a batch that belong to this rank (one process per GPU).  Every rank builds it from the
+    same list of standard forms; results stay local until `gather` is called (test / reporting only)."""
+
+    def __init__(self, sfs, world, rank):
+        self.nbatch, self.world, self.rank = len(sfs), world, rank
+        self.lo, self.hi = shard_range(self.nbatch, world, rank)
+        self.batch = Batch.from_standard_forms(sfs[self.lo:self.hi]) if self.hi > self.lo else None
+
+    def affine_scaling(self, max_iter=100000):
+        if self.batch is None:
+            return np.empty(0), np.empty((0, 0)), np.empty(0), np.empty(0, dtype=np.int32)
+        return self.batch.affine_scaling(max_iter)
+
+    def free(self):
+        if self.batch is not None:
+            self.batch.free()
+            self.batch = None
+
+
+def gather(local, world):
+    """Concatenate per-rank result arrays in rank order (torch.distributed must be initialised)."""
+    if world == 1:
+        return local
+    import torch.distributed as dist
+    parts = [None] * world
+    dist.all_gather_object(parts, local)
+    return tuple(np.concatenate([p[k] for p in parts if len(p[k])]) for k in range(len(local)))

@@ -20,6 +20,129 @@ _pkg.load()
 from cholesky_is_magic_b200 import lpgen, nes  # noqa: E402
 
 
+def _banded(rng, m, n, bw, per_col):
+    import scipy.sparse as sp
+    rows, cols, vals = [], [], []
+    for j in range(n):
+        c = j * m // n if j >= m else j
+        r = np.unique(np.clip(c + rng.integers(-bw, bw + 1, per_col - 1), 0, m - 1))
+        r = np.union1d(r, [c])
+        rows += r.tolist(); cols += [j] * len(r); vals += (1 + rng.random(len(r))).tolist()
+    A = sp.csc_matrix((vals, (rows, cols)), shape=(m, n))
+    A.sort_indices()
+    return A
+
+
+def cpu_sparse_and_batch(rank, world):
+    """Host logic of the sparse and batched multi-GPU paths over gloo: every rank analyzes the same
+    pattern (the mapping must agree), factors ITS subtrees with the NumPy emulation of the device
+    kernels, the exchange regions travel by broadcast exactly like ncclBroadcast moves them on the GPU,
+    every rank factors the top, solves, and the masked pieces are all-reduced."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from mf_emulation import Emu
+    from cholesky_is_magic_b200 import batched
+    from oracle import newton_solve as ons
+    rng = np.random.default_rng(11)
+    m, n = 1200, 2800
+    A = _banded(rng, m, n, 8, 5)
+    S = nes.symbolic_analyze(A.indptr, A.indices, m, n, world, 40)
+    own = torch.from_numpy(S["owner"].astype(np.int64))
+    ref = own.clone()
+    dist.broadcast(ref, 0)
+    assert torch.equal(own, ref)
+    assert (S["owner"] == rank).any() and (S["owner"] < 0).any()
+    s_ = np.sqrt(0.1 + 10 * rng.random(n))
+    M = ons.normal_matrix(A, s_)
+    b = rng.random(m)
+    e = Emu(S, rank)
+    e.assemble(M)
+    e.factor_phase(0)
+    for q, sl in e.exchange_regions("U"):
+        t = torch.from_numpy(e.U[sl])
+        dist.broadcast(t, q)
+    e.factor_phase(1)
+    x = b[S["perm"]].copy()
+    e.fwd_phase(0, x)
+    for q, sl in e.exchange_regions("uvec"):
+        t = torch.from_numpy(e.uvec[sl])
+        dist.broadcast(t, q)
+    e.fwd_phase(1, x)
+    e.bwd_phase(1, x)
+    e.bwd_phase(0, x)
+    first, owner = S["first"], S["owner"]
+    for s in range(int(S["nsuper"])):
+        if not (owner[s] == rank or (owner[s] < 0 and rank == 0)):
+            x[first[s]: first[s + 1]] = 0.0
+    t = torch.from_numpy(x)
+    dist.all_reduce(t)
+    sol = np.empty(m)
+    sol[S["perm"]] = x
+    assert np.linalg.norm(M @ sol - b) <= 1e-13 * np.linalg.norm(M) * np.linalg.norm(sol)
+    # batched path: the batch index is split, nothing else is exchanged
+    for nb in (1, 7, 1024):
+        lo, hi = batched.shard_range(nb, world, rank)
+        sizes = [None] * world
+        dist.all_gather_object(sizes, (lo, hi))
+        assert sizes[0][0] == 0 and sizes[-1][1] == nb
+        assert all(sizes[k][1] == sizes[k + 1][0] for k in range(world - 1))
+        assert max(h - l for l, h in sizes) - min(h - l for l, h in sizes) <= 1
+    lo, hi = batched.shard_range(10, world, rank)
+    got = batched.gather((np.arange(lo, hi, dtype=float), np.arange(lo, hi, dtype=np.int32) * 2), world)
+    assert np.array_equal(got[0], np.arange(10.0)) and np.array_equal(got[1], np.arange(10) * 2)
+
+
+def gpu_sparse_and_batch(c, rank, world):
+    """Sparse multifrontal path with subtrees sharded over the ranks, and the batch split (nccl)."""
+    import scipy.sparse as sp
+    from cholesky_is_magic_b200 import batched, pdas
+    from oracle import affine_scaling as oa
+    from oracle import newton_solve as ons
+    from oracle import pdas as opdas
+    rng = np.random.default_rng(21)
+    c.lib.nes_set_ordering_leaf(c.ptr, 60)
+    for (m, n) in ((900, 2000), (2500, 6000)):
+        A = _banded(rng, m, n, 10, 5)
+        s = np.sqrt(0.1 + 10 * rng.random(n))
+        b = rng.random(m)
+        Ad = nes.Matrix.from_csc(c, A.indptr, A.indices, A.data, m, n)
+        Ad.scale(s)
+        L = nes.Factor(c, Ad)
+        assert L.factorize(Ad)
+        x = L.solve(b)
+        M = ons.normal_matrix(A, s)
+        assert np.linalg.norm(M @ x - b) <= 1e-13 * np.linalg.norm(M) * np.linalg.norm(x)
+        out = np.zeros((m, m), order="F")
+        perm = np.zeros(m, dtype=np.int32)
+        c.check(c.lib.nes_factor_to_dense(L.ptr, out.ctypes.data_as(nes._dp), m, perm.ctypes.data_as(nes._ip), c.ptr),
+                "to_dense")
+        Mp = M[np.ix_(perm, perm)]
+        assert np.linalg.norm(out @ out.T - Mp) / np.linalg.norm(Mp) <= 1e-12
+        t = torch.from_numpy(x).cuda()
+        ref = t.clone()
+        dist.broadcast(ref, 0)
+        assert torch.equal(t, ref)        # the all-reduced solution is identical on every rank
+        L.free()
+        Ad.free()
+    sf = lpgen.sparse_lp(700, 1700, nnz_per_col=6, bandwidth=20, seed=3)
+    A = sp.csc_matrix((sf.A.value, (sf.A.row, sf.A.col)), shape=(700, 1700))
+    ost = opdas.make_pdas(sf.nvars, sf.ncons, sf.c_dense(), A, sf.b, sf.l, sf.u)
+    oobj, _, oit = opdas.pdas(ost, 400)
+    obj, _, it = pdas.pdas(pdas.make_pdas(sf), 400, native_loop=True)
+    assert it == oit and abs(obj - oobj) <= 1e-7 * abs(oobj), (it, oit, obj, oobj)
+    c.lib.nes_set_ordering_leaf(c.ptr, 0)
+    # batched path: every rank advances its slice of the LPs; gathered results match the oracle
+    B, m, n = 6, 24, 60
+    sfs = [lpgen.dense_lp(m, n, seed) for seed in range(B)]
+    sb = batched.ShardedBatch(sfs, world, rank)
+    obj, x, res, iters = batched.gather(sb.affine_scaling(9), world)
+    sb.free()
+    assert len(obj) == B
+    for k, sfk in enumerate(sfs):
+        ost = oa.make_affine_state(sfk.nvars, sfk.ncons, sfk.c_dense(), sfk.A_dense, sfk.b, sfk.l, sfk.u)
+        oa.affine_scaling(ost, 9)
+        np.testing.assert_allclose(x[k], ost.x, rtol=1e-6, atol=1e-8)
+
+
 def main():
     mode = sys.argv[1]
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
@@ -42,6 +165,7 @@ def main():
             counts = [int((g >= 0).sum()) for g in gathered]
             if m >= 8192:
                 assert max(counts) - min(counts) <= 0.02 * max(counts), counts
+        cpu_sparse_and_batch(rank, world)
         dist.destroy_process_group()
         print(f"rank {rank}: cpu dist ok")
         return
@@ -100,6 +224,7 @@ def main():
         # GEMV differs from OpenBLAS and is amplified by cond(M) late in the solve); the 1e-9 gate is
         # checked on the BASELINE config-1 LP in test_dense_gpu.py
         assert it == oit and abs(obj - oobj) <= 1e-7 * abs(oobj), (it, oit, obj, oobj)
+        gpu_sparse_and_batch(c, rank, world)
     dist.barrier()
     dist.destroy_process_group()
     print(f"rank {rank}: gpu dist ok ({world} ranks)")

@@ -10,6 +10,8 @@ import scipy.sparse as sp
 from cholesky_is_magic_b200 import nes
 from oracle import newton_solve as ons
 
+from mf_emulation import Emu, factor_and_solve_all_ranks
+
 
 def banded(rng, m, n, bw, per_col):
     rows, cols, vals = [], [], []
@@ -36,63 +38,6 @@ def true_colcounts(pattern):
         if len(below):
             F[np.ix_(below, below)] |= np.tril(np.ones((len(below), len(below)), dtype=bool))
     return F.sum(axis=0), F
-
-
-def multifrontal_numeric(S, M):
-    """NumPy emulation of sparse_chol.cu's numeric phase on the symbolic structure S."""
-    ns = int(S["nsuper"])
-    first, nr, ld, rowptr, rows, off = S["first"], S["nr"], S["ld"], S["rowptr"], S["rows"], S["off"]
-    nb0 = S["nb0"]
-    perm = S["perm"]
-    Lv = np.zeros(int(S["lsize"]))
-    U = np.full(int(S["usize"]), np.nan)       # pool with slot reuse
-    # assembly: entry e = M[ei, ej] -> edest
-    Lv[S["edest"]] = M[S["ei"], S["ej"]]
-    for lvl in range(int(S["nlevels"])):
-        for s in range(S["lvlptr"][lvl], S["lvlptr"][lvl + 1]):
-            nc = first[s + 1] - first[s]; nu = nr[s] - nc
-            full = Lv[off[s]: off[s] + ld[s] * nc].reshape(nc, ld[s]).T         # view, column-major
-            assert nb0[s] % 32 == 0 and nb0[s] >= nc and ld[s] >= nb0[s] + nu
-            blk = full[np.r_[0:nc, nb0[s]:nb0[s] + nu], :]                      # copy: diagonal block + rows below
-            Us = None
-            if nu:
-                Us = U[S["uoff"][s]: S["uoff"][s] + S["ldu"][s] * nu].reshape(nu, S["ldu"][s]).T
-                Us[:nu, :] = 0.0
-            for c in S["child"][S["childptr"][s]: S["childptr"][s + 1]]:        # extend-add, children ascending
-                cnc = first[c + 1] - first[c]; cnu = nr[c] - cnc
-                Uc = U[S["uoff"][c]: S["uoff"][c] + S["ldu"][c] * cnu].reshape(cnu, S["ldu"][c]).T
-                rel = S["rel"][S["relptr"][c]: S["relptr"][c + 1]]
-                tb = S["tb"][S["tbptr"][c]: S["tbptr"][c + 1]]               # 64-row slab boundaries
-                assert len(tb) == (nu + 63) // 64 + 1 and tb[-1] == cnu
-                for k in range(len(tb)):
-                    assert tb[k] == S["cut"][c] + np.searchsorted(rel[S["cut"][c]:], nc + 64 * k)
-                assert np.array_equal(rows[rowptr[s]: rowptr[s + 1]][rel], rows[rowptr[c] + cnc: rowptr[c + 1]])
-                cut = S["cut"][c]
-                assert np.all(rel[:cut] < nc) and np.all(rel[cut:] >= nc)
-                for j in range(cnu):
-                    i = np.arange(j, cnu)
-                    if j < cut:
-                        blk[rel[i], rel[j]] += Uc[i, j]
-                    else:
-                        Us[rel[i] - nc, rel[j] - nc] += Uc[i, j]
-            D = np.tril(blk[:nc, :nc]); D = D + np.tril(D, -1).T
-            Ld = np.linalg.cholesky(D)
-            blk[:nc, :nc] = Ld
-            if nu:
-                blk[nc:nr[s], :] = np.linalg.solve(Ld, blk[nc:nr[s], :].T).T
-                Us[:nu, :nu] -= np.tril(blk[nc:nr[s], :] @ blk[nc:nr[s], :].T)
-            full[0:nc, :] = blk[:nc, :]
-            full[nb0[s]:nb0[s] + nu, :] = blk[nc:, :]
-    m = len(perm)
-    L = np.zeros((m, m))
-    for s in range(ns):
-        nc = first[s + 1] - first[s]
-        full = Lv[off[s]: off[s] + ld[s] * nc].reshape(nc, ld[s]).T
-        blk = full[np.r_[0:nc, nb0[s]:nb0[s] + nr[s] - nc], :]
-        R = rows[rowptr[s]: rowptr[s + 1]]
-        for cc in range(nc):
-            L[R[cc:], first[s] + cc] = blk[cc:nr[s], cc]
-    return L
 
 
 CASES = [("random", 1, 1, 0), ("random", 7, 12, 0), ("random", 40, 90, 0), ("random", 150, 400, 0),
@@ -135,9 +80,25 @@ def test_symbolic_structure_and_multifrontal_maps(kind, m, n, leaf):
     # numeric emulation on the maps
     s_ = np.sqrt(0.1 + 10 * rng.random(n))
     M = ons.normal_matrix(A, s_)
-    L = multifrontal_numeric(S, M)
+    b = rng.random(m)
+    L, x = factor_and_solve_all_ranks(S, M, b, 1)
     Mp = M[np.ix_(perm, perm)]
     assert np.linalg.norm(L @ L.T - Mp) / np.linalg.norm(Mp) <= 1e-12
+    assert np.linalg.norm(M @ x - b) / np.linalg.norm(b) <= 1e-10
+    # slab tables: rows of every child that land in each 64-row slab of the parent's rows below
+    nc_all = np.diff(S["first"])
+    for c in range(ns):
+        p = S["sparent"][c]
+        tb = S["tb"][S["tbptr"][c]: S["tbptr"][c + 1]]
+        if p < 0 or nr[c] == nc_all[c]:
+            assert len(tb) == 0
+            continue
+        rel = S["rel"][S["relptr"][c]: S["relptr"][c + 1]]
+        nup = nr[p] - nc_all[p]
+        assert len(tb) == (nup + 63) // 64 + 1 and tb[-1] == len(rel)
+        for k in range(len(tb)):
+            assert tb[k] == S["cut"][c] + np.searchsorted(rel[S["cut"][c]:], nc_all[p] + 64 * k)
+    assert np.all(S["nb0"] % 32 == 0) and np.all(S["nb0"] >= nc_all) and np.all(S["ld"] >= S["nb0"] + nr - nc_all)
 
 
 def test_nested_dissection_gives_parallel_levels_and_reuses_update_slots():
@@ -158,9 +119,9 @@ def test_nested_dissection_gives_parallel_levels_and_reuses_update_slots():
 @pytest.mark.parametrize("Q", [2, 4, 8])
 def test_subtree_to_rank_mapping(Q):
     rng = np.random.default_rng(5)
-    m, n = 6000, 14000
-    A = banded(rng, m, n, 16, 6)
-    S = analyze(A, nranks=Q, leaf=150)
+    m, n = 1500, 3500
+    A = banded(rng, m, n, 8, 5)
+    S = analyze(A, nranks=Q, leaf=40)
     owner, par = S["owner"], S["sparent"]
     ns = int(S["nsuper"])
     assert owner.min() >= -1 and owner.max() < Q
@@ -173,9 +134,19 @@ def test_subtree_to_rank_mapping(Q):
             else:
                 assert owner[p] in (-1, owner[s])                     # subtrees are not split across ranks
     # the ordering / structure itself does not depend on the number of ranks
-    S1 = analyze(A, nranks=1, leaf=150)
+    S1 = analyze(A, nranks=1, leaf=40)
     for k in ("perm", "first", "rows", "level", "rel"):
         assert np.array_equal(S[k], S1[k])
+    # numeric phase + solves with the ranks' phases and exchanges emulated in NumPy
+    s_ = np.sqrt(0.1 + 10 * rng.random(n))
+    M = ons.normal_matrix(A, s_)
+    b = rng.random(m)
+    L, x = factor_and_solve_all_ranks(S, M, b, Q)
+    Mp = M[np.ix_(S["perm"], S["perm"])]
+    assert np.linalg.norm(L @ L.T - Mp) / np.linalg.norm(Mp) <= 1e-12
+    # backward-stable solve: residual small against |M| |x| (this banded M is ill-conditioned, |x| ~ 1e6 |b|)
+    assert np.linalg.norm(M @ x - b) <= 1e-13 * np.linalg.norm(M) * np.linalg.norm(x)
+    assert S["xu_off"][-1] == S["usize"] and len(S["xu_off"]) == Q + 1
     # load balance of the owned flops (nc * nr^2 model): no rank above 1.6x the mean
     nc = np.diff(S["first"]).astype(float)
     fl = nc * S["nr"].astype(float) ** 2
