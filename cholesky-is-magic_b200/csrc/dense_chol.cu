@@ -13,6 +13,9 @@
 //   trsm_panel_kernel   X L_kk' = B for the rows below: one thread per row, 32-column register blocks,
 //                       L_kk broadcast from shared memory (true substitution, no explicit inverse)
 //   dmma_nt_kernel      trailing update C -= P P' on the FP64 tensor cores (lower tiles only)
+#include <cstdio>
+#include <cstdlib>
+
 #include "dmma_nt.cuh"
 #include "nes_internal.h"
 #include "potrf_block.cuh"
@@ -184,7 +187,7 @@ int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, const CUtensorMap& 
 
 // One dmma_nt launch: C[r0.., c0..c0+ncols) -= X[r0.., k0..k0+K) X[c0..c0+ncols, k0..k0+K)^T
 static int chol_update(nes_ctx* c, nes_factor* L, int r0, int c0, int nrows, int ncols, int k0, int K,
-                       int lower) {
+                       int lower, cudaStream_t stream = nullptr, bool one_tile_per_cta = false) {
     NtArgs a{};
     a.C = L->d_M + r0 + (long long)c0 * (long long)L->ld;
     a.ldc = (long long)L->ld;
@@ -199,7 +202,10 @@ static int chol_update(nes_ctx* c, nes_factor* L, int r0, int c0, int nrows, int
     a.beta = 1.0;
     a.lower = lower;
     a.same_operand = (r0 == c0) ? 1 : 0;
-    cudaError_t e = nt_launch(L->mapM, L->mapM, a, c->num_sms, c->stream);
+    // one_tile_per_cta: a non-persistent grid, so SMs come free every tile and a higher-priority stream
+    // (the panel factorization of the look-ahead) gets them at tile granularity
+    cudaError_t e = nt_launch(L->mapM, L->mapM, a, one_tile_per_cta ? (1 << 30) : c->num_sms,
+                              stream ? stream : c->stream);
     ++c->launches;
     if (e != cudaSuccess)
         return fail(c, NES_ERR_CUDA, "Cholesky update launch failed: %s", cudaGetErrorString(e));
@@ -362,24 +368,75 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
     const int P = c->nranks;
     NES_CUDA(c, cudaMemsetAsync(L->d_info, 0, 2 * sizeof(int), c->stream));
     if (P > 1) NES_TRY(dense_cholesky_dist_steps(c, L));
-    for (int j0 = 0, J = 0; j0 < m && P == 1; j0 += NBO, ++J) {
-        const int jbo = (m - j0 < NBO) ? m - j0 : NBO;
-        for (int i0 = j0; i0 < j0 + jbo; i0 += CH_NB) {
-            const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
-            if (i0 > j0)  // bring block column i0 up to date with the inner panels already factored
-                NES_TRY(chol_update(c, L, i0, i0, m - i0, ib, j0, i0 - j0, 0));
-            potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->mapBlk, i0, ib, L->d_dinv,
-                                                                  c->dbound, L->d_info, 0);
-            NES_CHECK_LAUNCH(c);
-            const int rest = m - i0 - ib;
-            if (rest > 0) {
-                trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM, c->stream>>>(
-                    L->mapBlk, L->mapSlab, i0, m, L->d_dinv, 0);
-                NES_CHECK_LAUNCH(c);
-            }
+    if (P == 1) {
+        // Look-ahead (single GPU).  After panel J: (1) `stream` brings block column J+1 up to date and
+        // factors panel J+1 (latency-bound: one CTA for the diagonal block, a few for the TRSM), while
+        // (2) the low-priority side stream applies panel J to the rest of the trailing matrix with one
+        // tile per CTA.  Without it the ~64 diagonal blocks and TRSMs (4 ms at m = 8192) sit between the
+        // updates with 147 SMs idle.  Hazards: (1) of step J+1 touches columns the rest-update J writes,
+        // so `stream` waits for ev_update; rest-update J+1 needs panel J+1 (ev_panel) and follows
+        // rest-update J in stream order.
+        // Panel width by remaining size R = m - j0: while the trailing matrix is large the updates bound
+        // the step (wide panels: fewer passes over C, K = 512 / 256), once it is small the panel chain
+        // does (128 columns: no inner narrow updates).  NES_CHOL_SCHED="t512,t256" overrides the thresholds.
+        static int t512 = -1, t256 = -1;
+        if (t512 < 0) {
+            t512 = 6144;
+            t256 = 3072;
+            if (const char* e = getenv("NES_CHOL_SCHED")) sscanf(e, "%d,%d", &t512, &t256);
         }
-        const int r0 = j0 + jbo;
-        if (r0 < m) NES_TRY(chol_update(c, L, r0, r0, m - r0, m - r0, j0, jbo, 1));
+        auto width = [&](int j0) {
+            const int R = m - j0;
+            const int w = R > t512 ? 512 : (R > t256 ? 256 : CH_NB);
+            return R < w ? R : w;
+        };
+        auto factor_panel = [&](int j0, int jbo) -> int {
+            for (int i0 = j0; i0 < j0 + jbo; i0 += CH_NB) {
+                const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
+                if (i0 > j0)  // bring block column i0 up to date with the inner panels already factored
+                    NES_TRY(chol_update(c, L, i0, i0, m - i0, ib, j0, i0 - j0, 0));
+                potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->mapBlk, i0, ib, L->d_dinv,
+                                                                      c->dbound, L->d_info, 0);
+                NES_CHECK_LAUNCH(c);
+                const int rest = m - i0 - ib;
+                if (rest > 0) {
+                    trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM, c->stream>>>(
+                        L->mapBlk, L->mapSlab, i0, m, L->d_dinv, 0);
+                    NES_CHECK_LAUNCH(c);
+                }
+            }
+            return 0;
+        };
+        const bool lookahead = c->stream_aux && m > 1024;
+        int jbo = width(0);
+        NES_TRY(factor_panel(0, jbo));
+        bool pending_update = false;
+        for (int j0 = 0; j0 < m;) {
+            const int r0 = j0 + jbo;
+            if (r0 >= m) break;
+            const int jbn = width(r0);
+            if (!lookahead) {
+                NES_TRY(chol_update(c, L, r0, r0, m - r0, m - r0, j0, jbo, 1));
+                NES_TRY(factor_panel(r0, jbn));
+                j0 = r0;
+                jbo = jbn;
+                continue;
+            }
+            const int r1 = r0 + jbn;
+            NES_CUDA(c, cudaEventRecord(c->ev_panel, c->stream));                  // panel J is final
+            if (pending_update) NES_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_update, 0));
+            NES_TRY(chol_update(c, L, r0, r0, m - r0, jbn, j0, jbo, 0));           // (1) block column J+1
+            if (r1 < m) {                                                          // (2) the rest, side stream
+                NES_CUDA(c, cudaStreamWaitEvent(c->stream_aux, c->ev_panel, 0));
+                NES_TRY(chol_update(c, L, r1, r1, m - r1, m - r1, j0, jbo, 1, c->stream_aux, true));
+                NES_CUDA(c, cudaEventRecord(c->ev_update, c->stream_aux));
+                pending_update = true;
+            }
+            NES_TRY(factor_panel(r0, jbn));
+            j0 = r0;
+            jbo = jbn;
+        }
+        if (pending_update) NES_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_update, 0));
     }
     if (L->d_Winv) {  // block inverses for the solve phase (off the factorization's critical path)
         trtri_diag_kernel<<<(m + CH_NB - 1) / CH_NB, CH_NB, TI_SMEM, c->stream>>>(L->d_M, ld, m, L->d_dinv,

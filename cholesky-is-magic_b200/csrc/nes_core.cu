@@ -214,7 +214,12 @@ int nes_start(nes_ctx* c) {
         return 0;
     }
     c->num_sms = prop.multiProcessorCount;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // lo = least urgent (numerically greatest)
+    if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->stream_aux, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_update, cudaEventDisableTiming) != cudaSuccess) {
         fail(c, NES_ERR_CUDA, "cudaStreamCreate failed");
         return 0;
     }
@@ -262,6 +267,11 @@ int nes_finish(nes_ctx* c) {
     if (c->mark_a) cudaEventDestroy(c->mark_a);
     if (c->mark_b) cudaEventDestroy(c->mark_b);
     c->mark_a = c->mark_b = nullptr;
+    if (c->ev_panel) cudaEventDestroy(c->ev_panel);
+    if (c->ev_update) cudaEventDestroy(c->ev_update);
+    c->ev_panel = c->ev_update = nullptr;
+    if (c->stream_aux) cudaStreamDestroy(c->stream_aux);
+    c->stream_aux = nullptr;
     if (c->stream) cudaStreamDestroy(c->stream);
     c->stream = nullptr;
     c->started = 0;
