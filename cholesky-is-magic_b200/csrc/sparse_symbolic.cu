@@ -20,13 +20,42 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
+#include <cstdlib>
+#include <atomic>
 #include <numeric>
+#include <thread>
 
 namespace nes {
 
 namespace {
 
 constexpr int SN_MAX_COLS = 128;
+
+int host_threads() {
+    static int n = 0;
+    if (n == 0) {
+        n = (int)std::thread::hardware_concurrency();
+        if (const char* e = getenv("NES_HOST_THREADS")) n = atoi(e);
+        n = n < 1 ? 1 : (n > 32 ? 32 : n);
+    }
+    return n;
+}
+
+// f(chunk, begin, end) on contiguous chunks of [0, n); chunk ids are 0 .. nchunks-1 in index order
+template <typename F>
+void parallel_chunks(int n, int nchunks, F f) {
+    if (nchunks <= 1 || n < 4096) {
+        f(0, 0, n);
+        return;
+    }
+    std::vector<std::thread> th;
+    for (int k = 0; k < nchunks; ++k) {
+        const int b = (int)((long long)n * k / nchunks), e = (int)((long long)n * (k + 1) / nchunks);
+        th.emplace_back([=]() { f(k, b, e); });
+    }
+    for (auto& t : th) t.join();
+}
 
 void csc_to_csr(int m, int n, const int* cp, const int* ri, std::vector<int>& rp, std::vector<int>& cj) {
     rp.assign(m + 1, 0);
@@ -38,32 +67,44 @@ void csc_to_csr(int m, int n, const int* cp, const int* ri, std::vector<int>& rp
         for (int k = cp[j]; k < cp[j + 1]; ++k) cj[next[ri[k]]++] = j;
 }
 
-// full symmetric adjacency of A A' (without the diagonal), sorted per row
+// full symmetric adjacency of A A' (without the diagonal), sorted per row; rows are independent, so
+// chunks of rows are built by host threads and concatenated
 void aat_pattern(int m, int n, const int* cp, const int* ri, const std::vector<int>& rp,
                  const std::vector<int>& cj, std::vector<int>& ap, std::vector<int>& ai, double& aatfl) {
     ap.assign(m + 1, 0);
-    ai.clear();
-    std::vector<int> mark(m, -1);
     aatfl = 0;
     for (int j = 0; j < n; ++j) {
         const double c = cp[j + 1] - cp[j];
         aatfl += c * c;
     }
-    for (int i = 0; i < m; ++i) {
-        const size_t start = ai.size();
-        mark[i] = i;
-        for (int q = rp[i]; q < rp[i + 1]; ++q) {
-            const int k = cj[q];
-            for (int t = cp[k]; t < cp[k + 1]; ++t) {
-                const int r = ri[t];
-                if (mark[r] != i) {
-                    mark[r] = i;
-                    ai.push_back(r);
+    const int nch = (m < 4096) ? 1 : host_threads();
+    std::vector<std::vector<int>> part(nch);
+    parallel_chunks(m, nch, [&](int k, int b, int e) {
+        std::vector<int> mark(m, -1);
+        std::vector<int>& out = part[k];
+        for (int i = b; i < e; ++i) {
+            const size_t start = out.size();
+            mark[i] = i;
+            for (int q = rp[i]; q < rp[i + 1]; ++q) {
+                const int kk = cj[q];
+                for (int t = cp[kk]; t < cp[kk + 1]; ++t) {
+                    const int r = ri[t];
+                    if (mark[r] != i) {
+                        mark[r] = i;
+                        out.push_back(r);
+                    }
                 }
             }
+            std::sort(out.begin() + start, out.end());
+            ap[i + 1] = (int)(out.size() - start);
         }
-        std::sort(ai.begin() + start, ai.end());
-        ap[i + 1] = (int)ai.size();
+    });
+    for (int i = 0; i < m; ++i) ap[i + 1] += ap[i];
+    ai.resize(ap[m]);
+    size_t w = 0;
+    for (int k = 0; k < nch; ++k) {
+        std::copy(part[k].begin(), part[k].end(), ai.begin() + w);
+        w += part[k].size();
     }
 }
 
@@ -74,16 +115,13 @@ struct Orderer {
     const std::vector<int>& ai;
     std::vector<int> part;   // label of the vertex set a vertex currently belongs to (-1: removed)
     std::vector<int> deg;
-    std::vector<int> lev;    // scratch: BFS level
-    std::vector<int> queue;  // scratch
-    std::vector<int> out;    // elimination order
-    int next_label = 1;
+    std::vector<int> lev;    // scratch: BFS level (sets being dissected concurrently are disjoint)
+    std::atomic<int> next_label{1};
     int leaf;
 
     Orderer(int m_, const std::vector<int>& ap_, const std::vector<int>& ai_, int leaf_)
         : m(m_), ap(ap_), ai(ai_), part(m_, 0), deg(m_), lev(m_, -1), leaf(leaf_) {
         for (int i = 0; i < m; ++i) deg[i] = ap[i + 1] - ap[i];
-        out.reserve(m);
     }
 
     // BFS inside label `lab` from `start`; fills `order` (visit order) and lev[]; returns the number of levels
@@ -110,8 +148,9 @@ struct Orderer {
         for (int v : order) lev[v] = -1;
     }
 
-    // reverse Cuthill-McKee of the vertices carrying label `lab` (they are relabelled -1 = done)
-    void rcm(const std::vector<int>& verts, int lab) {
+    // reverse Cuthill-McKee of the vertices carrying label `lab` (they are relabelled -1 = done),
+    // appended to `out`
+    void rcm(const std::vector<int>& verts, int lab, std::vector<int>& out) {
         std::vector<int> byDeg(verts);
         std::stable_sort(byDeg.begin(), byDeg.end(), [&](int a, int b) { return deg[a] < deg[b]; });
         std::vector<int> order, nbr;
@@ -139,13 +178,16 @@ struct Orderer {
         out.insert(out.end(), order.rbegin(), order.rend());
     }
 
-    void dissect(std::vector<int> verts, int lab, int depth) {
+    // elimination order of `verts` (all labelled `lab`) appended to `out`.  `connected`: the set is known to
+    // be one component (the near side of a level-structure cut always is).  The two sides of a cut are
+    // independent, so the first `par_depth` levels of the recursion run them on two host threads; the
+    // result does not depend on the number of threads.
+    void dissect(std::vector<int> verts, int lab, int depth, bool connected, int par_depth, std::vector<int>& out) {
         if ((int)verts.size() <= leaf || depth > 48) {
-            rcm(verts, lab);
+            rcm(verts, lab, out);
             return;
         }
-        // connected components are independent subtrees of the elimination forest
-        {
+        if (!connected) {  // connected components are independent subtrees of the elimination forest
             std::vector<int> order;
             std::vector<std::vector<int>> comps;
             size_t seen = 0;
@@ -161,31 +203,26 @@ struct Orderer {
                 for (auto& cvec : comps) {
                     const int l2 = next_label++;
                     for (int v : cvec) part[v] = l2;
-                    dissect(std::move(cvec), l2, depth + 1);
+                    dissect(std::move(cvec), l2, depth + 1, true, 0, out);
                 }
                 return;
             }
         }
-        // pseudo-peripheral start: min degree, then twice the far end of the level structure
+        // pseudo-peripheral start: min degree, then the far end of its level structure
         int start = verts[0];
         for (int v : verts)
             if (deg[v] < deg[start]) start = v;
         std::vector<int> order;
         int h = bfs(start, lab, order);
-        for (int sweep = 0; sweep < 2; ++sweep) {
+        {
             const int far = order.back();
             clear_lev(order);
-            const int h2 = bfs(far, lab, order);
-            if (h2 <= h && sweep > 0) {
-                h = h2;
-                break;
-            }
-            h = h2;
+            h = bfs(far, lab, order);
         }
         const int nv = (int)verts.size();
         if (h < 3) {
             clear_lev(order);
-            rcm(verts, lab);
+            rcm(verts, lab, out);
             return;
         }
         std::vector<int> lsize(h, 0);
@@ -214,7 +251,7 @@ struct Orderer {
         }
         if (lsize[k] * 3 > nv) {  // no useful separator (close to a clique)
             clear_lev(order);
-            rcm(verts, lab);
+            rcm(verts, lab, out);
             return;
         }
         const int la = next_label++, lb = next_label++, ls = next_label++;
@@ -228,7 +265,7 @@ struct Orderer {
                 bool touches = false;
                 for (int q = ap[v]; q < ap[v + 1] && !touches; ++q) {
                     const int u = ai[q];
-                    touches = (part[u] == lab || part[u] == lb) && lev[u] == k + 1;
+                    touches = part[u] == lab && lev[u] == k + 1;
                 }
                 (touches ? S : A).push_back(v);
             }
@@ -241,9 +278,18 @@ struct Orderer {
         order.shrink_to_fit();
         verts.clear();
         verts.shrink_to_fit();
-        dissect(std::move(A), la, depth + 1);
-        dissect(std::move(B), lb, depth + 1);
-        rcm(S, ls);
+        if (par_depth > 0 && A.size() > 4096 && B.size() > 4096) {
+            std::vector<int> outA, outB;
+            std::thread ta([&]() { dissect(std::move(A), la, depth + 1, true, par_depth - 1, outA); });
+            dissect(std::move(B), lb, depth + 1, false, par_depth - 1, outB);
+            ta.join();
+            out.insert(out.end(), outA.begin(), outA.end());
+            out.insert(out.end(), outB.begin(), outB.end());
+        } else {
+            dissect(std::move(A), la, depth + 1, true, 0, out);
+            dissect(std::move(B), lb, depth + 1, false, 0, out);
+        }
+        rcm(S, ls, out);
     }
 };
 
@@ -259,8 +305,11 @@ void order_nd(int m, const std::vector<int>& ap, const std::vector<int>& ai, int
             sparse_rows.push_back(i);
         }
     }
-    o.dissect(std::move(sparse_rows), 0, 0);
-    perm = o.out;
+    int par_depth = 0;
+    for (int t = host_threads(); t > 1; t >>= 1) ++par_depth;
+    perm.clear();
+    perm.reserve(m);
+    o.dissect(std::move(sparse_rows), 0, 0, false, par_depth, perm);
     perm.insert(perm.end(), dense_rows.begin(), dense_rows.end());
 }
 
@@ -270,10 +319,12 @@ void permute_graph(int m, const std::vector<int>& ap, const std::vector<int>& ai
     pp.assign(m + 1, 0);
     pi.resize(ai.size());
     for (int j = 0; j < m; ++j) pp[j + 1] = pp[j] + (ap[perm[j] + 1] - ap[perm[j]]);
-    for (int j = 0; j < m; ++j) {
-        int w = pp[j];
-        for (int q = ap[perm[j]]; q < ap[perm[j] + 1]; ++q) pi[w++] = iperm[ai[q]];
-    }
+    parallel_chunks(m, host_threads(), [&](int, int b, int e) {
+        for (int j = b; j < e; ++j) {
+            int w = pp[j];
+            for (int q = ap[perm[j]]; q < ap[perm[j] + 1]; ++q) pi[w++] = iperm[ai[q]];
+        }
+    });
 }
 
 void etree(int m, const std::vector<int>& pp, const std::vector<int>& pi, std::vector<int>& parent) {
@@ -372,17 +423,27 @@ int set_err(char* err, size_t n, const char* msg, int a = 0, int b = 0) {
 
 int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicOptions& opt, Symbolic* S,
                      char* err, size_t errlen) {
+    const bool timing = getenv("NES_SYMBOLIC_TIMING") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[symbolic] %-28s %7.1f ms\n", what, std::chrono::duration<double, std::milli>(now - t_last).count());
+        t_last = now;
+    };
     *S = Symbolic();
     S->m = m;
     std::vector<int> rp, cj, ap, ai;
     csc_to_csr(m, n, cp, ri, rp, cj);
     aat_pattern(m, n, cp, ri, rp, cj, ap, ai, S->aatfl);
     S->anz = (long long)m + (long long)ai.size() / 2;
+    lap("pattern of A A'");
 
     // ---- ordering, etree, postorder, column counts ---------------------------------------------------
     const int leaf = opt.nd_leaf > 0 ? opt.nd_leaf : std::max(256, m / 128);
     std::vector<int> perm, iperm(m), pp, pi, parent, cc;
     order_nd(m, ap, ai, leaf, perm);
+    lap("nested dissection ordering");
     if ((int)perm.size() != m) return set_err(err, errlen, "ordering lost vertices (%d of %d)", (int)perm.size(), m);
     for (int i = 0; i < m; ++i) iperm[perm[i]] = i;
     permute_graph(m, ap, ai, perm, iperm, pp, pi);
@@ -395,9 +456,14 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
         perm.swap(perm2);
         for (int i = 0; i < m; ++i) iperm[perm[i]] = i;
         permute_graph(m, ap, ai, perm, iperm, pp, pi);
-        etree(m, pp, pi, parent);  // same tree, relabelled; vertex k is now k-th in postorder
+        std::vector<int> ipost(m), parent2(m);  // same tree, relabelled: vertex k is now k-th in postorder
+        for (int k = 0; k < m; ++k) ipost[post[k]] = k;
+        for (int k = 0; k < m; ++k) parent2[k] = parent[post[k]] < 0 ? -1 : ipost[parent[post[k]]];
+        parent.swap(parent2);
     }
+    lap("etree + postorder");
     column_counts(m, pp, pi, parent, cc);
+    lap("column counts");
     for (int j = 0; j < m; ++j) {
         S->lnz += cc[j];
         S->fl += (double)cc[j] * cc[j];
@@ -485,6 +551,7 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
             if (S->sparent[s] >= 0) S->child[next[S->sparent[s]]++] = s;
     }
 
+    lap("supernodes + levels");
     // ---- supernodal row structures -------------------------------------------------------------------------
     // rows(s) = columns of s, then { i > last(s) : i adjacent to a column of s, or i below a child of s }
     S->nr.resize(ns);
@@ -533,6 +600,7 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
     }
     S->lsize = S->off[ns];
 
+    lap("supernodal structures");
     // ---- parent-relative maps -----------------------------------------------------------------------------------
     S->relptr.assign(ns + 1, 0);
     S->cut.assign(ns, 0);
@@ -762,35 +830,59 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
         }
     }
 
+    lap("maps, pool, segments");
     // ---- assembly map -----------------------------------------------------------------------------------------
-    S->ei.reserve(S->anz);
-    S->ej.reserve(S->anz);
-    S->edest.reserve(S->anz);
     {
-        std::vector<int> col;
-        for (int j = 0; j < m; ++j) {
-            const int s = col2sn[j];
-            const int* R = S->rows.data() + S->rowptr[s];
-            const int nrs = S->nr[s];
-            const long long base = S->off[s] + (long long)(j - first[s]) * S->ld[s];
-            col.clear();
-            col.push_back(j);
-            const int oj = perm[j];
-            for (int q = ap[oj]; q < ap[oj + 1]; ++q) {
-                const int i = iperm[ai[q]];
-                if (i > j) col.push_back(i);
+        // columns are independent: count the entries of every column, prefix-sum, fill in parallel
+        std::vector<long long> cstart(m + 1, 0);
+        parallel_chunks(m, host_threads(), [&](int, int b, int e) {
+            for (int j = b; j < e; ++j) {
+                const int oj = perm[j];
+                int cnt = 1;
+                for (int q = ap[oj]; q < ap[oj + 1]; ++q) cnt += iperm[ai[q]] > j;
+                cstart[j + 1] = cnt;
             }
-            std::sort(col.begin(), col.end());
-            int p = 0;
-            for (int i : col) {
-                while (p < nrs && R[p] < i) ++p;
-                if (p >= nrs) return set_err(err, errlen, "symbolic analysis: entry (%d, %d) outside its supernode", i, j);
-                S->ei.push_back(perm[i]);
-                S->ej.push_back(oj);
-                S->edest.push_back(base + (p < first[s + 1] - first[s] ? p : p + S->nb0[s] - (first[s + 1] - first[s])));
+        });
+        for (int j = 0; j < m; ++j) cstart[j + 1] += cstart[j];
+        if (cstart[m] != S->anz)
+            return set_err(err, errlen, "symbolic analysis: assembled %d entries, expected %d", (int)cstart[m], (int)S->anz);
+        S->ei.resize(S->anz);
+        S->ej.resize(S->anz);
+        S->edest.resize(S->anz);
+        std::atomic<int> bad{-1};
+        parallel_chunks(m, host_threads(), [&](int, int b, int e) {
+            std::vector<int> col;
+            for (int j = b; j < e; ++j) {
+                const int s = col2sn[j];
+                const int* R = S->rows.data() + S->rowptr[s];
+                const int nrs = S->nr[s], ncs = first[s + 1] - first[s];
+                const long long base = S->off[s] + (long long)(j - first[s]) * S->ld[s];
+                col.clear();
+                col.push_back(j);
+                const int oj = perm[j];
+                for (int q = ap[oj]; q < ap[oj + 1]; ++q) {
+                    const int i = iperm[ai[q]];
+                    if (i > j) col.push_back(i);
+                }
+                std::sort(col.begin(), col.end());
+                long long w = cstart[j];
+                int p = 0;
+                for (int i : col) {
+                    while (p < nrs && R[p] < i) ++p;
+                    if (p >= nrs) {
+                        bad = j;
+                        break;
+                    }
+                    S->ei[w] = perm[i];
+                    S->ej[w] = oj;
+                    S->edest[w] = base + (p < ncs ? p : p + S->nb0[s] - ncs);
+                    ++w;
+                }
             }
-        }
+        });
+        if (bad >= 0) return set_err(err, errlen, "symbolic analysis: an entry of column %d lies outside its supernode", bad, 0);
     }
+    lap("assembly map");
     if ((long long)S->ei.size() != S->anz)
         return set_err(err, errlen, "symbolic analysis: assembled %d entries, expected %d", (int)S->ei.size(), (int)S->anz);
 
