@@ -316,7 +316,8 @@ static int dist_exchange_panel(nes_ctx* c, nes_factor* L, int J) {
 }
 
 // owned tiles [tile_begin, tile_end) -= panel J panel J'
-static int dist_update(nes_ctx* c, nes_factor* L, int J, int tile_begin, int tile_end) {
+static int dist_update(nes_ctx* c, nes_factor* L, int J, int tile_begin, int tile_end,
+                       cudaStream_t stream = nullptr, bool one_tile_per_cta = false) {
     if (tile_begin >= tile_end) return 0;
     const int m = (int)L->m, nbo = L->nbo, j0 = J * nbo;
     NtArgs a{};
@@ -331,31 +332,41 @@ static int dist_update(nes_ctx* c, nes_factor* L, int J, int tile_begin, int til
     a.same_operand = 1;
     a.tile_list = L->d_tile_list + tile_begin;
     a.ntiles = tile_end - tile_begin;
-    cudaError_t e = nt_launch(L->mapM, L->mapM, a, c->num_sms, c->stream);
+    cudaError_t e = nt_launch(L->mapM, L->mapM, a, one_tile_per_cta ? (1 << 30) : c->num_sms,
+                              stream ? stream : c->stream);
     ++c->launches;
     if (e != cudaSuccess)
         return fail(c, NES_ERR_CUDA, "distributed update launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
+// Every rank: the main (high-priority) stream carries the panel chain -- update of the next block
+// column (owner only), its factorization (owner only), the broadcast and the unpack -- while the
+// low-priority side stream applies the previous panel to the rest of this rank's tiles, one tile per
+// CTA so the chain (and NCCL's kernels) get SMs at tile granularity.  Same two events as the
+// single-GPU look-ahead.
 static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L) {
     const int m = (int)L->m, nbo = L->nbo, P = c->nranks;
     const int nblk = (m + nbo - 1) / nbo;
+    const int* tf = L->tile_first.data();
     if (c->rank == dist_owner(0, P)) NES_TRY(dist_factor_panel(c, L, 0));
     NES_TRY(dist_exchange_panel(c, L, 0));
+    bool pending_update = false;
     for (int J = 0; J + 1 < nblk; ++J) {
         const int next = J + 1;
-        const int* tf = L->tile_first.data();
-        if (c->rank == dist_owner(next, P)) {
-            NES_TRY(dist_update(c, L, J, tf[next], tf[next + 1]));       // block column `next` only
-            NES_TRY(dist_factor_panel(c, L, next));
-            NES_TRY(dist_exchange_panel(c, L, next));                     // root of the broadcast
-            NES_TRY(dist_update(c, L, J, tf[next + 1], L->ntiles_owned)); // the rest of my columns
-        } else {
-            NES_TRY(dist_update(c, L, J, tf[next], L->ntiles_owned));
-            NES_TRY(dist_exchange_panel(c, L, next));
+        NES_CUDA(c, cudaEventRecord(c->ev_panel, c->stream));                       // panel J is here
+        if (pending_update) NES_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_update, 0));
+        NES_TRY(dist_update(c, L, J, tf[next], tf[next + 1]));                      // block column `next` (owner)
+        if (tf[next + 1] < L->ntiles_owned) {                                       // the rest, side stream
+            NES_CUDA(c, cudaStreamWaitEvent(c->stream_aux, c->ev_panel, 0));
+            NES_TRY(dist_update(c, L, J, tf[next + 1], L->ntiles_owned, c->stream_aux, true));
+            NES_CUDA(c, cudaEventRecord(c->ev_update, c->stream_aux));
+            pending_update = true;
         }
+        if (c->rank == dist_owner(next, P)) NES_TRY(dist_factor_panel(c, L, next));
+        NES_TRY(dist_exchange_panel(c, L, next));
     }
+    if (pending_update) NES_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_update, 0));
     return 0;
 }
 
