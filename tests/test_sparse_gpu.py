@@ -156,3 +156,47 @@ def test_config4_flow_mps_to_pdas(common, tmp_path):
     oobj, ogap, oit = opdas.pdas(ost, 400)
     obj, gap, it = pdas.pdas(pdas.make_pdas(sf), 400)
     assert it == oit and abs(obj - oobj) <= 1e-8 * abs(oobj)
+
+
+@pytest.mark.parametrize("name", ["dense_row", "components", "dense_block"])
+def test_sparse_edge_patterns(common, name):
+    """A fully dense row, a forest of disconnected components, chains wider than one supernode."""
+    from test_symbolic import _edge_matrices
+    A = _edge_matrices()[name]
+    m, n = A.shape
+    rng = np.random.default_rng(1)
+    s = np.sqrt(0.1 + 10 * rng.random(n))
+    b = rng.random(m)
+    common.lib.nes_set_ordering_leaf(common.ptr, 64)
+    try:
+        Ad = to_device(common, A)
+        Ad.scale(s)
+        L = nes.Factor(common, Ad)
+        assert L.factorize(Ad)
+        x = L.solve(b)
+        M = ons.normal_matrix(A, s)
+        assert np.linalg.norm(M @ x - b) <= 1e-12 * np.linalg.norm(M) * np.linalg.norm(x)
+        out = np.zeros((m, m), order="F")
+        perm = np.zeros(m, dtype=np.int32)
+        common.check(common.lib.nes_factor_to_dense(L.ptr, out.ctypes.data_as(nes._dp), m,
+                                                    perm.ctypes.data_as(nes._ip), common.ptr), "to_dense")
+        Mp = M[np.ix_(perm, perm)]
+        assert relerr(out @ out.T, Mp) <= 1e-12
+        # refactorize with another scale through the same analysis (solve-sparse-recycle), bitwise repeatable
+        x1 = L.solve(b)
+        assert L.factorize(Ad)
+        np.testing.assert_array_equal(L.solve(b), x1)
+        L.free()
+        Ad.free()
+    finally:
+        common.lib.nes_set_ordering_leaf(common.ptr, 0)
+
+
+def test_sparse_empty_row_is_not_positive_definite(common):
+    A = sp.csc_matrix(np.array([[1.0, 2.0, 0.0], [0.0, 0.0, 0.0], [0.0, 1.0, 1.0]]))   # row 1 is empty
+    Ad = to_device(common, A)
+    L = nes.Factor(common, Ad)
+    assert not L.factorize(Ad)
+    assert common.status == nes.NES_NOT_POSDEF and 0 <= common.minor < 3
+    L.free()
+    Ad.free()

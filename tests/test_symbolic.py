@@ -152,3 +152,57 @@ def test_subtree_to_rank_mapping(Q):
     fl = nc * S["nr"].astype(float) ** 2
     load = np.array([fl[owner == q].sum() for q in range(Q)])
     assert load.max() <= 1.6 * load.mean()
+
+
+def _edge_matrices():
+    rng = np.random.default_rng(9)
+    out = {}
+    # one fully dense row (goes last in the ordering), the rest banded
+    A = banded(rng, 500, 1100, 6, 4).tolil()
+    A[137, :] = 1.0 + rng.random(1100)
+    out["dense_row"] = sp.csc_matrix(A)
+    # three disconnected components (independent subtrees of the elimination forest) + an isolated row
+    blocks = [banded(rng, k, 2 * k + 3, 5, 4) for k in (150, 90, 260)] + [sp.csc_matrix(np.array([[2.0]]))]
+    out["components"] = sp.block_diag(blocks, format="csc")
+    # dense-ish: chains longer than 128 columns must be split into several supernodes
+    out["dense_block"] = sp.csc_matrix(rng.random((300, 400)) * (rng.random((300, 400)) < 0.3) + np.eye(300, 400))
+    return out
+
+
+@pytest.mark.parametrize("name", ["dense_row", "components", "dense_block"])
+def test_symbolic_edge_patterns(name):
+    A = _edge_matrices()[name]
+    m, n = A.shape
+    S = analyze(A, leaf=64)
+    perm = S["perm"]
+    assert sorted(perm.tolist()) == list(range(m))
+    if name == "dense_row":
+        assert perm[-1] == 137                      # the dense row is eliminated last
+    if name == "components":
+        assert (S["sparent"] == -1).sum() >= 4      # a forest: one root per component
+    if name == "dense_block":
+        assert np.diff(S["first"]).max() == 128 and S["nsuper"] >= 3
+    rng = np.random.default_rng(1)
+    s_ = np.sqrt(0.1 + 10 * rng.random(n))
+    M = ons.normal_matrix(A, s_)
+    b = rng.random(m)
+    L, x = factor_and_solve_all_ranks(S, M, b, 1)
+    Mp = M[np.ix_(perm, perm)]
+    assert np.linalg.norm(L @ L.T - Mp) / np.linalg.norm(Mp) <= 1e-12
+    assert np.linalg.norm(M @ x - b) <= 1e-12 * np.linalg.norm(M) * np.linalg.norm(x)
+    # the same patterns sharded over 3 ranks (odd count, forest with several roots)
+    S3 = analyze(A, nranks=3, leaf=64)
+    L3, x3 = factor_and_solve_all_ranks(S3, M, b, 3)
+    Mp3 = M[np.ix_(S3["perm"], S3["perm"])]
+    assert np.linalg.norm(L3 @ L3.T - Mp3) / np.linalg.norm(Mp3) <= 1e-12
+    assert np.linalg.norm(M @ x3 - b) <= 1e-12 * np.linalg.norm(M) * np.linalg.norm(x3)
+
+
+def test_symbolic_degenerate_shapes():
+    # no columns at all, a single entry, an empty row: the analysis must still produce a valid structure
+    for A in (sp.csc_matrix((4, 0)), sp.csc_matrix(np.array([[3.0]])),
+              sp.csc_matrix(np.array([[1.0, 2.0, 0.0], [0.0, 0.0, 0.0], [0.0, 1.0, 1.0]]))):
+        S = analyze(A)
+        m = A.shape[0]
+        assert sorted(S["perm"].tolist()) == list(range(m))
+        assert S["first"][-1] == m and S["lnz"] >= m
