@@ -219,7 +219,8 @@ int nes_start(nes_ctx* c) {
     if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->stream_aux, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&c->ev_update, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&c->ev_update, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming) != cudaSuccess) {
         fail(c, NES_ERR_CUDA, "cudaStreamCreate failed");
         return 0;
     }
@@ -269,7 +270,8 @@ int nes_finish(nes_ctx* c) {
     c->mark_a = c->mark_b = nullptr;
     if (c->ev_panel) cudaEventDestroy(c->ev_panel);
     if (c->ev_update) cudaEventDestroy(c->ev_update);
-    c->ev_panel = c->ev_update = nullptr;
+    if (c->ev_aux) cudaEventDestroy(c->ev_aux);
+    c->ev_panel = c->ev_update = c->ev_aux = nullptr;
     if (c->stream_aux) cudaStreamDestroy(c->stream_aux);
     c->stream_aux = nullptr;
     if (c->stream) cudaStreamDestroy(c->stream);

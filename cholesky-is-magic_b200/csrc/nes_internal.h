@@ -38,7 +38,7 @@ struct nes_ctx {
     // low-priority side stream + events for the look-ahead of the dense Cholesky (trailing update of
     // panel J overlaps the factorization of panel J+1, which runs on `stream` at high priority)
     cudaStream_t stream_aux = nullptr;
-    cudaEvent_t ev_panel = nullptr, ev_update = nullptr;
+    cudaEvent_t ev_panel = nullptr, ev_update = nullptr, ev_aux = nullptr;
     char err[512] = {0};
     long long launches = 0;
 

@@ -76,7 +76,6 @@ struct MfDesc {
     const CUtensorMap* maps;
     int* info;
     double dbound;
-    int dbg;
 };
 
 // NES_SPARSE_SYNC=1: synchronise after every launch of the sparse path and name the kernel that failed
@@ -898,9 +897,13 @@ void sparse_free(nes_ctx* c, nes_factor* L) {
 // ------------------------------------------------------------------------------------------------
 // host: numeric factorization
 // ------------------------------------------------------------------------------------------------
+// Level loop of one phase on the library's stream.  The low-priority side stream computes the inverses
+// W_s of the diagonal blocks (needed by the solves only) while the narrow top of the tree leaves most
+// SMs idle; they used to be one 0.7 ms launch at the end.
 static int run_factor_phase(nes_ctx* c, SparseFactor* sf, int ph) {
     const Phase& P = sf->phase[ph];
     const Symbolic& S = sf->S;
+    int trtri_done = 0;  // supernodes [0, trtri_done) of this phase's list have their inverse enqueued
     for (int l = 0; l < S.nlevels; ++l) {
         if (P.pptr[l + 1] == P.pptr[l]) continue;
         for (int wide = 0; wide < 2; ++wide) {
@@ -909,6 +912,17 @@ static int run_factor_phase(nes_ctx* c, SparseFactor* sf, int ph) {
             const int ncmax = wide ? CH_NB : 64;
             mf_potrf_kernel<<<b - a, 256, mf_diag_smem(ncmax), c->stream>>>(sf->d, P.d_potrf + a, ncmax);
             MF_LAUNCHED(c, "mf_potrf_kernel");
+        }
+        // block inverses: held back while the levels are wide (they would take SMs from the factorization),
+        // released in one go when the tree narrows to <= 32 supernodes per level and the SMs are mostly idle
+        const int width = P.pptr[l + 1] - P.pptr[l];
+        if (width <= 32 || l + 1 == S.nlevels || P.pptr[l + 1] == P.count) {
+            NES_CUDA(c, cudaEventRecord(c->ev_panel, c->stream));
+            NES_CUDA(c, cudaStreamWaitEvent(c->stream_aux, c->ev_panel, 0));
+            const int from = trtri_done;
+            mf_trtri_kernel<<<P.pptr[l + 1] - from, CH_NB, MF_TI_SMEM, c->stream_aux>>>(sf->d, P.d_potrf + from);
+            NES_CHECK_LAUNCH(c);
+            trtri_done = P.pptr[l + 1];
         }
         for (int wide = 0; wide < 2; ++wide) {
             const int a = wide ? P.tsplit[l] : P.tptr[l], b = wide ? P.tptr[l + 1] : P.tsplit[l];
@@ -935,6 +949,8 @@ static int enqueue_factorization(nes_ctx* c, SparseFactor* sf, const MatrixBase*
     const Symbolic& S = sf->S;
     NES_CUDA(c, cudaMemsetAsync(sf->d.Lv, 0, (size_t)S.lsize * sizeof(double), c->stream));
     NES_CUDA(c, cudaMemsetAsync(sf->d_info, 0, 2 * sizeof(int), c->stream));
+    // (assembling the levels above the bottom one on the side stream was measured: the low-priority
+    // kernel starves behind the bottom level and the factorization then waits for it, +2.2 ms)
     if (S.anz > 0) {
         sparse_assemble_kernel<<<(unsigned)((S.anz + 255) / 256), 256, 0, c->stream>>>(
             S.anz, sf->d_ei, sf->d_ej, sf->d_edest, b->d_rowptr, b->d_colidx, b->d_csr_val, d_theta, sf->d.Lv);
@@ -952,7 +968,6 @@ int sparse_factorize(nes_ctx* c, nes_matrix* A, nes_factor* L) {
     const Symbolic& S = sf->S;
     L->factorized = 0;
     sf->d.dbound = c->dbound;
-    sf->d.dbg = getenv("NES_SPARSE_DBG") ? atoi(getenv("NES_SPARSE_DBG")) : 0;
     {
         StageTimer t(c, NES_STAGE_FACTOR);
         NES_TRY(enqueue_factorization(c, sf, b, A->d_theta));
@@ -964,10 +979,8 @@ int sparse_factorize(nes_ctx* c, nes_matrix* A, nes_factor* L) {
             }
         }
         NES_TRY(run_factor_phase(c, sf, 1));
-        if (sf->nall > 0) {  // block inverses for the solves
-            mf_trtri_kernel<<<sf->nall, CH_NB, MF_TI_SMEM, c->stream>>>(sf->d, sf->d_all);
-            MF_LAUNCHED(c, "mf_trtri_kernel");
-        }
+        NES_CUDA(c, cudaEventRecord(c->ev_aux, c->stream_aux));  // join: the block inverses are complete
+        NES_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_aux, 0));
         if (c->nranks > 1) {  // a failed pivot is seen by one rank only: agree on {status, first minor}
             info_first_minor_kernel<<<1, 32, 0, c->stream>>>(sf->d_info);
             NES_CHECK_LAUNCH(c);

@@ -17,5 +17,7 @@ Lisp control flow and algebra operation-for-operation and plays CHOLMOD/LAPACK's
 OpenBLAS (dsyrk-like products + dpotrf/dpotrs through scipy.linalg).  It is pinned only by the
 reference's own property tests, which tests/test_oracle.py re-runs with the reference's
 generators and thresholds (four KKT residuals <= 1e-6), plus the literal IPM rules (init, step,
-stop) transcribed from primal-dual-affine-scaling.lisp / affine-scaling.lisp.
+stop) transcribed from primal-dual-affine-scaling.lisp / affine-scaling.lisp, and -- independently of
+this restatement -- by tests/test_known_answers.py: its PDAS and affine scaling must reach the optimum
+that HiGHS (scipy.optimize.linprog) finds on the same LPs, within the reference's stop tolerance.
 """

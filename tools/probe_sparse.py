@@ -6,8 +6,10 @@ from cholesky_is_magic_b200.sparse_cholesky import with_cholmod
 m = int(sys.argv[1]) if len(sys.argv) > 1 else 100000
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 250000
 bw = int(sys.argv[3]) if len(sys.argv) > 3 else 400
+leaf = int(sys.argv[4]) if len(sys.argv) > 4 else 0
 t0 = time.perf_counter(); sf = lpgen.sparse_lp(m, n, nnz_per_col=10, bandwidth=bw, seed=0); print("gen %.2fs nnz %d" % (time.perf_counter() - t0, len(sf.A)))
 with with_cholmod(device=0, timing=True) as c:
+    c.lib.nes_set_ordering_leaf(c.ptr, leaf)
     t0 = time.perf_counter(); A = nes.Matrix.from_triplets(c, sf.A.row, sf.A.col, sf.A.value, m, n); print("upload %.2fs" % (time.perf_counter() - t0))
     A.scale(np.sqrt(0.1 + 10 * np.random.default_rng(0).random(n)))
     t0 = time.perf_counter(); L = nes.Factor(c, A); print("analyze %.2fs anz %.3g aatfl %.3g lnz %.3g fl %.3g mem %.2f GB" % (time.perf_counter() - t0, c.anz, c.aatfl, c.lnz, c.fl, c.memory_inuse / 1e9))
