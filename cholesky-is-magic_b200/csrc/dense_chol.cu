@@ -375,7 +375,6 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
     NES_TRY(chol_configure(c));
     const int m = (int)L->m;
     const long long ld = (long long)L->ld;
-    const int NBO = dense_outer_block(m);
     const int P = c->nranks;
     NES_CUDA(c, cudaMemsetAsync(L->d_info, 0, 2 * sizeof(int), c->stream));
     if (P > 1) NES_TRY(dense_cholesky_dist_steps(c, L));

@@ -11,6 +11,7 @@
 //
 // NCCL is resolved at run time (dlopen) so the library still loads on hosts without it; the unique id
 // travels through the caller's launcher (torch.distributed in bench.py / tests).
+#include <cstdlib>
 #include <dlfcn.h>
 #include <nccl.h>
 
@@ -50,7 +51,18 @@ static NcclApi* nccl_api() {
     return &api;
 }
 
-int dense_outer_block(int m) { return (m > 12288) ? 512 : 256; }
+// Distribution block = outer panel width of the distributed factorization.  Wide panels (512) make the
+// trailing updates efficient, which is what bounds the step on 1-2 GPUs; from 4 GPUs on every rank's share of
+// the update is small and the panel chain (owner's column update + panel + broadcast) bounds it, and
+// that chain is shorter per column with 256-wide panels.  NES_DIST_NBO overrides (testing).
+int dense_outer_block(int m, int nranks) {
+    if (const char* e = getenv("NES_DIST_NBO")) {
+        const int v = atoi(e);
+        if (v == 128 || v == 256 || v == 512) return v;
+    }
+    if (m <= 12288) return 256;
+    return nranks >= 4 ? 256 : 512;
+}
 
 // Owner of outer block column J.  Plain cyclic ownership always hands rank 0 the longest column of
 // every round (11% more tiles than average at m = 32768 on 8 ranks); walking the ranks back and forth
@@ -171,7 +183,7 @@ int nes_dist_plan(int m, int nranks, int rank, int* tile_rows, int* tile_cols, i
     if (m <= 0 || nranks < 1 || rank < 0 || rank >= nranks) return NES_ERR_INVALID;
     std::vector<int2> tiles;
     std::vector<int> first;
-    const int n = dist_plan_tiles(m, dense_outer_block(m), nranks, rank, tiles, first);
+    const int n = dist_plan_tiles(m, dense_outer_block(m, nranks), nranks, rank, tiles, first);
     for (int i = 0; i < n && i < cap; ++i) {
         if (tile_rows) tile_rows[i] = tiles[i].x;
         if (tile_cols) tile_cols[i] = tiles[i].y;

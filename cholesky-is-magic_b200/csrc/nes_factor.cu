@@ -71,7 +71,7 @@ nes_factor* nes_analyze(nes_matrix* A, nes_ctx* c) {
     }
     if (c->nranks > 1) {
         // distributed factorization: owned-tile list + packed-panel staging buffer
-        L->nbo = dense_outer_block((int)m);
+        L->nbo = dense_outer_block((int)m, c->nranks);
         std::vector<int2> tiles;
         L->ntiles_owned = dist_plan_tiles((int)m, L->nbo, c->nranks, c->rank, tiles, L->tile_first);
         L->d_tile_list = static_cast<int2*>(dev_alloc(c, (tiles.size() + 1) * sizeof(int2)));

@@ -212,7 +212,7 @@ int dist_plan_tiles(int m, int nbo, int nranks, int rank, std::vector<int2>& til
                     std::vector<int>& tile_first);
 int dist_broadcast(nes_ctx* c, double* d_buf, size_t count, int root);
 int dist_allreduce_int(nes_ctx* c, int* d_buf, size_t count, int op_max_else_min);
-int dense_outer_block(int m);
+int dense_outer_block(int m, int nranks);
 int dist_owner(int J, int nranks);
 // install a column scale that already lives on the device (nes_scale without the PCIe hop)
 int set_scale_dev(nes_ctx* c, nes_matrix* A, const double* d_s);
