@@ -121,10 +121,69 @@ __global__ void spmv_csc_t_kernel(const int* __restrict__ colptr, const int* __r
     y[j] = (beta == 0.0) ? alpha * acc : fma(alpha, acc, beta * y[j]);
 }
 
+__global__ void axpby_kernel(int n, double alpha, const double* __restrict__ t, double beta,
+                             double* __restrict__ y) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = (beta == 0.0) ? alpha * t[i] : fma(alpha, t[i], beta * y[i]);
+}
+
+int dist_allreduce_sum(nes_ctx* c, double* d_buf, size_t count);  // nes_dist.cu
+
+// Multi-GPU dense products: A is replicated, so every rank multiplies only ITS block
+// of columns -- 1/Q of the HBM traffic -- and one all-reduce of the m-vector (forward) or of the
+// zero-padded n-vector (transposed) completes the product; NCCL's all-reduce returns bit-identical
+// results on every rank, so the replicated control flow of the IPM stays in lockstep.
+static int matvec_dense_split(nes_ctx* c, const MatrixBase* b, const double* d_s, int transpose, double alpha,
+                              const double* d_x, double beta, double* d_y) {
+    const int m = (int)b->m, n = (int)b->n, Q = c->nranks, r = c->rank;
+    const int k0 = (int)((long long)n * r / Q) & ~15, k1 = (r + 1 == Q) ? n : ((int)((long long)n * (r + 1) / Q) & ~15);
+    const int nsub = k1 - k0;
+    const double* Asub = b->d_val + (size_t)k0 * b->ld;
+    const double* ssub = d_s ? d_s + k0 : nullptr;
+    if (!transpose) {
+        const int rowblocks = (m + 2 * GN_THREADS - 1) / (2 * GN_THREADS);
+        int want = (c->num_sms * 4 + rowblocks - 1) / rowblocks;
+        int cols = (nsub + want - 1) / want;
+        cols = (cols + 63) / 64 * 64;
+        if (cols < 64) cols = 64;
+        const int nparts = nsub > 0 ? (nsub + cols - 1) / cols : 0;
+        const size_t ldp = (size_t)(m + 1) / 2 * 2;
+        double* ws = ensure_ws(c, WS_MATVEC, ((size_t)(nparts + 1) * ldp + 16) * sizeof(double));
+        if (!ws) return c->status;
+        double* sum = ws;
+        double* part = ws + ldp;
+        if (nparts > 0) {
+            gemv_n_partial_kernel<<<dim3(rowblocks, nparts), GN_THREADS, 0, c->stream>>>(
+                Asub, b->ld, m, nsub, cols, d_x + k0, ssub, part, ldp);
+            NES_CHECK_LAUNCH(c);
+        }
+        gemv_n_finish_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(part, ldp, nparts, m, 1.0, 0.0, sum);
+        NES_CHECK_LAUNCH(c);
+        NES_TRY(dist_allreduce_sum(c, sum, (size_t)m));
+        axpby_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(m, alpha, sum, beta, d_y);
+        NES_CHECK_LAUNCH(c);
+    } else {
+        double* tmp = ensure_ws(c, WS_MATVEC, ((size_t)n + 16) * sizeof(double));
+        if (!tmp) return c->status;
+        NES_CUDA(c, cudaMemsetAsync(tmp, 0, (size_t)n * sizeof(double), c->stream));
+        if (nsub > 0) {
+            gemv_t_kernel<<<(nsub + 15) / 16, 256, 0, c->stream>>>(Asub, b->ld, m, nsub, d_x, ssub, 1.0, 0.0,
+                                                                   tmp + k0);
+            NES_CHECK_LAUNCH(c);
+        }
+        NES_TRY(dist_allreduce_sum(c, tmp, (size_t)n));
+        axpby_kernel<<<(n + 255) / 256, 256, 0, c->stream>>>(n, alpha, tmp, beta, d_y);
+        NES_CHECK_LAUNCH(c);
+    }
+    return 0;
+}
+
 static int matvec_impl(nes_ctx* c, const MatrixBase* b, const double* d_s, int transpose, double alpha,
                        const double* d_x, double beta, double* d_y) {
     StageTimer timer(c, NES_STAGE_GEMV);
     const int m = (int)b->m, n = (int)b->n;
+    if (b->dense && c->nranks > 1 && c->nccl_comm && (long long)m * n >= (1 << 18) && n >= 64 * c->nranks)
+        return matvec_dense_split(c, b, d_s, transpose, alpha, d_x, beta, d_y);
     if (b->dense) {
         if (!transpose) {
             const int rowblocks = (m + 2 * GN_THREADS - 1) / (2 * GN_THREADS);
