@@ -1,0 +1,418 @@
+// First-order solver of approx.lisp on the GPU: APPROX -- accelerated parallel
+// proximal coordinate descent with full-vector steps -- on the penalised primal-dual formulation
+// min sum_i 1/2 (scale_i (k_i . v - rhs_i))^2 + lin . v + complementarity terms,  l <= v <= u,
+// v = [x | y | z | w].  The stacked constraint matrix K (one row per `quadratic`, approx.lisp:36-58) is an
+// ordinary sparse nes_matrix, so value-&-gradient (approx.lisp:301-351) is two of the engine's
+// atomic-free SpMV kernels (K v by rows, K' r by columns) plus elementwise / reduction kernels; every
+// iteration of `approx` (:425-459) is HBM-bound: two gradients = 4 passes over K.
+//   scale-quadratic (:70-74)        approx_scale_kernel
+//   accumulate-nu (:97-113)         approx_nu_kernel
+//   violation, %value-&-gradient    approx_resid_kernel + SpMVs + approx_comp_kernel
+//   solve-coordinate, approx-iteration (:353-398)   approx_y_kernel, approx_descent_kernel
+//   restart test, project-gradient (:400-423, :441-449)   approx_reduce_kernel, approx_apply_kernel
+// Reductions run in one CTA in a fixed order: results are bitwise reproducible.
+#include "nes_internal.h"
+
+struct nes_approx {
+    nes_matrix* K = nullptr;  // borrowed
+    int R = 0, N = 0, ncomp = 0;
+    double z0 = 0.0;
+    double *rhs = nullptr, *scale = nullptr, *beta = nullptr, *lin = nullptr, *nu = nullptr, *l = nullptr, *u = nullptr;
+    int *comp_x = nullptr, *comp_y = nullptr, *comp_flip = nullptr;
+    double* comp_x0 = nullptr;
+    // iteration state
+    double *x = nullptr, *z = nullptr, *y = nullptr, *zp = nullptr, *g = nullptr, *t = nullptr, *rs = nullptr;
+    double* red = nullptr;  // 8 scalars
+};
+
+namespace nes {
+
+constexpr int AP_T = 1024;
+
+__global__ void approx_scale_kernel(int R, const int* __restrict__ rowptr, const double* __restrict__ val,
+                                    const double* __restrict__ rhs, int do_scale, double* __restrict__ scale,
+                                    double* __restrict__ beta) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    double acc = 0.0;
+    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) acc = fma(val[k], val[k], acc);
+    acc = fma(rhs[r], rhs[r], acc);
+    const double norm = sqrt(acc);
+    scale[r] = (do_scale && norm > 1e-6) ? 1.0 / norm : 1.0;
+    beta[r] = (double)(rowptr[r + 1] - rowptr[r]);
+}
+
+__global__ void approx_nu_kernel(int N, const int* __restrict__ colptr, const int* __restrict__ rowidx,
+                                 const double* __restrict__ val, const double* __restrict__ scale,
+                                 const double* __restrict__ beta, double* __restrict__ nu) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    double acc = 0.0;
+    for (int k = colptr[j]; k < colptr[j + 1]; ++k) {
+        const int r = rowidx[k];
+        const double cs = val[k] * scale[r];
+        acc = fma(beta[r], cs * cs, acc);
+    }
+    nu[j] = acc;
+}
+
+// viol_r = (t_r - rhs_r) scale_r; rs_r = scale_r viol_r (the factor of the gradient K' rs)
+__global__ void approx_resid_kernel(int R, const double* __restrict__ t, const double* __restrict__ rhs,
+                                    const double* __restrict__ scale, double* __restrict__ rs) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= R) return;
+    const double v = (t[r] - rhs[r]) * scale[r];
+    rs[r] = scale[r] * v;
+}
+
+// complementarity constraints of one orientation (each x_i and each y_i appears at most once per
+// orientation, so plain read-modify-writes do not collide)
+__global__ void approx_comp_kernel(int ncomp, const int* __restrict__ cx, const int* __restrict__ cy,
+                                   const double* __restrict__ cx0, const int* __restrict__ flip, int want_flip,
+                                   const double* __restrict__ v, double* __restrict__ g) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ncomp || flip[k] != want_flip) return;
+    double xk = v[cx[k]] - cx0[k];
+    double yk = v[cy[k]];
+    if (want_flip) xk = -xk;
+    xk = xk < 0.0 ? 0.0 : xk;
+    yk = yk < 0.0 ? 0.0 : yk;
+    g[cx[k]] += want_flip ? -yk : yk;
+    g[cy[k]] += xk;
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    sh[tid] = v;
+    __syncthreads();
+    for (int o = AP_T / 2; o > 0; o >>= 1) {
+        if (tid < o) sh[tid] += sh[tid + o];
+        __syncthreads();
+    }
+    return sh[0];
+}
+__device__ __forceinline__ double block_max(double v, double* sh) {
+    const int tid = threadIdx.x;
+    __syncthreads();
+    sh[tid] = v;
+    __syncthreads();
+    for (int o = AP_T / 2; o > 0; o >>= 1) {
+        if (tid < o) sh[tid] = fmax(sh[tid], sh[tid + o]);
+        __syncthreads();
+    }
+    return sh[0];
+}
+
+// value-&-gradient scalars (approx.lisp:338-351) of the point v whose residuals are in t:
+// red[0] = sum of constraint values, red[1] = max |constraint value|
+__global__ void __launch_bounds__(AP_T)
+approx_value_kernel(int R, int N, int ncomp, const double* __restrict__ t, const double* __restrict__ rhs,
+                    const double* __restrict__ scale, const double* __restrict__ lin,
+                    const int* __restrict__ cx, const int* __restrict__ cy, const double* __restrict__ cx0,
+                    const int* __restrict__ flip, const double* __restrict__ v, double* __restrict__ red) {
+    __shared__ double sh[AP_T];
+    const int tid = threadIdx.x;
+    double sum = 0.0, mx = 0.0;
+    for (int r = tid; r < R; r += AP_T) {
+        const double vi = (t[r] - rhs[r]) * scale[r];
+        const double val = 0.5 * vi * vi;
+        sum += val;
+        mx = fmax(mx, val);
+    }
+    double lsum = 0.0;
+    for (int j = tid; j < N; j += AP_T) lsum = fma(lin[j], v[j], lsum);
+    for (int k = tid; k < ncomp; k += AP_T) {
+        double xk = v[cx[k]] - cx0[k];
+        double yk = v[cy[k]];
+        if (flip[k]) xk = -xk;
+        xk = xk < 0.0 ? 0.0 : xk;
+        yk = yk < 0.0 ? 0.0 : yk;
+        const double val = yk * xk;
+        sum += val;
+        mx = fmax(mx, fabs(val));
+    }
+    const double lin_total = block_sum(lsum, sh);
+    const double total = block_sum(sum, sh);
+    const double m = block_max(mx, sh);
+    if (tid == 0) {
+        red[0] = total + lin_total;
+        red[1] = fmax(m, fabs(lin_total));
+    }
+}
+
+__global__ void approx_addlin_kernel(int N, const double* __restrict__ lin, double* __restrict__ g) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < N) g[j] += lin[j];
+}
+
+__global__ void approx_y_kernel(int N, double theta, const double* __restrict__ x, const double* __restrict__ z,
+                                double* __restrict__ y) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < N) y[j] = (1.0 - theta) * x[j] + theta * z[j];
+}
+
+// zp = solve-coordinate (approx.lisp:353-369); x <- y + theta (zp - z) (approx-iteration :390-392)
+__global__ void approx_descent_kernel(int N, double theta, const double* __restrict__ y, const double* __restrict__ z,
+                                      const double* __restrict__ nu, const double* __restrict__ g,
+                                      const double* __restrict__ l, const double* __restrict__ u,
+                                      double* __restrict__ zp, double* __restrict__ x) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    const double step = theta * nu[j];
+    const double zj = z[j], gj = g[j];
+    double best;
+    if (step == 0.0) {
+        best = gj < 0.0 ? u[j] : (gj > 0.0 ? l[j] : zj);
+    } else {
+        best = zj - gj / step;
+        if (best < l[j]) best = l[j];
+        else if (best > u[j]) best = u[j];
+    }
+    zp[j] = best;
+    x[j] = y[j] + theta * (best - zj);
+}
+
+// red[2] = g . (zp - z) (dot-diff, :412-417), red[3] = |g|_2
+__global__ void __launch_bounds__(AP_T)
+approx_dot_kernel(int N, const double* __restrict__ g, const double* __restrict__ z, const double* __restrict__ zp,
+                  double* __restrict__ red) {
+    __shared__ double sh[AP_T];
+    double d = 0.0, gg = 0.0;
+    for (int j = threadIdx.x; j < N; j += AP_T) {
+        d = fma(g[j], zp[j] - z[j], d);
+        gg = fma(g[j], g[j], gg);
+    }
+    const double ds = block_sum(d, sh);
+    const double gs = block_sum(gg, sh);
+    if (threadIdx.x == 0) {
+        red[2] = ds;
+        red[3] = sqrt(gs);
+    }
+}
+
+// restart (x <- z) or accept (z <- zp) (:441-446), then red[4] = |z - clamp(z - g)|_2 (project-gradient)
+__global__ void __launch_bounds__(AP_T)
+approx_apply_kernel(int N, int restart, const double* __restrict__ g, const double* __restrict__ zp,
+                    const double* __restrict__ l, const double* __restrict__ u, double* __restrict__ z,
+                    double* __restrict__ x, double* __restrict__ red) {
+    __shared__ double sh[AP_T];
+    double acc = 0.0;
+    for (int j = threadIdx.x; j < N; j += AP_T) {
+        double zj;
+        if (restart) {
+            zj = z[j];
+            x[j] = zj;
+        } else {
+            zj = zp[j];
+            z[j] = zj;
+        }
+        double xp = zj - g[j];
+        if (xp < l[j]) xp = l[j];
+        if (xp > u[j]) xp = u[j];
+        const double dd = zj - xp;
+        acc = fma(dd, dd, acc);
+    }
+    const double s = block_sum(acc, sh);
+    if (threadIdx.x == 0) red[4] = sqrt(s);
+}
+
+__global__ void approx_project_kernel(int N, const double* __restrict__ l, const double* __restrict__ u,
+                                      double* __restrict__ x, double* __restrict__ z) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= N) return;
+    double v = x[j];
+    v = fmin(u[j], fmax(l[j], v));
+    x[j] = v;
+    z[j] = v;
+}
+
+// g <- gradient at v, red[0..1] <- value, max
+static int approx_value_gradient_dev(nes_ctx* c, nes_approx* st, const double* d_v) {
+    const MatrixBase* b = st->K->base;
+    NES_TRY(matvec_unscaled(c, b, 0, 1.0, d_v, 0.0, st->t));
+    StageTimer timer(c, NES_STAGE_VECTOR);
+    approx_resid_kernel<<<(st->R + 255) / 256, 256, 0, c->stream>>>(st->R, st->t, st->rhs, st->scale, st->rs);
+    NES_CHECK_LAUNCH(c);
+    approx_value_kernel<<<1, AP_T, 0, c->stream>>>(st->R, st->N, st->ncomp, st->t, st->rhs, st->scale, st->lin,
+                                                   st->comp_x, st->comp_y, st->comp_x0, st->comp_flip, d_v, st->red);
+    NES_CHECK_LAUNCH(c);
+    NES_TRY(matvec_unscaled(c, b, 1, 1.0, st->rs, 0.0, st->g));
+    approx_addlin_kernel<<<(st->N + 255) / 256, 256, 0, c->stream>>>(st->N, st->lin, st->g);
+    NES_CHECK_LAUNCH(c);
+    if (st->ncomp > 0) {
+        for (int flip = 0; flip < 2; ++flip) {
+            approx_comp_kernel<<<(st->ncomp + 255) / 256, 256, 0, c->stream>>>(
+                st->ncomp, st->comp_x, st->comp_y, st->comp_x0, st->comp_flip, flip, d_v, st->g);
+            NES_CHECK_LAUNCH(c);
+        }
+    }
+    return 0;
+}
+
+template <typename T>
+static T* ap_upload(nes_ctx* c, const T* h, size_t n) {
+    T* p = static_cast<T*>(dev_alloc(c, (n + 2) * sizeof(T)));
+    if (!p) return nullptr;
+    if (n && h && upload(c, p, h, n * sizeof(T)) != 0) return nullptr;
+    return p;
+}
+
+}  // namespace nes
+
+using namespace nes;
+
+extern "C" {
+
+nes_approx* nes_approx_create(nes_matrix* K, const double* rhs, const double* lin, const double* l, const double* u,
+                              const int* comp_x, const int* comp_y, const double* comp_x0, const int* comp_flipped,
+                              int ncomp, int scale, double z0, nes_ctx* c) {
+    NES_ENTER_PTR(c);
+    if (!K || !K->base || K->base->dense || !rhs || !lin || !l || !u || ncomp < 0) {
+        fail(c, NES_ERR_INVALID, "nes_approx_create: needs a sparse constraint matrix and its vectors");
+        return nullptr;
+    }
+    nes_approx* st = new nes_approx();
+    st->K = K;
+    st->R = (int)K->base->m;
+    st->N = (int)K->base->n;
+    st->ncomp = ncomp;
+    st->z0 = z0;
+    const size_t R = st->R, N = st->N;
+    st->rhs = ap_upload(c, rhs, R);
+    st->lin = ap_upload(c, lin, N);
+    st->l = ap_upload(c, l, N);
+    st->u = ap_upload(c, u, N);
+    st->comp_x = ap_upload(c, comp_x, (size_t)ncomp);
+    st->comp_y = ap_upload(c, comp_y, (size_t)ncomp);
+    st->comp_x0 = ap_upload(c, comp_x0, (size_t)ncomp);
+    st->comp_flip = ap_upload(c, comp_flipped, (size_t)ncomp);
+    st->scale = ap_upload<double>(c, nullptr, R);
+    st->beta = ap_upload<double>(c, nullptr, R);
+    st->nu = ap_upload<double>(c, nullptr, N);
+    st->x = ap_upload<double>(c, nullptr, N);
+    st->z = ap_upload<double>(c, nullptr, N);
+    st->y = ap_upload<double>(c, nullptr, N);
+    st->zp = ap_upload<double>(c, nullptr, N);
+    st->g = ap_upload<double>(c, nullptr, N);
+    st->t = ap_upload<double>(c, nullptr, R);
+    st->rs = ap_upload<double>(c, nullptr, R);
+    st->red = ap_upload<double>(c, nullptr, 8);
+    void* all[] = {st->rhs, st->lin, st->l, st->u, st->comp_x, st->comp_y, st->comp_x0, st->comp_flip, st->scale,
+                   st->beta, st->nu, st->x, st->z, st->y, st->zp, st->g, st->t, st->rs, st->red};
+    for (void* p : all)
+        if (!p) {
+            nes_approx* tmp = st;
+            nes_approx_free(&tmp, c);
+            return nullptr;
+        }
+    const MatrixBase* b = K->base;
+    approx_scale_kernel<<<(st->R + 255) / 256, 256, 0, c->stream>>>(st->R, b->d_rowptr, b->d_csr_val, st->rhs, scale,
+                                                                   st->scale, st->beta);
+    ++c->launches;
+    approx_nu_kernel<<<(st->N + 255) / 256, 256, 0, c->stream>>>(st->N, b->d_colptr, b->d_rowidx, b->d_values,
+                                                                st->scale, st->beta, st->nu);
+    ++c->launches;
+    if (cudaGetLastError() != cudaSuccess) {
+        fail(c, NES_ERR_CUDA, "nes_approx_create: kernel launch failed");
+        nes_approx* tmp = st;
+        nes_approx_free(&tmp, c);
+        return nullptr;
+    }
+    return st;
+}
+
+int nes_approx_free(nes_approx** pst, nes_ctx* c) {
+    if (!c) return 0;
+    if (!pst || !*pst) return 1;
+    nes_approx* st = *pst;
+    if (c->started) cudaSetDevice(c->device);
+    void* all[] = {st->rhs, st->lin, st->l, st->u, st->comp_x, st->comp_y, st->comp_x0, st->comp_flip, st->scale,
+                   st->beta, st->nu, st->x, st->z, st->y, st->zp, st->g, st->t, st->rs, st->red};
+    for (void* p : all) dev_free(c, p);
+    delete st;
+    *pst = nullptr;
+    return 1;
+}
+
+int nes_approx_value_gradient(nes_approx* st, const double* x, double* value, double* g, double* maxv, nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st || !x) return fail(c, NES_ERR_INVALID, "nes_approx_value_gradient: null argument");
+    NES_TRY(upload(c, st->y, x, (size_t)st->N * sizeof(double)));
+    NES_TRY(approx_value_gradient_dev(c, st, st->y));
+    double red[2];
+    NES_TRY(download(c, red, st->red, sizeof(red)));
+    if (value) *value = red[0];
+    if (maxv) *maxv = red[1];
+    if (g) NES_TRY(download(c, g, st->g, (size_t)st->N * sizeof(double)));
+    return 0;
+}
+
+int nes_approx_get(nes_approx* st, int which, double* out, nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st || !out) return fail(c, NES_ERR_INVALID, "nes_approx_get: null argument");
+    switch (which) {
+        case 'n': return download(c, out, st->nu, (size_t)st->N * sizeof(double));
+        case 's': return download(c, out, st->scale, (size_t)st->R * sizeof(double));
+        case 'z': return download(c, out, st->z, (size_t)st->N * sizeof(double));
+        case 'x': return download(c, out, st->x, (size_t)st->N * sizeof(double));
+        default: return fail(c, NES_ERR_INVALID, "nes_approx_get: bad selector");
+    }
+}
+
+// approx (approx.lisp:425-459).  stats[6] = {|g|_2, projected-gradient norm, max constraint value,
+// value + z0, last dot-diff, theta} of the last iteration.
+int nes_approx_solve(nes_approx* st, int n_iter, const double* x0, double* z_out, int* iters, int* restarts,
+                     double* stats, nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st) return fail(c, NES_ERR_INVALID, "nes_approx_solve: null state");
+    const int N = st->N;
+    const int nb = (N + 255) / 256;
+    if (x0) NES_TRY(upload(c, st->x, x0, (size_t)N * sizeof(double)));
+    else NES_CUDA(c, cudaMemsetAsync(st->x, 0, (size_t)N * sizeof(double), c->stream));
+    approx_project_kernel<<<nb, 256, 0, c->stream>>>(N, st->l, st->u, st->x, st->z);
+    NES_CHECK_LAUNCH(c);
+    double theta = 1.0;
+    int nrestart = 0, done_at = n_iter;
+    double red[8] = {0};
+    for (int i = 0; i < n_iter; ++i) {
+        approx_y_kernel<<<nb, 256, 0, c->stream>>>(N, theta, st->x, st->z, st->y);
+        NES_CHECK_LAUNCH(c);
+        NES_TRY(approx_value_gradient_dev(c, st, st->y));
+        approx_descent_kernel<<<nb, 256, 0, c->stream>>>(N, theta, st->y, st->z, st->nu, st->g, st->l, st->u, st->zp,
+                                                        st->x);
+        NES_CHECK_LAUNCH(c);
+        const double t2 = theta * theta;
+        theta = 0.5 * (sqrt(t2 * t2 + 4.0 * t2) - t2);
+        NES_TRY(approx_value_gradient_dev(c, st, st->zp));
+        approx_dot_kernel<<<1, AP_T, 0, c->stream>>>(N, st->g, st->z, st->zp, st->red);
+        NES_CHECK_LAUNCH(c);
+        NES_TRY(download(c, red, st->red, 4 * sizeof(double)));
+        const int restart = red[2] > 0.0;
+        if (restart) {
+            ++nrestart;
+            theta = 1.0;
+        }
+        approx_apply_kernel<<<1, AP_T, 0, c->stream>>>(N, restart, st->g, st->zp, st->l, st->u, st->z, st->x, st->red);
+        NES_CHECK_LAUNCH(c);
+        NES_TRY(download(c, red + 4, st->red + 4, sizeof(double)));
+        if (red[4] < 1e-10) {
+            done_at = i + 1;
+            break;
+        }
+    }
+    if (iters) *iters = done_at;
+    if (restarts) *restarts = nrestart;
+    if (stats) {
+        stats[0] = red[3];
+        stats[1] = red[4];
+        stats[2] = red[1];
+        stats[3] = red[0] + st->z0;
+        stats[4] = red[2];
+        stats[5] = theta;
+    }
+    if (z_out) NES_TRY(download(c, z_out, st->z, (size_t)N * sizeof(double)));
+    return 0;
+}
+
+}  // extern "C"

@@ -235,6 +235,28 @@ int nes_comm_nranks(const nes_ctx* c);
  * and fills up to `cap` (tile row, tile column) pairs. */
 int nes_dist_plan(int m, int nranks, int rank, int* tile_rows, int* tile_cols, int cap);
 
+/* ---- first-order solver of approx.lisp (APPROX on the penalised primal-dual LP) ---------------------
+ * K: sparse matrix with one row per `quadratic` constraint (approx.lisp:36-58, built by make-approx
+ * :195-299) over the stacked variables [x | y | z | w]; rhs per row, lin / l / u per variable;
+ * complementarity constraints (:85-95) as parallel arrays (x index, y index, x0, flipped).  `scale` != 0
+ * applies scale-quadratic (:70-74).  The handle borrows K (free it after the handle). */
+typedef struct nes_approx nes_approx;
+nes_approx* nes_approx_create(nes_matrix* K, const double* rhs, const double* lin, const double* l,
+                              const double* u, const int* comp_x, const int* comp_y, const double* comp_x0,
+                              const int* comp_flipped, int ncomp, int scale, double z0, nes_ctx* c);
+int nes_approx_free(nes_approx** st, nes_ctx* c);
+/* value-&-gradient (approx.lisp:338-351) at a host vector x: sum of constraint values, gradient (may be
+ * NULL), max |constraint value| */
+int nes_approx_value_gradient(nes_approx* st, const double* x, double* value, double* g, double* maxv,
+                              nes_ctx* c);
+/* which: 'n' nu (accumulate-nu, :97-113), 's' row scales, 'z' / 'x' current iterates */
+int nes_approx_get(nes_approx* st, int which, double* out, nes_ctx* c);
+/* approx (approx.lisp:425-459): up to n_iter iterations from x0 (NULL = 0, projected on the bounds);
+ * stops when the projected-gradient norm drops below 1e-10.  stats[6] = {|g|, projected gradient,
+ * max constraint value, value + z0, last g.(zp - z), theta}. */
+int nes_approx_solve(nes_approx* st, int n_iter, const double* x0, double* z_out, int* iters, int* restarts,
+                     double* stats, nes_ctx* c);
+
 /* ---- symbolic analysis on its own (host only, no device needed) ---------------------------------
  * What nes_analyze computes for a sparse A before anything touches the GPU: the fill-reducing
  * ordering (nested dissection + reverse Cuthill-McKee leaves), supernodes, assembly-tree levels, index
