@@ -33,7 +33,8 @@ class ApproxState:
 
     @property
     def scale(self):
-        return self._get("s", len(self.rhs))
+        """Scales of the quadratics in constraint order (the gap row, kept dense, is last)."""
+        return np.concatenate([self._get("s", len(self.rhs)), self._get("d", 2)[:1]])
 
     def free(self):
         com = cholmod_common()
@@ -110,15 +111,19 @@ def make_approx(sf, complementarity=False, scale=True, l1_penalty=0.0):
     rows, cols, vals = np.asarray(rows), np.asarray(cols), np.asarray(vals, dtype=np.float64)
     keep = vals != 0                           # make-quadratic drops zero coefficients (:47)
     rows, cols, vals = rows[keep], cols[keep], vals[keep]
-    # quadratics in constraint order: non-empty primal rows, all dual rows, the gap row
-    present = np.zeros(n + 1, dtype=bool)
+    # the duality-gap quadratic touches every variable: it travels as a dense coefficient vector
+    isgap = rows == gap
+    gap_row = np.zeros(n)
+    np.add.at(gap_row, cols[isgap], vals[isgap])
+    rows, cols, vals = rows[~isgap], cols[~isgap], vals[~isgap]
+    # remaining quadratics in constraint order: non-empty primal rows, then all dual rows
+    present = np.zeros(n, dtype=bool)
     present[:ncons] = has_pairs
     present[ncons: ncons + nvars] = True
-    present[gap] = True
     newrow = np.cumsum(present) - 1
     R = int(present.sum())
     K = nes.Matrix.from_triplets(com, newrow[rows].astype(np.int32), cols.astype(np.int32), vals, R, n)
-    rhs_c = np.ascontiguousarray(rhs[present])
+    rhs_c = np.ascontiguousarray(rhs[:n][present])
     cx = np.array([c_[0] for c_ in comp], dtype=np.int32)
     cy = np.array([c_[1] for c_ in comp], dtype=np.int32)
     cx0 = np.array([c_[2] for c_ in comp], dtype=np.float64)
@@ -127,7 +132,7 @@ def make_approx(sf, complementarity=False, scale=True, l1_penalty=0.0):
     h = com.lib.nes_approx_create(K.ptr, rhs_c.ctypes.data_as(nes._dp), lin.ctypes.data_as(nes._dp),
                                   l.ctypes.data_as(nes._dp), u.ctypes.data_as(nes._dp), ptr(cx, nes._ip),
                                   ptr(cy, nes._ip), ptr(cx0, nes._dp), ptr(cf, nes._ip), len(comp),
-                                  1 if scale else 0, 0.0, com.ptr)
+                                  gap_row.ctypes.data_as(nes._dp), 0.0, 1 if scale else 0, 0.0, com.ptr)
     if not h:
         K.free()
         raise nes.NesError(f"nes_approx_create failed: {com.error()}")

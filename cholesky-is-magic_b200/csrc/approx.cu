@@ -9,8 +9,8 @@
 //   accumulate-nu (:97-113)         approx_nu_kernel
 //   violation, %value-&-gradient    approx_resid_kernel + SpMVs + approx_comp_kernel
 //   solve-coordinate, approx-iteration (:353-398)   approx_y_kernel, approx_descent_kernel
-//   restart test, project-gradient (:400-423, :441-449)   approx_reduce_kernel, approx_apply_kernel
-// Reductions run in one CTA in a fixed order: results are bitwise reproducible.
+//   restart test, project-gradient (:400-423, :441-449)   approx_dot_kernel, approx_apply_kernel
+// Reductions are two-stage (per-CTA partials, combined by one thread in block order): bitwise reproducible.
 #include "nes_internal.h"
 
 struct nes_approx {
@@ -20,14 +20,19 @@ struct nes_approx {
     double *rhs = nullptr, *scale = nullptr, *beta = nullptr, *lin = nullptr, *nu = nullptr, *l = nullptr, *u = nullptr;
     int *comp_x = nullptr, *comp_y = nullptr, *comp_flip = nullptr;
     double* comp_x0 = nullptr;
+    // one dense quadratic kept out of K (the duality-gap row of make-approx touches every variable; a
+    // thread-per-row SpMV would serialise on it): coefficients, rhs; dense[N] = scale, dense[N+1] = beta
+    double* dense = nullptr;
+    double dense_rhs = 0.0;
+    int has_dense = 0;
     // iteration state
     double *x = nullptr, *z = nullptr, *y = nullptr, *zp = nullptr, *g = nullptr, *t = nullptr, *rs = nullptr;
     double* red = nullptr;  // 8 scalars
+    double *partr = nullptr, *partn = nullptr;  // per-CTA partials of the row / variable reductions
 };
 
 namespace nes {
 
-constexpr int AP_T = 1024;
 
 __global__ void approx_scale_kernel(int R, const int* __restrict__ rowptr, const double* __restrict__ val,
                                     const double* __restrict__ rhs, int do_scale, double* __restrict__ scale,
@@ -44,10 +49,15 @@ __global__ void approx_scale_kernel(int R, const int* __restrict__ rowptr, const
 
 __global__ void approx_nu_kernel(int N, const int* __restrict__ colptr, const int* __restrict__ rowidx,
                                  const double* __restrict__ val, const double* __restrict__ scale,
-                                 const double* __restrict__ beta, double* __restrict__ nu) {
+                                 const double* __restrict__ beta, const double* __restrict__ dense,
+                                 double* __restrict__ nu) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
     double acc = 0.0;
+    if (dense) {
+        const double cs = dense[j] * dense[N];
+        acc = dense[N + 1] * cs * cs;
+    }
     for (int k = colptr[j]; k < colptr[j + 1]; ++k) {
         const int r = rowidx[k];
         const double cs = val[k] * scale[r];
@@ -56,94 +66,154 @@ __global__ void approx_nu_kernel(int N, const int* __restrict__ colptr, const in
     nu[j] = acc;
 }
 
-// viol_r = (t_r - rhs_r) scale_r; rs_r = scale_r viol_r (the factor of the gradient K' rs)
-__global__ void approx_resid_kernel(int R, const double* __restrict__ t, const double* __restrict__ rhs,
-                                    const double* __restrict__ scale, double* __restrict__ rs) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= R) return;
-    const double v = (t[r] - rhs[r]) * scale[r];
-    rs[r] = scale[r] * v;
-}
-
-// complementarity constraints of one orientation (each x_i and each y_i appears at most once per
-// orientation, so plain read-modify-writes do not collide)
-__global__ void approx_comp_kernel(int ncomp, const int* __restrict__ cx, const int* __restrict__ cy,
-                                   const double* __restrict__ cx0, const int* __restrict__ flip, int want_flip,
-                                   const double* __restrict__ v, double* __restrict__ g) {
-    const int k = blockIdx.x * blockDim.x + threadIdx.x;
-    if (k >= ncomp || flip[k] != want_flip) return;
-    double xk = v[cx[k]] - cx0[k];
-    double yk = v[cy[k]];
-    if (want_flip) xk = -xk;
-    xk = xk < 0.0 ? 0.0 : xk;
-    yk = yk < 0.0 ? 0.0 : yk;
-    g[cx[k]] += want_flip ? -yk : yk;
-    g[cy[k]] += xk;
-}
-
-__device__ __forceinline__ double block_sum(double v, double* sh) {
-    const int tid = threadIdx.x;
+// scale-quadratic and beta of the dense row: dense[N] = scale, dense[N+1] = number of non-zero coefficients
+__global__ void __launch_bounds__(1024)
+approx_dense_scale_kernel(int N, double* __restrict__ dense, double rhs, int do_scale) {
+    __shared__ double sh[1024];
+    __shared__ double shc[1024];
+    double a = 0.0, cnt = 0.0;
+    for (int j = threadIdx.x; j < N; j += 1024) {
+        a = fma(dense[j], dense[j], a);
+        cnt += dense[j] != 0.0 ? 1.0 : 0.0;
+    }
+    sh[threadIdx.x] = a;
+    shc[threadIdx.x] = cnt;
     __syncthreads();
-    sh[tid] = v;
-    __syncthreads();
-    for (int o = AP_T / 2; o > 0; o >>= 1) {
-        if (tid < o) sh[tid] += sh[tid + o];
+    for (int o = 512; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) {
+            sh[threadIdx.x] += sh[threadIdx.x + o];
+            shc[threadIdx.x] += shc[threadIdx.x + o];
+        }
         __syncthreads();
     }
-    return sh[0];
-}
-__device__ __forceinline__ double block_max(double v, double* sh) {
-    const int tid = threadIdx.x;
-    __syncthreads();
-    sh[tid] = v;
-    __syncthreads();
-    for (int o = AP_T / 2; o > 0; o >>= 1) {
-        if (tid < o) sh[tid] = fmax(sh[tid], sh[tid + o]);
-        __syncthreads();
+    if (threadIdx.x == 0) {
+        const double norm = sqrt(sh[0] + rhs * rhs);
+        dense[N] = (do_scale && norm > 1e-6) ? 1.0 / norm : 1.0;
+        dense[N + 1] = shc[0];
     }
-    return sh[0];
 }
 
-// value-&-gradient scalars (approx.lisp:338-351) of the point v whose residuals are in t:
-// red[0] = sum of constraint values, red[1] = max |constraint value|
-__global__ void __launch_bounds__(AP_T)
-approx_value_kernel(int R, int N, int ncomp, const double* __restrict__ t, const double* __restrict__ rhs,
-                    const double* __restrict__ scale, const double* __restrict__ lin,
-                    const int* __restrict__ cx, const int* __restrict__ cy, const double* __restrict__ cx0,
-                    const int* __restrict__ flip, const double* __restrict__ v, double* __restrict__ red) {
-    __shared__ double sh[AP_T];
-    const int tid = threadIdx.x;
+// ---- two-stage reductions: every CTA leaves up to 4 partial values in part[blockIdx.x][0..3], a single
+// small CTA combines them in block order (fixed order => bitwise reproducible, no atomics)
+constexpr int AP_B = 256;       // threads of the stage-1 kernels
+constexpr int AP_MAXG = 1184;   // at most 8 CTAs per SM worth of partials
+
+__device__ __forceinline__ double cta_sum(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < AP_B / 32; ++w) r += sh[w];
+    return r;  // valid in thread 0
+}
+__device__ __forceinline__ double cta_max(double v, double* sh) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (threadIdx.x == 0)
+        for (int w = 0; w < AP_B / 32; ++w) r = fmax(r, sh[w]);
+    return r;
+}
+
+// rows: viol_r = (t_r - rhs_r) scale_r; rs_r = scale_r viol_r (factor of the gradient K' rs);
+// partials: [0] sum 1/2 viol^2, [1] max 1/2 viol^2
+__global__ void __launch_bounds__(AP_B)
+approx_resid_kernel(int R, const double* __restrict__ t, const double* __restrict__ rhs,
+                    const double* __restrict__ scale, double* __restrict__ rs, double* __restrict__ part) {
+    __shared__ double sh[AP_B / 32];
     double sum = 0.0, mx = 0.0;
-    for (int r = tid; r < R; r += AP_T) {
-        const double vi = (t[r] - rhs[r]) * scale[r];
-        const double val = 0.5 * vi * vi;
+    for (int r = blockIdx.x * AP_B + threadIdx.x; r < R; r += gridDim.x * AP_B) {
+        const double v = (t[r] - rhs[r]) * scale[r];
+        rs[r] = scale[r] * v;
+        const double val = 0.5 * v * v;
         sum += val;
         mx = fmax(mx, val);
     }
-    double lsum = 0.0;
-    for (int j = tid; j < N; j += AP_T) lsum = fma(lin[j], v[j], lsum);
-    for (int k = tid; k < ncomp; k += AP_T) {
+    const double s = cta_sum(sum, sh);
+    const double m = cta_max(mx, sh);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x * 4 + 0] = s;
+        part[blockIdx.x * 4 + 1] = m;
+    }
+}
+
+// variables: partials [0] lin . v, [1] dense . v, [2] sum of complementarity values, [3] their max
+__global__ void __launch_bounds__(AP_B)
+approx_ndot_kernel(int N, int ncomp, const double* __restrict__ lin, const double* __restrict__ dense,
+                   const int* __restrict__ cx, const int* __restrict__ cy, const double* __restrict__ cx0,
+                   const int* __restrict__ flip, const double* __restrict__ v, double* __restrict__ part) {
+    __shared__ double sh[AP_B / 32];
+    double ls = 0.0, ds = 0.0, cs = 0.0, cm = 0.0;
+    for (int j = blockIdx.x * AP_B + threadIdx.x; j < N; j += gridDim.x * AP_B) {
+        const double vj = v[j];
+        ls = fma(lin[j], vj, ls);
+        if (dense) ds = fma(dense[j], vj, ds);
+    }
+    for (int k = blockIdx.x * AP_B + threadIdx.x; k < ncomp; k += gridDim.x * AP_B) {
         double xk = v[cx[k]] - cx0[k];
         double yk = v[cy[k]];
         if (flip[k]) xk = -xk;
         xk = xk < 0.0 ? 0.0 : xk;
         yk = yk < 0.0 ? 0.0 : yk;
         const double val = yk * xk;
-        sum += val;
-        mx = fmax(mx, fabs(val));
+        cs += val;
+        cm = fmax(cm, fabs(val));
     }
-    const double lin_total = block_sum(lsum, sh);
-    const double total = block_sum(sum, sh);
-    const double m = block_max(mx, sh);
-    if (tid == 0) {
-        red[0] = total + lin_total;
-        red[1] = fmax(m, fabs(lin_total));
+    const double a = cta_sum(ls, sh), b2 = cta_sum(ds, sh), c2 = cta_sum(cs, sh), d2 = cta_max(cm, sh);
+    if (threadIdx.x == 0) {
+        part[blockIdx.x * 4 + 0] = a;
+        part[blockIdx.x * 4 + 1] = b2;
+        part[blockIdx.x * 4 + 2] = c2;
+        part[blockIdx.x * 4 + 3] = d2;
     }
 }
 
-__global__ void approx_addlin_kernel(int N, const double* __restrict__ lin, double* __restrict__ g) {
+// value-&-gradient scalars (approx.lisp:338-351): red[0] = sum of constraint values, red[1] = max |value|,
+// red[5] = scale^2 * (dense . v - rhs) (multiplies the dense row in the gradient)
+__global__ void __launch_bounds__(AP_B)
+approx_value_finish_kernel(int gr, const double* __restrict__ partr, int gn, const double* __restrict__ partn,
+                           const double* __restrict__ dense, int N, double dense_rhs, double* __restrict__ red) {
+    __shared__ double sh[AP_B / 32];
+    double qs = 0.0, qm = 0.0, ls = 0.0, ds = 0.0, cs = 0.0, cm = 0.0;
+    for (int b = threadIdx.x; b < gr; b += AP_B) {
+        qs += partr[b * 4 + 0];
+        qm = fmax(qm, partr[b * 4 + 1]);
+    }
+    for (int b = threadIdx.x; b < gn; b += AP_B) {
+        ls += partn[b * 4 + 0];
+        ds += partn[b * 4 + 1];
+        cs += partn[b * 4 + 2];
+        cm = fmax(cm, partn[b * 4 + 3]);
+    }
+    qs = cta_sum(qs, sh);
+    qm = cta_max(qm, sh);
+    ls = cta_sum(ls, sh);
+    ds = cta_sum(ds, sh);
+    cs = cta_sum(cs, sh);
+    cm = cta_max(cm, sh);
+    if (threadIdx.x != 0) return;
+    double tot = qs + cs + ls, mm = fmax(fmax(qm, cm), fabs(ls)), fac = 0.0;
+    if (dense) {
+        const double viol = (ds - dense_rhs) * dense[N];
+        tot += 0.5 * viol * viol;
+        mm = fmax(mm, 0.5 * viol * viol);
+        fac = dense[N] * viol;
+    }
+    red[0] = tot;
+    red[1] = mm;
+    red[5] = fac;
+}
+
+__global__ void approx_addlin_kernel(int N, const double* __restrict__ lin, const double* __restrict__ dense,
+                                     const double* __restrict__ red, double* __restrict__ g) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j < N) g[j] += lin[j];
+    if (j < N) g[j] += lin[j] + (dense ? dense[j] * red[5] : 0.0);
 }
 
 __global__ void approx_y_kernel(int N, double theta, const double* __restrict__ x, const double* __restrict__ z,
@@ -173,32 +243,32 @@ __global__ void approx_descent_kernel(int N, double theta, const double* __restr
     x[j] = y[j] + theta * (best - zj);
 }
 
-// red[2] = g . (zp - z) (dot-diff, :412-417), red[3] = |g|_2
-__global__ void __launch_bounds__(AP_T)
+// partials [0] g . (zp - z) (dot-diff, :412-417), [1] g . g
+__global__ void __launch_bounds__(AP_B)
 approx_dot_kernel(int N, const double* __restrict__ g, const double* __restrict__ z, const double* __restrict__ zp,
-                  double* __restrict__ red) {
-    __shared__ double sh[AP_T];
+                  double* __restrict__ part) {
+    __shared__ double sh[AP_B / 32];
     double d = 0.0, gg = 0.0;
-    for (int j = threadIdx.x; j < N; j += AP_T) {
+    for (int j = blockIdx.x * AP_B + threadIdx.x; j < N; j += gridDim.x * AP_B) {
         d = fma(g[j], zp[j] - z[j], d);
         gg = fma(g[j], g[j], gg);
     }
-    const double ds = block_sum(d, sh);
-    const double gs = block_sum(gg, sh);
+    const double a = cta_sum(d, sh), b2 = cta_sum(gg, sh);
     if (threadIdx.x == 0) {
-        red[2] = ds;
-        red[3] = sqrt(gs);
+        part[blockIdx.x * 4 + 0] = a;
+        part[blockIdx.x * 4 + 1] = b2;
     }
 }
 
-// restart (x <- z) or accept (z <- zp) (:441-446), then red[4] = |z - clamp(z - g)|_2 (project-gradient)
-__global__ void __launch_bounds__(AP_T)
-approx_apply_kernel(int N, int restart, const double* __restrict__ g, const double* __restrict__ zp,
-                    const double* __restrict__ l, const double* __restrict__ u, double* __restrict__ z,
-                    double* __restrict__ x, double* __restrict__ red) {
-    __shared__ double sh[AP_T];
+// restart (x <- z) or accept (z <- zp) (:441-446); partial [0] of |z - clamp(z - g)|^2 (project-gradient)
+__global__ void __launch_bounds__(AP_B)
+approx_apply_kernel(int N, const double* __restrict__ red, const double* __restrict__ g,
+                    const double* __restrict__ zp, const double* __restrict__ l, const double* __restrict__ u,
+                    double* __restrict__ z, double* __restrict__ x, double* __restrict__ part) {
+    __shared__ double sh[AP_B / 32];
+    const bool restart = red[2] > 0.0;  // dot-diff of this iteration, decided on the device: one host sync less
     double acc = 0.0;
-    for (int j = threadIdx.x; j < N; j += AP_T) {
+    for (int j = blockIdx.x * AP_B + threadIdx.x; j < N; j += gridDim.x * AP_B) {
         double zj;
         if (restart) {
             zj = z[j];
@@ -213,8 +283,40 @@ approx_apply_kernel(int N, int restart, const double* __restrict__ g, const doub
         const double dd = zj - xp;
         acc = fma(dd, dd, acc);
     }
-    const double s = block_sum(acc, sh);
-    if (threadIdx.x == 0) red[4] = sqrt(s);
+    const double a = cta_sum(acc, sh);
+    if (threadIdx.x == 0) part[blockIdx.x * 4 + 0] = a;
+}
+
+// red[o0] = sum of partial 0 (sqrt if sq0), red[o1] = sqrt(sum of partial 1) when o1 >= 0 (one CTA, fixed tree)
+__global__ void __launch_bounds__(AP_B)
+approx_finish_kernel(int g, const double* __restrict__ part, int o0, int sq0, int o1, double* __restrict__ red) {
+    __shared__ double sh[AP_B / 32];
+    double a = 0.0, b = 0.0;
+    for (int k = threadIdx.x; k < g; k += AP_B) {
+        a += part[k * 4 + 0];
+        b += part[k * 4 + 1];
+    }
+    a = cta_sum(a, sh);
+    b = cta_sum(b, sh);
+    if (threadIdx.x != 0) return;
+    red[o0] = sq0 ? sqrt(a) : a;
+    if (o1 >= 0) red[o1] = sqrt(b);
+}
+
+// complementarity constraints of one orientation (each x_i and each y_i appears at most once per
+// orientation, so plain read-modify-writes do not collide)
+__global__ void approx_comp_kernel(int ncomp, const int* __restrict__ cx, const int* __restrict__ cy,
+                                   const double* __restrict__ cx0, const int* __restrict__ flip, int want_flip,
+                                   const double* __restrict__ v, double* __restrict__ g) {
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= ncomp || flip[k] != want_flip) return;
+    double xk = v[cx[k]] - cx0[k];
+    double yk = v[cy[k]];
+    if (want_flip) xk = -xk;
+    xk = xk < 0.0 ? 0.0 : xk;
+    yk = yk < 0.0 ? 0.0 : yk;
+    g[cx[k]] += want_flip ? -yk : yk;
+    g[cy[k]] += xk;
 }
 
 __global__ void approx_project_kernel(int N, const double* __restrict__ l, const double* __restrict__ u,
@@ -227,18 +329,32 @@ __global__ void approx_project_kernel(int N, const double* __restrict__ l, const
     z[j] = v;
 }
 
+static int ap_grid(nes_ctx* c, int n) {
+    int g = (n + AP_B - 1) / AP_B;
+    const int cap = c->num_sms * 4 < AP_MAXG ? c->num_sms * 4 : AP_MAXG;
+    return g < 1 ? 1 : (g > cap ? cap : g);
+}
+
 // g <- gradient at v, red[0..1] <- value, max
 static int approx_value_gradient_dev(nes_ctx* c, nes_approx* st, const double* d_v) {
     const MatrixBase* b = st->K->base;
+    const double* dense = st->has_dense ? st->dense : nullptr;
     NES_TRY(matvec_unscaled(c, b, 0, 1.0, d_v, 0.0, st->t));
-    StageTimer timer(c, NES_STAGE_VECTOR);
-    approx_resid_kernel<<<(st->R + 255) / 256, 256, 0, c->stream>>>(st->R, st->t, st->rhs, st->scale, st->rs);
-    NES_CHECK_LAUNCH(c);
-    approx_value_kernel<<<1, AP_T, 0, c->stream>>>(st->R, st->N, st->ncomp, st->t, st->rhs, st->scale, st->lin,
-                                                   st->comp_x, st->comp_y, st->comp_x0, st->comp_flip, d_v, st->red);
-    NES_CHECK_LAUNCH(c);
+    {
+        StageTimer timer(c, NES_STAGE_VECTOR);
+        const int gr = ap_grid(c, st->R), gn = ap_grid(c, st->N);
+        approx_resid_kernel<<<gr, AP_B, 0, c->stream>>>(st->R, st->t, st->rhs, st->scale, st->rs, st->partr);
+        NES_CHECK_LAUNCH(c);
+        approx_ndot_kernel<<<gn, AP_B, 0, c->stream>>>(st->N, st->ncomp, st->lin, dense, st->comp_x, st->comp_y,
+                                                      st->comp_x0, st->comp_flip, d_v, st->partn);
+        NES_CHECK_LAUNCH(c);
+        approx_value_finish_kernel<<<1, AP_B, 0, c->stream>>>(gr, st->partr, gn, st->partn, dense, st->N, st->dense_rhs,
+                                                           st->red);
+        NES_CHECK_LAUNCH(c);
+    }
     NES_TRY(matvec_unscaled(c, b, 1, 1.0, st->rs, 0.0, st->g));
-    approx_addlin_kernel<<<(st->N + 255) / 256, 256, 0, c->stream>>>(st->N, st->lin, st->g);
+    StageTimer timer(c, NES_STAGE_VECTOR);
+    approx_addlin_kernel<<<(st->N + 255) / 256, 256, 0, c->stream>>>(st->N, st->lin, dense, st->red, st->g);
     NES_CHECK_LAUNCH(c);
     if (st->ncomp > 0) {
         for (int flip = 0; flip < 2; ++flip) {
@@ -266,7 +382,8 @@ extern "C" {
 
 nes_approx* nes_approx_create(nes_matrix* K, const double* rhs, const double* lin, const double* l, const double* u,
                               const int* comp_x, const int* comp_y, const double* comp_x0, const int* comp_flipped,
-                              int ncomp, int scale, double z0, nes_ctx* c) {
+                              int ncomp, const double* dense_row, double dense_rhs, int scale, double z0,
+                              nes_ctx* c) {
     NES_ENTER_PTR(c);
     if (!K || !K->base || K->base->dense || !rhs || !lin || !l || !u || ncomp < 0) {
         fail(c, NES_ERR_INVALID, "nes_approx_create: needs a sparse constraint matrix and its vectors");
@@ -287,6 +404,9 @@ nes_approx* nes_approx_create(nes_matrix* K, const double* rhs, const double* li
     st->comp_y = ap_upload(c, comp_y, (size_t)ncomp);
     st->comp_x0 = ap_upload(c, comp_x0, (size_t)ncomp);
     st->comp_flip = ap_upload(c, comp_flipped, (size_t)ncomp);
+    st->has_dense = dense_row != nullptr;
+    st->dense_rhs = dense_rhs;
+    st->dense = ap_upload(c, dense_row, N);  // two extra slots hold its scale and beta
     st->scale = ap_upload<double>(c, nullptr, R);
     st->beta = ap_upload<double>(c, nullptr, R);
     st->nu = ap_upload<double>(c, nullptr, N);
@@ -298,8 +418,11 @@ nes_approx* nes_approx_create(nes_matrix* K, const double* rhs, const double* li
     st->t = ap_upload<double>(c, nullptr, R);
     st->rs = ap_upload<double>(c, nullptr, R);
     st->red = ap_upload<double>(c, nullptr, 8);
+    st->partr = ap_upload<double>(c, nullptr, (size_t)AP_MAXG * 4);
+    st->partn = ap_upload<double>(c, nullptr, (size_t)AP_MAXG * 4);
     void* all[] = {st->rhs, st->lin, st->l, st->u, st->comp_x, st->comp_y, st->comp_x0, st->comp_flip, st->scale,
-                   st->beta, st->nu, st->x, st->z, st->y, st->zp, st->g, st->t, st->rs, st->red};
+                   st->beta, st->nu, st->x, st->z, st->y, st->zp, st->g, st->t, st->rs, st->red, st->dense, st->partr,
+                   st->partn};
     for (void* p : all)
         if (!p) {
             nes_approx* tmp = st;
@@ -310,8 +433,13 @@ nes_approx* nes_approx_create(nes_matrix* K, const double* rhs, const double* li
     approx_scale_kernel<<<(st->R + 255) / 256, 256, 0, c->stream>>>(st->R, b->d_rowptr, b->d_csr_val, st->rhs, scale,
                                                                    st->scale, st->beta);
     ++c->launches;
+    if (st->has_dense) {
+        approx_dense_scale_kernel<<<1, 1024, 0, c->stream>>>(st->N, st->dense, dense_rhs, scale);
+        ++c->launches;
+    }
     approx_nu_kernel<<<(st->N + 255) / 256, 256, 0, c->stream>>>(st->N, b->d_colptr, b->d_rowidx, b->d_values,
-                                                                st->scale, st->beta, st->nu);
+                                                                st->scale, st->beta,
+                                                                st->has_dense ? st->dense : nullptr, st->nu);
     ++c->launches;
     if (cudaGetLastError() != cudaSuccess) {
         fail(c, NES_ERR_CUDA, "nes_approx_create: kernel launch failed");
@@ -328,7 +456,8 @@ int nes_approx_free(nes_approx** pst, nes_ctx* c) {
     nes_approx* st = *pst;
     if (c->started) cudaSetDevice(c->device);
     void* all[] = {st->rhs, st->lin, st->l, st->u, st->comp_x, st->comp_y, st->comp_x0, st->comp_flip, st->scale,
-                   st->beta, st->nu, st->x, st->z, st->y, st->zp, st->g, st->t, st->rs, st->red};
+                   st->beta, st->nu, st->x, st->z, st->y, st->zp, st->g, st->t, st->rs, st->red, st->dense, st->partr,
+                   st->partn};
     for (void* p : all) dev_free(c, p);
     delete st;
     *pst = nullptr;
@@ -354,6 +483,8 @@ int nes_approx_get(nes_approx* st, int which, double* out, nes_ctx* c) {
     switch (which) {
         case 'n': return download(c, out, st->nu, (size_t)st->N * sizeof(double));
         case 's': return download(c, out, st->scale, (size_t)st->R * sizeof(double));
+        case 'd': return st->has_dense ? download(c, out, st->dense + st->N, 2 * sizeof(double))
+                                       : fail(c, NES_ERR_INVALID, "nes_approx_get: no dense row");
         case 'z': return download(c, out, st->z, (size_t)st->N * sizeof(double));
         case 'x': return download(c, out, st->x, (size_t)st->N * sizeof(double));
         default: return fail(c, NES_ERR_INVALID, "nes_approx_get: bad selector");
@@ -385,17 +516,21 @@ int nes_approx_solve(nes_approx* st, int n_iter, const double* x0, double* z_out
         const double t2 = theta * theta;
         theta = 0.5 * (sqrt(t2 * t2 + 4.0 * t2) - t2);
         NES_TRY(approx_value_gradient_dev(c, st, st->zp));
-        approx_dot_kernel<<<1, AP_T, 0, c->stream>>>(N, st->g, st->z, st->zp, st->red);
+        const int gn = ap_grid(c, N);
+        approx_dot_kernel<<<gn, AP_B, 0, c->stream>>>(N, st->g, st->z, st->zp, st->partn);
         NES_CHECK_LAUNCH(c);
-        NES_TRY(download(c, red, st->red, 4 * sizeof(double)));
-        const int restart = red[2] > 0.0;
-        if (restart) {
+        approx_finish_kernel<<<1, AP_B, 0, c->stream>>>(gn, st->partn, 2, 0, 3, st->red);
+        NES_CHECK_LAUNCH(c);
+        approx_apply_kernel<<<gn, AP_B, 0, c->stream>>>(N, st->red, st->g, st->zp, st->l, st->u, st->z, st->x,
+                                                        st->partn);
+        NES_CHECK_LAUNCH(c);
+        approx_finish_kernel<<<1, AP_B, 0, c->stream>>>(gn, st->partn, 4, 1, -1, st->red);
+        NES_CHECK_LAUNCH(c);
+        NES_TRY(download(c, red, st->red, 5 * sizeof(double)));  // the iteration's only host sync
+        if (red[2] > 0.0) {
             ++nrestart;
             theta = 1.0;
         }
-        approx_apply_kernel<<<1, AP_T, 0, c->stream>>>(N, restart, st->g, st->zp, st->l, st->u, st->z, st->x, st->red);
-        NES_CHECK_LAUNCH(c);
-        NES_TRY(download(c, red + 4, st->red + 4, sizeof(double)));
         if (red[4] < 1e-10) {
             done_at = i + 1;
             break;

@@ -4,8 +4,8 @@
 // (dense: 8mn bytes per product) and atomic-free, so results are bitwise reproducible.
 //   dense  N : row-pair per thread (16B loads), columns split across CTAs, partials + fixed-order sum
 //   dense  T : one warp per column pair, 16B loads along the column, shuffle reduction
-//   CSC    N : row gather over the CSR mirror (thread per row)
-//   CSC    T : column gather (thread per column)
+//   CSC    N : row gather over the CSR mirror (1-8 lanes per row, fixed shuffle tree)
+//   CSC    T : column gather (1-8 lanes per column)
 // The column scale s of nes_scale is folded in: N uses x_k*s_k, T multiplies the result by s_j.
 #include "nes_internal.h"
 
@@ -95,32 +95,6 @@ gemv_t_kernel(const double* __restrict__ A, size_t ld, int m, int n, const doubl
     }
 }
 
-__global__ void spmv_csr_kernel(const int* __restrict__ rowptr, const int* __restrict__ colidx,
-                                const double* __restrict__ val, int m, const double* __restrict__ x,
-                                const double* __restrict__ s, double alpha, double beta,
-                                double* __restrict__ y) {
-    const int r = blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= m) return;
-    double acc = 0.0;
-    for (int k = rowptr[r]; k < rowptr[r + 1]; ++k) {
-        const int j = colidx[k];
-        acc = fma(val[k], s ? x[j] * s[j] : x[j], acc);
-    }
-    y[r] = (beta == 0.0) ? alpha * acc : fma(alpha, acc, beta * y[r]);
-}
-
-__global__ void spmv_csc_t_kernel(const int* __restrict__ colptr, const int* __restrict__ rowidx,
-                                  const double* __restrict__ val, int n, const double* __restrict__ x,
-                                  const double* __restrict__ s, double alpha, double beta,
-                                  double* __restrict__ y) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    double acc = 0.0;
-    for (int k = colptr[j]; k < colptr[j + 1]; ++k) acc = fma(val[k], x[rowidx[k]], acc);
-    if (s) acc *= s[j];
-    y[j] = (beta == 0.0) ? alpha * acc : fma(alpha, acc, beta * y[j]);
-}
-
 __global__ void axpby_kernel(int n, double alpha, const double* __restrict__ t, double beta,
                              double* __restrict__ y) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -133,6 +107,51 @@ int dist_allreduce_sum(nes_ctx* c, double* d_buf, size_t count);  // nes_dist.cu
 // of columns -- 1/Q of the HBM traffic -- and one all-reduce of the m-vector (forward) or of the
 // zero-padded n-vector (transposed) completes the product; NCCL's all-reduce returns bit-identical
 // results on every rank, so the replicated control flow of the IPM stays in lockstep.
+// Sub-warp CSR / CSC gathers: LANES threads share one row (column), reading consecutive entries (coalesced
+// index + value segments), and combine with a fixed shuffle tree -- deterministic, and 2-3x the bandwidth of
+// one thread per row once rows hold more than a few entries.
+template <int LANES>
+__global__ void __launch_bounds__(256)
+spmv_gather_kernel(const int* __restrict__ ptr, const int* __restrict__ idx, const double* __restrict__ val,
+                   int nrows, const double* __restrict__ x, const double* __restrict__ s_in,
+                   const double* __restrict__ s_out, double alpha, double beta, double* __restrict__ y) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    const int r = t / LANES, lane = t % LANES;
+    double acc = 0.0;
+    if (r < nrows) {
+        const int e = ptr[r + 1];
+        for (int k = ptr[r] + lane; k < e; k += LANES) {
+            const int j = idx[k];
+            acc = fma(val[k], s_in ? x[j] * s_in[j] : x[j], acc);
+        }
+    }
+#pragma unroll
+    for (int o = LANES / 2; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o, LANES);
+    if (r < nrows && lane == 0) {
+        if (s_out) acc *= s_out[r];
+        y[r] = (beta == 0.0) ? alpha * acc : fma(alpha, acc, beta * y[r]);
+    }
+}
+
+template <int LANES>
+static void spmv_gather_launch(cudaStream_t st, const int* ptr, const int* idx, const double* val, int nrows,
+                               const double* x, const double* s_in, const double* s_out, double alpha, double beta,
+                               double* y) {
+    const long long threads = (long long)nrows * LANES;
+    spmv_gather_kernel<LANES><<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ptr, idx, val, nrows, x, s_in, s_out,
+                                                                               alpha, beta, y);
+}
+
+static void spmv_gather(cudaStream_t st, const int* ptr, const int* idx, const double* val, int nrows, size_t nnz,
+                        const double* x, const double* s_in, const double* s_out, double alpha, double beta,
+                        double* y) {
+    const double avg = nrows > 0 ? (double)nnz / nrows : 0.0;
+    if (avg >= 12.0) spmv_gather_launch<8>(st, ptr, idx, val, nrows, x, s_in, s_out, alpha, beta, y);
+    else if (avg >= 5.0) spmv_gather_launch<4>(st, ptr, idx, val, nrows, x, s_in, s_out, alpha, beta, y);
+    else if (avg >= 2.5) spmv_gather_launch<2>(st, ptr, idx, val, nrows, x, s_in, s_out, alpha, beta, y);
+    else spmv_gather_launch<1>(st, ptr, idx, val, nrows, x, s_in, s_out, alpha, beta, y);
+}
+
 static int matvec_dense_split(nes_ctx* c, const MatrixBase* b, const double* d_s, int transpose, double alpha,
                               const double* d_x, double beta, double* d_y) {
     const int m = (int)b->m, n = (int)b->n, Q = c->nranks, r = c->rank;
@@ -206,15 +225,13 @@ static int matvec_impl(nes_ctx* c, const MatrixBase* b, const double* d_s, int t
             NES_CHECK_LAUNCH(c);
         }
     } else {
-        if (!transpose) {
-            spmv_csr_kernel<<<(m + 127) / 128, 128, 0, c->stream>>>(b->d_rowptr, b->d_colidx,
-                                                                    b->d_csr_val, m, d_x, d_s, alpha,
-                                                                    beta, d_y);
+        if (!transpose) {  // rows of the CSR mirror; the column scale multiplies x
+            spmv_gather(c->stream, b->d_rowptr, b->d_colidx, b->d_csr_val, m, b->nnz, d_x, d_s, nullptr, alpha,
+                        beta, d_y);
             NES_CHECK_LAUNCH(c);
-        } else {
-            spmv_csc_t_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(b->d_colptr, b->d_rowidx,
-                                                                      b->d_values, n, d_x, d_s, alpha,
-                                                                      beta, d_y);
+        } else {           // columns of the CSC arrays; the column scale multiplies the result
+            spmv_gather(c->stream, b->d_colptr, b->d_rowidx, b->d_values, n, b->nnz, d_x, nullptr, d_s, alpha,
+                        beta, d_y);
             NES_CHECK_LAUNCH(c);
         }
     }

@@ -122,7 +122,8 @@ def _prototypes(lib):
     fn("nes_dist_plan", C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int)
     fn("nes_mark_begin", C.c_int, _vp)
     fn("nes_mark_end", C.c_int, _vp, _dp)
-    fn("nes_approx_create", _vp, _vp, _dp, _dp, _dp, _dp, _ip, _ip, _dp, _ip, C.c_int, C.c_int, C.c_double, _vp)
+    fn("nes_approx_create", _vp, _vp, _dp, _dp, _dp, _dp, _ip, _ip, _dp, _ip, C.c_int, _dp, C.c_double, C.c_int,
+       C.c_double, _vp)
     fn("nes_approx_free", C.c_int, _vpp, _vp)
     fn("nes_approx_value_gradient", C.c_int, _vp, _dp, _dp, _dp, _dp, _vp)
     fn("nes_approx_get", C.c_int, _vp, C.c_int, _dp, _vp)

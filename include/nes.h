@@ -239,17 +239,21 @@ int nes_dist_plan(int m, int nranks, int rank, int* tile_rows, int* tile_cols, i
  * K: sparse matrix with one row per `quadratic` constraint (approx.lisp:36-58, built by make-approx
  * :195-299) over the stacked variables [x | y | z | w]; rhs per row, lin / l / u per variable;
  * complementarity constraints (:85-95) as parallel arrays (x index, y index, x0, flipped).  `scale` != 0
- * applies scale-quadratic (:70-74).  The handle borrows K (free it after the handle). */
+ * applies scale-quadratic (:70-74).  One quadratic may be passed as a dense coefficient vector instead of a
+ * row of K (dense_row, dense_rhs; NULL = none): make-approx's duality-gap row touches every variable.
+ * The handle borrows K (free it after the handle). */
 typedef struct nes_approx nes_approx;
 nes_approx* nes_approx_create(nes_matrix* K, const double* rhs, const double* lin, const double* l,
                               const double* u, const int* comp_x, const int* comp_y, const double* comp_x0,
-                              const int* comp_flipped, int ncomp, int scale, double z0, nes_ctx* c);
+                              const int* comp_flipped, int ncomp, const double* dense_row, double dense_rhs,
+                              int scale, double z0, nes_ctx* c);
 int nes_approx_free(nes_approx** st, nes_ctx* c);
 /* value-&-gradient (approx.lisp:338-351) at a host vector x: sum of constraint values, gradient (may be
  * NULL), max |constraint value| */
 int nes_approx_value_gradient(nes_approx* st, const double* x, double* value, double* g, double* maxv,
                               nes_ctx* c);
-/* which: 'n' nu (accumulate-nu, :97-113), 's' row scales, 'z' / 'x' current iterates */
+/* which: 'n' nu (accumulate-nu, :97-113), 's' row scales, 'd' {scale, beta} of the dense row,
+ * 'z' / 'x' current iterates */
 int nes_approx_get(nes_approx* st, int which, double* out, nes_ctx* c);
 /* approx (approx.lisp:425-459): up to n_iter iterations from x0 (NULL = 0, projected on the bounds);
  * stops when the projected-gradient norm drops below 1e-10.  stats[6] = {|g|, projected gradient,
