@@ -157,7 +157,7 @@ def approx(state, n, x=None):
     com = cholmod_common()
     z = np.empty(state.nvars)
     it, rs = C.c_int(), C.c_int()
-    stats = np.zeros(6)
+    stats = np.zeros(7)
     x0 = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
     com.check(com.lib.nes_approx_solve(state.ptr, n, None if x0 is None else x0.ctypes.data_as(nes._dp),
                                        z.ctypes.data_as(nes._dp), C.byref(it), C.byref(rs),

@@ -29,6 +29,10 @@ struct nes_approx {
     double *x = nullptr, *z = nullptr, *y = nullptr, *zp = nullptr, *g = nullptr, *t = nullptr, *rs = nullptr;
     double* red = nullptr;  // 8 scalars
     double *partr = nullptr, *partn = nullptr;  // per-CTA partials of the row / variable reductions
+    // variant 0 = approx.lisp; 1 = alm-approx.lisp: step damped by 0.95 (:198-216), stop when i > 10 and
+    // |pg| < accuracy or at the last iteration (:328-333), the max ignores the linear term (:188-190)
+    int variant = 0;
+    double accuracy = 1e-10;
 };
 
 namespace nes {
@@ -178,7 +182,8 @@ approx_ndot_kernel(int N, int ncomp, const double* __restrict__ lin, const doubl
 // red[5] = scale^2 * (dense . v - rhs) (multiplies the dense row in the gradient)
 __global__ void __launch_bounds__(AP_B)
 approx_value_finish_kernel(int gr, const double* __restrict__ partr, int gn, const double* __restrict__ partn,
-                           const double* __restrict__ dense, int N, double dense_rhs, double* __restrict__ red) {
+                           const double* __restrict__ dense, int N, double dense_rhs, int max_skips_linear,
+                           double* __restrict__ red) {
     __shared__ double sh[AP_B / 32];
     double qs = 0.0, qm = 0.0, ls = 0.0, ds = 0.0, cs = 0.0, cm = 0.0;
     for (int b = threadIdx.x; b < gr; b += AP_B) {
@@ -198,7 +203,8 @@ approx_value_finish_kernel(int gr, const double* __restrict__ partr, int gn, con
     cs = cta_sum(cs, sh);
     cm = cta_max(cm, sh);
     if (threadIdx.x != 0) return;
-    double tot = qs + cs + ls, mm = fmax(fmax(qm, cm), fabs(ls)), fac = 0.0;
+    double tot = qs + cs + ls, mm = fmax(qm, cm), fac = 0.0;
+    if (!max_skips_linear) mm = fmax(mm, fabs(ls));
     if (dense) {
         const double viol = (ds - dense_rhs) * dense[N];
         tot += 0.5 * viol * viol;
@@ -208,6 +214,7 @@ approx_value_finish_kernel(int gr, const double* __restrict__ partr, int gn, con
     red[0] = tot;
     red[1] = mm;
     red[5] = fac;
+    red[6] = ls;  // value of the linear constraint (dual-value of alm-approx.lisp:136-140 = z0 + this)
 }
 
 __global__ void approx_addlin_kernel(int N, const double* __restrict__ lin, const double* __restrict__ dense,
@@ -223,7 +230,8 @@ __global__ void approx_y_kernel(int N, double theta, const double* __restrict__ 
 }
 
 // zp = solve-coordinate (approx.lisp:353-369); x <- y + theta (zp - z) (approx-iteration :390-392)
-__global__ void approx_descent_kernel(int N, double theta, const double* __restrict__ y, const double* __restrict__ z,
+__global__ void approx_descent_kernel(int N, double theta, double damping, const double* __restrict__ y,
+                                      const double* __restrict__ z,
                                       const double* __restrict__ nu, const double* __restrict__ g,
                                       const double* __restrict__ l, const double* __restrict__ u,
                                       double* __restrict__ zp, double* __restrict__ x) {
@@ -235,7 +243,7 @@ __global__ void approx_descent_kernel(int N, double theta, const double* __restr
     if (step == 0.0) {
         best = gj < 0.0 ? u[j] : (gj > 0.0 ? l[j] : zj);
     } else {
-        best = zj - gj / step;
+        best = zj - damping * (gj / step);
         if (best < l[j]) best = l[j];
         else if (best > u[j]) best = u[j];
     }
@@ -319,6 +327,11 @@ __global__ void approx_comp_kernel(int ncomp, const int* __restrict__ cx, const 
     g[cy[k]] += xk;
 }
 
+__global__ void approx_fill_kernel(int n, double v, double* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = v;
+}
+
 __global__ void approx_project_kernel(int N, const double* __restrict__ l, const double* __restrict__ u,
                                       double* __restrict__ x, double* __restrict__ z) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
@@ -349,7 +362,7 @@ static int approx_value_gradient_dev(nes_ctx* c, nes_approx* st, const double* d
                                                       st->comp_x0, st->comp_flip, d_v, st->partn);
         NES_CHECK_LAUNCH(c);
         approx_value_finish_kernel<<<1, AP_B, 0, c->stream>>>(gr, st->partr, gn, st->partn, dense, st->N, st->dense_rhs,
-                                                           st->red);
+                                                             st->variant == 1, st->red);
         NES_CHECK_LAUNCH(c);
     }
     NES_TRY(matvec_unscaled(c, b, 1, 1.0, st->rs, 0.0, st->g));
@@ -491,8 +504,8 @@ int nes_approx_get(nes_approx* st, int which, double* out, nes_ctx* c) {
     }
 }
 
-// approx (approx.lisp:425-459).  stats[6] = {|g|_2, projected-gradient norm, max constraint value,
-// value + z0, last dot-diff, theta} of the last iteration.
+// approx (approx.lisp:425-459, alm-approx.lisp:307-346).  stats[7] = {|g|_2, projected-gradient norm, max
+// constraint value, value + z0, last dot-diff, theta, z0 + linear value} of the last iteration.
 int nes_approx_solve(nes_approx* st, int n_iter, const double* x0, double* z_out, int* iters, int* restarts,
                      double* stats, nes_ctx* c) {
     NES_ENTER(c);
@@ -506,15 +519,17 @@ int nes_approx_solve(nes_approx* st, int n_iter, const double* x0, double* z_out
     double theta = 1.0;
     int nrestart = 0, done_at = n_iter;
     double red[8] = {0};
+    double lin_value = 0.0;
     for (int i = 0; i < n_iter; ++i) {
         approx_y_kernel<<<nb, 256, 0, c->stream>>>(N, theta, st->x, st->z, st->y);
         NES_CHECK_LAUNCH(c);
         NES_TRY(approx_value_gradient_dev(c, st, st->y));
-        approx_descent_kernel<<<nb, 256, 0, c->stream>>>(N, theta, st->y, st->z, st->nu, st->g, st->l, st->u, st->zp,
-                                                        st->x);
+        approx_descent_kernel<<<nb, 256, 0, c->stream>>>(N, theta, st->variant == 1 ? 0.95 : 1.0, st->y, st->z, st->nu,
+                                                        st->g, st->l, st->u, st->zp, st->x);
         NES_CHECK_LAUNCH(c);
         const double t2 = theta * theta;
-        theta = 0.5 * (sqrt(t2 * t2 + 4.0 * t2) - t2);
+        theta = st->variant == 1 ? 0.5 * (sqrt((4.0 + t2) * t2) - t2)    // alm-approx.lisp:258-263
+                                 : 0.5 * (sqrt(t2 * t2 + 4.0 * t2) - t2);  // approx.lisp:393-396
         NES_TRY(approx_value_gradient_dev(c, st, st->zp));
         const int gn = ap_grid(c, N);
         approx_dot_kernel<<<gn, AP_B, 0, c->stream>>>(N, st->g, st->z, st->zp, st->partn);
@@ -526,12 +541,15 @@ int nes_approx_solve(nes_approx* st, int n_iter, const double* x0, double* z_out
         NES_CHECK_LAUNCH(c);
         approx_finish_kernel<<<1, AP_B, 0, c->stream>>>(gn, st->partn, 4, 1, -1, st->red);
         NES_CHECK_LAUNCH(c);
-        NES_TRY(download(c, red, st->red, 5 * sizeof(double)));  // the iteration's only host sync
+        NES_TRY(download(c, red, st->red, 7 * sizeof(double)));  // the iteration's only host sync
+        lin_value = red[6];
         if (red[2] > 0.0) {
             ++nrestart;
             theta = 1.0;
         }
-        if (red[4] < 1e-10) {
+        const bool done = st->variant == 1 ? ((i > 10 && red[4] < st->accuracy) || i == n_iter - 1)
+                                           : red[4] < 1e-10;
+        if (done) {
             done_at = i + 1;
             break;
         }
@@ -545,8 +563,35 @@ int nes_approx_solve(nes_approx* st, int n_iter, const double* x0, double* z_out
         stats[3] = red[0] + st->z0;
         stats[4] = red[2];
         stats[5] = theta;
+        stats[6] = st->z0 + lin_value;  // dual-value at the last zp (alm-approx.lisp:136-140, :340)
     }
     if (z_out) NES_TRY(download(c, z_out, st->z, (size_t)N * sizeof(double)));
+    return 0;
+}
+
+int nes_approx_set_variant(nes_approx* st, int variant, double accuracy, nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st || variant < 0 || variant > 1) return fail(c, NES_ERR_INVALID, "nes_approx_set_variant: bad argument");
+    st->variant = variant;
+    st->accuracy = accuracy;
+    return 0;
+}
+
+// make-alm-subproblem (alm-approx.lisp:355-403) over the same constraint rows: every quadratic gets the
+// scale sqrt(weight), the linear term becomes c + A' lambda (computed by the caller with nes_sdmult),
+// z0 = -lambda . b; nu is recomputed (accumulate-nu).
+int nes_approx_set_subproblem(nes_approx* st, double row_scale, const double* lin, double z0, nes_ctx* c) {
+    NES_ENTER(c);
+    if (!st || !lin) return fail(c, NES_ERR_INVALID, "nes_approx_set_subproblem: null argument");
+    const MatrixBase* b = st->K->base;
+    NES_TRY(upload(c, st->lin, lin, (size_t)st->N * sizeof(double)));
+    st->z0 = z0;
+    approx_fill_kernel<<<(st->R + 255) / 256, 256, 0, c->stream>>>(st->R, row_scale, st->scale);
+    NES_CHECK_LAUNCH(c);
+    approx_nu_kernel<<<(st->N + 255) / 256, 256, 0, c->stream>>>(st->N, b->d_colptr, b->d_rowidx, b->d_values,
+                                                                st->scale, st->beta,
+                                                                st->has_dense ? st->dense : nullptr, st->nu);
+    NES_CHECK_LAUNCH(c);
     return 0;
 }
 

@@ -128,6 +128,8 @@ def _prototypes(lib):
     fn("nes_approx_value_gradient", C.c_int, _vp, _dp, _dp, _dp, _dp, _vp)
     fn("nes_approx_get", C.c_int, _vp, C.c_int, _dp, _vp)
     fn("nes_approx_solve", C.c_int, _vp, C.c_int, _dp, _dp, _ip, _ip, _dp, _vp)
+    fn("nes_approx_set_variant", C.c_int, _vp, C.c_int, C.c_double, _vp)
+    fn("nes_approx_set_subproblem", C.c_int, _vp, C.c_double, _dp, C.c_double, _vp)
     fn("nes_symbolic_create", _vp, C.c_int, C.c_int, _ip, _ip, C.c_int, C.c_int, C.c_char_p, C.c_size_t)
     fn("nes_symbolic_ints", C.c_longlong, _vp, C.c_char_p, C.POINTER(_ip))
     fn("nes_symbolic_longs", C.c_longlong, _vp, C.c_char_p, C.POINTER(C.POINTER(C.c_longlong)))

@@ -256,10 +256,17 @@ int nes_approx_value_gradient(nes_approx* st, const double* x, double* value, do
  * 'z' / 'x' current iterates */
 int nes_approx_get(nes_approx* st, int which, double* out, nes_ctx* c);
 /* approx (approx.lisp:425-459): up to n_iter iterations from x0 (NULL = 0, projected on the bounds);
- * stops when the projected-gradient norm drops below 1e-10.  stats[6] = {|g|, projected gradient,
- * max constraint value, value + z0, last g.(zp - z), theta}. */
+ * stops when the projected-gradient norm drops below 1e-10.  stats[7] = {|g|, projected gradient,
+ * max constraint value, value + z0, last g.(zp - z), theta, z0 + value of the linear term}. */
 int nes_approx_solve(nes_approx* st, int n_iter, const double* x0, double* z_out, int* iters, int* restarts,
                      double* stats, nes_ctx* c);
+
+/* variant 1 = the inner solver of alm-approx.lisp (:198-346): step damped by 0.95, stop when i > 10 and the
+ * projected gradient is below `accuracy` (or at the last iteration), max ignores the linear term. */
+int nes_approx_set_variant(nes_approx* st, int variant, double accuracy, nes_ctx* c);
+/* make-alm-subproblem (alm-approx.lisp:355-403) over the same rows: uniform row scale sqrt(weight), linear
+ * term c + A'lambda, constant z0 = -lambda.b; nu is recomputed on the device. */
+int nes_approx_set_subproblem(nes_approx* st, double row_scale, const double* lin, double z0, nes_ctx* c);
 
 /* ---- symbolic analysis on its own (host only, no device needed) ---------------------------------
  * What nes_analyze computes for a sparse A before anything touches the GPU: the fill-reducing
