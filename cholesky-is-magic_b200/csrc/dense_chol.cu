@@ -6,13 +6,15 @@
 // a non-positive pivot sets status = 1 (CHOLMOD_NOT_POSDEF) and records the column ("minor");
 // the Lisp maps any non-zero status to NIL (:420-421).
 //
-// Step k (block column of NB=128):
-//   potrf_diag_kernel   one CTA: 128x128 diagonal block in shared memory; 16-column sub-panels, the
-//                       16x16 pivot block by ONE WARP with shuffles (lane = row), rows below by one
-//                       thread per row, trailing rank-16 update register-tiled over a 16x16 thread grid
-//   trsm_panel_kernel   X L_kk' = B for the rows below: one thread per row, 32-column register blocks,
-//                       L_kk broadcast from shared memory (true substitution, no explicit inverse)
-//   dmma_nt_kernel      trailing update C -= P P' on the FP64 tensor cores (lower tiles only)
+// Per 128-column inner panel:
+//   potrf_diag_kernel   one CTA: the 128x128 diagonal block arrives by one TMA box; 8-column sub-panels, every
+//                       row-owning thread factors the 8x8 pivot block redundantly in registers and solves its
+//                       row, rank-8 update on a 16x16 thread grid (potrf_block.cuh); TMA store
+//   trsm_panel_kernel   X L_kk' = B for a 64-row slab: operands by TMA, 4 threads per row (true substitution,
+//                       no explicit inverse), TMA store
+//   dmma_nt_kernel      updates C -= P P' on the FP64 tensor cores (lower tiles only)
+// Panels are grouped into outer panels (512 / 256 / 128 columns by remaining size) with look-ahead: see
+// dense_cholesky() below; the multi-GPU variant is dense_cholesky_dist_steps().
 #include <cstdio>
 #include <cstdlib>
 
