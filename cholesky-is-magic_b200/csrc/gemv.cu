@@ -7,6 +7,8 @@
 //   CSC    N : row gather over the CSR mirror (1-8 lanes per row, fixed shuffle tree)
 //   CSC    T : column gather (1-8 lanes per column)
 // The column scale s of nes_scale is folded in: N uses x_k*s_k, T multiplies the result by s_j.
+#include <cstdlib>
+
 #include "nes_internal.h"
 
 namespace nes {
@@ -145,8 +147,18 @@ static void spmv_gather_launch(cudaStream_t st, const int* ptr, const int* idx, 
 static void spmv_gather(cudaStream_t st, const int* ptr, const int* idx, const double* val, int nrows, size_t nnz,
                         const double* x, const double* s_in, const double* s_out, double alpha, double beta,
                         double* y) {
-    const double avg = nrows > 0 ? (double)nnz / nrows : 0.0;
-    if (avg >= 12.0) spmv_gather_launch<8>(st, ptr, idx, val, nrows, x, s_in, s_out, alpha, beta, y);
+    double avg = nrows > 0 ? (double)nnz / nrows : 0.0;
+    static int forced = -1;
+    if (forced < 0) forced = getenv("NES_SPMV_LANES") ? atoi(getenv("NES_SPMV_LANES")) : 0;
+    if (forced == 32) avg = 1000.0;
+    else if (forced == 16) avg = 300.0;
+    else if (forced == 8) avg = 100.0;
+    else if (forced == 4) avg = 6.0;
+    else if (forced == 2) avg = 3.0;
+    else if (forced == 1) avg = 0.0;
+    if (avg >= 500.0) spmv_gather_launch<32>(st, ptr, idx, val, nrows, x, s_in, s_out, alpha, beta, y);
+    else if (avg >= 200.0) spmv_gather_launch<16>(st, ptr, idx, val, nrows, x, s_in, s_out, alpha, beta, y);
+    else if (avg >= 12.0) spmv_gather_launch<8>(st, ptr, idx, val, nrows, x, s_in, s_out, alpha, beta, y);
     else if (avg >= 5.0) spmv_gather_launch<4>(st, ptr, idx, val, nrows, x, s_in, s_out, alpha, beta, y);
     else if (avg >= 2.5) spmv_gather_launch<2>(st, ptr, idx, val, nrows, x, s_in, s_out, alpha, beta, y);
     else spmv_gather_launch<1>(st, ptr, idx, val, nrows, x, s_in, s_out, alpha, beta, y);

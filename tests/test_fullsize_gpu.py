@@ -82,5 +82,42 @@ def test_config4_sparse_m100k_n250k(common):
     x = L.solve(b)
     r = A.sdmult(A.sdmult(x, transpose=True)) - b
     assert np.linalg.norm(r) / np.linalg.norm(b) <= 1e-8
+    # bitwise reproducible (owner-computes extend-add, fixed-order reductions), analysis reused
+    assert L.factorize(A)
+    np.testing.assert_array_equal(L.solve(b), x)
+    # linearity of the solve: (M^-1)(2 b + c) = 2 M^-1 b + M^-1 c up to rounding
+    c2 = rng.random(m)
+    lhs = L.solve(2 * b + c2)
+    rhs = 2 * x + L.solve(c2)
+    assert np.linalg.norm(lhs - rhs) <= 1e-9 * np.linalg.norm(rhs)
+    # the counters the reference prints (affine-scaling.lisp:273-279) are consistent
+    assert common.fl >= common.lnz >= common.anz and common.aatfl == float(
+        (np.bincount(sf.A.col, minlength=n).astype(float) ** 2).sum())
     L.free()
     A.free()
+
+
+def test_config4_scale_first_order_solver_properties(common):
+    """APPROX at config-4 scale (850k stacked variables): the gradient is consistent with the value along a
+    random direction, a run is bitwise repeatable, and the penalised objective goes down."""
+    from cholesky_is_magic_b200 import approx as gap
+    m, n = 100_000, 250_000
+    sf = lpgen.sparse_lp(m, n, nnz_per_col=10, bandwidth=200, seed=0)
+    st = gap.make_approx(sf)
+    try:
+        rng = np.random.default_rng(0)
+        x = rng.standard_normal(st.nvars)
+        d = rng.standard_normal(st.nvars)
+        f0, g, _ = gap.value_and_gradient(st, x)
+        h = 1e-6
+        fp = gap.value_and_gradient(st, x + h * d)[0]
+        fm = gap.value_and_gradient(st, x - h * d)[0]
+        assert abs((fp - fm) / (2 * h) - g @ d) <= 1e-5 * abs(g @ d)
+        v0 = gap.value_and_gradient(st, np.clip(np.zeros(st.nvars), st.l, st.u))[0]
+        z1, it1, r1, s1 = gap.approx(st, 200)
+        z2, it2, r2, s2 = gap.approx(st, 200)
+        np.testing.assert_array_equal(z1, z2)
+        assert it1 == it2 == 200 and s1[3] < 0.5 * v0
+        assert np.all(z1 >= st.l) and np.all(z1 <= st.u)
+    finally:
+        st.free()
