@@ -113,3 +113,93 @@ def alm(st, x0=None, maxiter=None, max_inner=1000000):
         if not (v > 1e-5 or pg > 1e-5):
             return i, total, v, pg, z, x
     return i + 1, total, v, pg, z, x
+
+
+# ---- the other outer-loop variants of alm-approx.lisp (host loops over the same device solver) -------
+def _inner(st, x, accuracy, max_inner):
+    """make-alm-subproblem + approx on the device; returns (x, pg, dual value, violation, inner iterations)."""
+    com = cholmod_common()
+    lin = st.c + st.A.sdmult(st.multipliers, transpose=True)
+    z0 = -float(st.multipliers @ st.b)
+    com.check(com.lib.nes_approx_set_subproblem(st.ptr, math.sqrt(st.mu), lin.ctypes.data_as(nes._dp), z0, com.ptr),
+              "nes_approx_set_subproblem")
+    com.check(com.lib.nes_approx_set_variant(st.ptr, 1, accuracy, com.ptr), "nes_approx_set_variant")
+    z = np.empty(st.sf.nvars)
+    it, rs = C.c_int(), C.c_int()
+    stats = np.zeros(7)
+    x0 = None if x is None else np.ascontiguousarray(x, dtype=np.float64)
+    com.check(com.lib.nes_approx_solve(st.ptr, max_inner, None if x0 is None else x0.ctypes.data_as(nes._dp),
+                                       z.ctypes.data_as(nes._dp), C.byref(it), C.byref(rs),
+                                       stats.ctypes.data_as(nes._dp), com.ptr), "nes_approx_solve")
+    return z, float(stats[1]), z0 + float(lin @ z), st.A.sdmult(z) - st.b, it.value
+
+
+def alm_iteration(st, x, precision=None, max_inner=1000000):
+    """alm-iteration (alm-approx.lisp:448-490): (x, violation, dual value, "minor" | "major")."""
+    x, pg, value, violation, inner = _inner(st, x, precision if precision is not None else max(st.omega, 1e-5),
+                                            max_inner)
+    vnorm = float(np.linalg.norm(violation))
+    st.multipliers = st.multipliers + st.mu * violation
+    if vnorm < st.nu:
+        st.nu = st.nu / st.mu ** 0.9
+        st.omega = max(st.omega / st.mu, 1e-5)
+        kind = "minor"
+    else:
+        st.mu = min(1.5 * st.mu, 1e6)
+        st.nu = 1.0 / st.mu ** 0.1
+        st.omega = max(1.0 / st.mu, 1e-5)
+        kind = "major"
+    st.log.append((vnorm, pg, value, kind, inner))
+    return x, violation, value, kind
+
+
+def next_extrapolation(weight):
+    """next-extrapolation (alm-approx.lisp:563-564)."""
+    return 0.5 * (1 + math.sqrt(1 + 4 * weight * weight))
+
+
+def extrapolate(weight, prev, accelerated, current):
+    """extrapolate (alm-approx.lisp:566-577)."""
+    nxt = next_extrapolation(weight)
+    return current + ((weight - 1) / nxt) * (current - prev) + (weight / nxt) * (current - accelerated)
+
+
+def aalm(st, x0=None, maxiter=None, max_inner=1000000):
+    """aalm (alm-approx.lisp:579-610)."""
+    x, v, pg, z = x0, None, None, None
+    accuracy = math.inf
+    prev_multipliers = st.multipliers
+    extrapolation = 1.0
+    total = 0
+    i = 0
+    for i in range(maxiter or 10000):
+        prev_accelerated = st.multipliers
+        if i > 0:
+            extrapolation = next_extrapolation(extrapolation)
+        x, vv, pg, z, inner = alm_iteration2(st, x, min(accuracy, st.omega), max_inner)
+        total += inner
+        v = float(np.abs(vv).max(initial=0.0))
+        accuracy = min(accuracy, max(1e-6, v))
+        if v < 1e-5:
+            accuracy = 1e-6
+        prev_multipliers, st.multipliers = st.multipliers, extrapolate(extrapolation, prev_multipliers,
+                                                                       prev_accelerated, st.multipliers)
+        if not (v > 1e-5 or (pg > 1e-5 and pg > 2e-6 * (1 + abs(z)))):
+            return i, total, v, pg, z, x
+    return i + 1, total, v, pg, z, x
+
+
+def adcd_iteration(st, x):
+    """adcd-iteration (alm-approx.lisp:612-656): (x, violation, done)."""
+    close = x is not None and float(np.linalg.norm(st.A.sdmult(x) - st.b)) < 5e-2
+    x, pg, value, violation, inner = _inner(st, x, 1e-2, 10000 if close else 100)
+    vnorm = float(np.linalg.norm(violation))
+    out_close = pg < 5e-2
+    almost = vnorm < 5e-2
+    if pg < 1e-2 and vnorm < 1e-2:
+        return x, violation, True
+    st.multipliers = st.multipliers + ((1.0 if out_close else 0.5) * st.mu) * violation
+    st.mu = min(1e6, (1.0 if (out_close and almost) else (10.0 if out_close else 1.0)) * st.mu)
+    st.nu = 1.0 / st.mu ** 0.1
+    st.omega = 1.0 / st.mu
+    return x, violation, False

@@ -172,3 +172,81 @@ def alm(st, x0=None, maxiter=None, max_inner=1000000):
         if not (v > 1e-5 or pg > 1e-5):
             return i, total_inner, v, pg, z, x
     return i + 1, total_inner, v, pg, z, x
+
+
+# ---- the other outer-loop variants of alm-approx.lisp ----------------------------------------------
+def alm_iteration(st, x, precision=None, max_inner=1000000):
+    """alm-iteration (:448-490): "minor" step (multipliers only) when the violation is below nu, else "major"
+    (mu grows by 1.5).  Returns (x, violation, dual value, kind)."""
+    sub = make_alm_subproblem(st.A, st.b, st.c, st.l, st.u, st.multipliers, st.mu)
+    x, pg, inner, _ = approx(sub, max_inner, x, precision if precision is not None else max(st.omega, 1e-5))
+    value = dual_value(sub, x)
+    violation = unscaled_violation(sub, x)
+    vnorm = float(np.linalg.norm(violation))
+    st.multipliers = st.multipliers + st.mu * violation
+    if vnorm < st.nu:
+        st.nu = st.nu / st.mu ** 0.9
+        st.omega = max(st.omega / st.mu, 1e-5)
+        kind = "minor"
+    else:
+        st.mu = min(1.5 * st.mu, 1e6)
+        st.nu = 1.0 / st.mu ** 0.1
+        st.omega = max(1.0 / st.mu, 1e-5)
+        kind = "major"
+    st.log.append((vnorm, pg, value, kind, inner))
+    return x, violation, value, kind
+
+
+def next_extrapolation(weight):
+    """next-extrapolation (:563-564)."""
+    return 0.5 * (1 + math.sqrt(1 + 4 * weight * weight))
+
+
+def extrapolate(weight, prev, accelerated, current):
+    """extrapolate (:566-577)."""
+    nxt = next_extrapolation(weight)
+    return current + ((weight - 1) / nxt) * (current - prev) + (weight / nxt) * (current - accelerated)
+
+
+def aalm(st, x0=None, maxiter=None, max_inner=1000000):
+    """aalm (:579-610), the accelerated outer loop ("not very good" in the source)."""
+    x, v, pg, z = x0, None, None, None
+    accuracy = math.inf
+    prev_multipliers = st.multipliers
+    extrapolation = 1.0
+    total = 0
+    i = 0
+    for i in range(maxiter or 10000):
+        prev_accelerated = st.multipliers
+        if i > 0:
+            extrapolation = next_extrapolation(extrapolation)
+        x, vv, pg, z, inner = alm_iteration2(st, x, min(accuracy, st.omega), max_inner)
+        total += inner
+        v = float(np.abs(vv).max(initial=0.0))
+        accuracy = min(accuracy, max(1e-6, v))
+        if v < 1e-5:
+            accuracy = 1e-6
+        prev_multipliers, st.multipliers = st.multipliers, extrapolate(extrapolation, prev_multipliers,
+                                                                       prev_accelerated, st.multipliers)
+        if not (v > 1e-5 or (pg > 1e-5 and pg > 2e-6 * (1 + abs(z)))):
+            return i, total, v, pg, z, x
+    return i + 1, total, v, pg, z, x
+
+
+def adcd_iteration(st, x):
+    """adcd-iteration (:612-656): short inner solves (100 iterations, 10000 once close) to accuracy 1e-2.
+    Returns (x, violation, done)."""
+    sub = make_alm_subproblem(st.A, st.b, st.c, st.l, st.u, st.multipliers, st.mu)
+    close = x is not None and float(np.linalg.norm(unscaled_violation(sub, x))) < 5e-2
+    x, pg, inner, _ = approx(sub, 10000 if close else 100, x, 1e-2)
+    violation = unscaled_violation(sub, x)
+    vnorm = float(np.linalg.norm(violation))
+    out_close = pg < 5e-2
+    almost = vnorm < 5e-2
+    if pg < 1e-2 and vnorm < 1e-2:
+        return x, violation, True
+    st.multipliers = st.multipliers + ((1.0 if out_close else 0.5) * st.mu) * violation
+    st.mu = min(1e6, (1.0 if (out_close and almost) else (10.0 if out_close else 1.0)) * st.mu)
+    st.nu = 1.0 / st.mu ** 0.1
+    st.omega = 1.0 / st.mu
+    return x, violation, False

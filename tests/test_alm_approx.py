@@ -78,3 +78,65 @@ def test_gpu_alm_matches_oracle_and_highs(common, kind, m, n, ub):
     # counts agree closely but not exactly; objective and multipliers are what is pinned
     assert abs(outer - oouter) <= 2 and abs(inner - oinner) <= 0.1 * oinner + 20
     assert abs(value - ovalue) <= 1e-6 * abs(ovalue)
+
+
+def test_oracle_other_outer_loops_make_progress():
+    """alm-iteration (minor/major rule), aalm and adcd-iteration drive |Ax - b| down on a small LP."""
+    sf, A = lp("dense", 8, 20, 1)
+    fun = highs(sf, A)
+    st = oalm.make_alm(A, sf.b, sf.c_dense(), sf.l, sf.u, list(sf.type))
+    x = None
+    for _ in range(12):
+        x, viol, value, kind = oalm.alm_iteration(st, x)
+        assert kind in ("minor", "major")
+    assert np.linalg.norm(viol) <= 1e-3 and abs(value - fun) <= 1e-3 * abs(fun)
+    st = oalm.make_alm(A, sf.b, sf.c_dense(), sf.l, sf.u, list(sf.type))
+    outer, inner, v, pg, z, x = oalm.aalm(st, maxiter=40)
+    assert v <= 1e-3
+    st = oalm.make_alm(A, sf.b, sf.c_dense(), sf.l, sf.u, list(sf.type))
+    x, done = None, False
+    for _ in range(200):
+        x, viol, done = oalm.adcd_iteration(st, x)
+        if done:
+            break
+    assert done and np.linalg.norm(viol) < 1e-2
+    assert oalm.next_extrapolation(1.0) == 0.5 * (1 + 5 ** 0.5)
+
+
+@pytest.mark.gpu
+def test_gpu_other_outer_loops_match_oracle(common):
+    """Same sequences of outer iterations as the oracle (kinds, mu, multipliers) for alm-iteration and
+    adcd-iteration; aalm ends within the same tolerance."""
+    from cholesky_is_magic_b200 import alm_approx as galm
+    sf, A = lp("sparse", 30, 70, 1)
+    ost = oalm.make_alm(A, sf.b, sf.c_dense(), sf.l, sf.u, list(sf.type))
+    st = galm.make_alm(sf)
+    try:
+        x = ox = None
+        for k in range(6):
+            x, viol, value, kind = galm.alm_iteration(st, x)
+            ox, oviol, ovalue, okind = oalm.alm_iteration(ost, ox)
+            assert kind == okind and abs(st.mu - ost.mu) <= 1e-12 * ost.mu
+            assert abs(value - ovalue) <= 1e-4 * abs(ovalue) + 1e-6
+            np.testing.assert_allclose(st.multipliers, ost.multipliers, rtol=1e-3, atol=1e-4)
+    finally:
+        st.free()
+    ost = oalm.make_alm(A, sf.b, sf.c_dense(), sf.l, sf.u, list(sf.type))
+    st = galm.make_alm(sf)
+    try:
+        x = ox = None
+        for k in range(8):
+            x, viol, done = galm.adcd_iteration(st, x)
+            ox, oviol, odone = oalm.adcd_iteration(ost, ox)
+            assert done == odone and abs(st.mu - ost.mu) <= 1e-12 * ost.mu
+            np.testing.assert_allclose(x, ox, rtol=1e-6, atol=1e-8)
+            if done:
+                break
+    finally:
+        st.free()
+    st = galm.make_alm(sf)
+    try:
+        outer, inner, v, pg, z, x = galm.aalm(st, maxiter=60)
+        assert v <= 1e-3
+    finally:
+        st.free()
