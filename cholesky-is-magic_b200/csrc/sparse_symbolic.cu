@@ -11,7 +11,7 @@
 //      profile ordering leaves a chain of ~m/128 supernodes, each waiting for the previous one.
 //   3. elimination tree (Liu, path compression), postorder, column counts (Gilbert-Ng-Peyton skeleton
 //      counting) -- near-linear in nnz(A A'), no per-column structures
-//   4. supernodes: etree chains, relaxed amalgamation (<= 128 columns, <= 15% explicit zeros)
+//   4. supernodes: etree chains, relaxed amalgamation (<= 128 columns, <= 30% explicit zeros)
 //   5. assembly tree levels; supernodes renumbered by level (a topological order, so fill is unchanged)
 //   6. supernodal row structures, parent-relative index maps, update-matrix pool with slot reuse,
 //      solve segments, assembly map, subtree-to-rank mapping
@@ -472,6 +472,8 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
     // ---- supernodes: chains parent(j) = j+1, relaxed amalgamation --------------------------------------
     std::vector<int> sfirst;  // in postorder numbering
     sfirst.push_back(0);
+    double relax = 0.30;  // explicit zeros tolerated in a relaxed supernode (NES_RELAX overrides: experiments)
+    if (const char* e = getenv("NES_RELAX")) relax = atof(e);
     {
         int f = 0;
         for (int j = 0; j < m; ++j) {
@@ -482,7 +484,7 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
                 long long z = 0;
                 for (int q = f; q <= j + 1; ++q) z += (nrows - (q - f)) - cc[q];
                 const long long total = nrows * width - (long long)width * (width - 1) / 2;
-                if (width <= SN_MAX_COLS && (width <= 4 || z <= 0.15 * total)) merge = true;
+                if (width <= SN_MAX_COLS && (width <= 4 || z <= relax * total)) merge = true;
             }
             if (!merge) {
                 sfirst.push_back(j + 1);
