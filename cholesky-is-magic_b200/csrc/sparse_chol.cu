@@ -128,10 +128,61 @@ struct SparseFactor {
     double* d_dots = nullptr;  // backward sweep: B_s' z per column
     int* d_info = nullptr;
     long long wsize = 0;
-    cudaGraphExec_t graph = nullptr;  // captured factorization (replayed while the operands stay put)
-    const void* graph_theta = nullptr;
-    const void* graph_vals = nullptr;
+    // The launch sequences of a factorization (~180 launches) and of a solve (~140) depend only on the
+    // pattern: they are captured into CUDA graphs on first use and replayed while their operands stay put
+    // (single rank only: the multi-rank sequences contain NCCL calls).
+    struct GraphCache {
+        cudaGraphExec_t exec = nullptr;
+        const void* k0 = nullptr;
+        const void* k1 = nullptr;
+        double k2 = 0.0;
+        long long launches = 0;
+    };
+    GraphCache g_factor[4];  // keyed by the scale vector (Newton step and repair step use different ones)
+    int g_factor_next = 0;
+    GraphCache g_solve[4];  // keyed by the right-hand-side vector (the IPM drivers solve into 2-3 different ones)
+    int g_solve_next = 0;
+    bool graphs_off = false;
 };
+
+template <class F>
+static int run_captured(nes_ctx* c, SparseFactor* sf, SparseFactor::GraphCache& g, const void* k0, const void* k1,
+                        double k2, F enqueue) {
+    static const bool env_off = getenv("NES_NO_GRAPH") != nullptr;
+    if (env_off || sf->graphs_off || c->nranks > 1 || sparse_sync_debug() || c->timing > 1) return enqueue();
+    if (g.exec && (g.k0 != k0 || g.k1 != k1 || g.k2 != k2)) {
+        cudaGraphExecDestroy(g.exec);
+        g.exec = nullptr;
+    }
+    if (!g.exec) {
+        const long long l0 = c->launches;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+            cudaGetLastError();
+            sf->graphs_off = true;
+            return enqueue();
+        }
+        const int rc = enqueue();
+        cudaGraph_t graph = nullptr;
+        cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+        if (rc == 0 && e == cudaSuccess && graph) e = cudaGraphInstantiate(&g.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (rc != 0 || e != cudaSuccess || !g.exec) {  // could not capture: run directly from now on
+            cudaGetLastError();
+            g.exec = nullptr;
+            sf->graphs_off = true;
+            c->launches = l0;
+            return rc != 0 ? rc : enqueue();
+        }
+        g.launches = c->launches - l0;
+        c->launches = l0;
+        g.k0 = k0;
+        g.k1 = k1;
+        g.k2 = k2;
+    }
+    NES_CUDA(c, cudaGraphLaunch(g.exec, c->stream));
+    c->launches += g.launches;
+    return 0;
+}
 
 // ------------------------------------------------------------------------------------------------
 // device: numeric factorization
@@ -888,7 +939,10 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
 void sparse_free(nes_ctx* c, nes_factor* L) {
     SparseFactor* sf = L->sparse;
     if (!sf) return;
-    if (sf->graph) cudaGraphExecDestroy(sf->graph);
+    for (auto& g : sf->g_factor)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    for (auto& g : sf->g_solve)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
     for (void* p : sf->owned) dev_free(c, p);
     delete sf;
     L->sparse = nullptr;
@@ -968,7 +1022,23 @@ int sparse_factorize(nes_ctx* c, nes_matrix* A, nes_factor* L) {
     const Symbolic& S = sf->S;
     L->factorized = 0;
     sf->d.dbound = c->dbound;
-    {
+    if (c->nranks == 1) {
+        StageTimer t(c, NES_STAGE_FACTOR);
+        const double* d_theta = A->d_theta;
+        SparseFactor::GraphCache* gc = nullptr;
+        for (auto& cand : sf->g_factor)
+            if (cand.exec && cand.k0 == d_theta && cand.k1 == b->d_csr_val && cand.k2 == c->dbound) gc = &cand;
+        if (!gc) {
+            gc = &sf->g_factor[sf->g_factor_next];
+            sf->g_factor_next = (sf->g_factor_next + 1) % 4;
+        }
+        NES_TRY(run_captured(c, sf, *gc, d_theta, b->d_csr_val, c->dbound, [&]() -> int {
+            NES_TRY(enqueue_factorization(c, sf, b, d_theta));
+            NES_CUDA(c, cudaEventRecord(c->ev_aux, c->stream_aux));  // join: the block inverses are complete
+            NES_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_aux, 0));
+            return 0;
+        }));
+    } else {
         StageTimer t(c, NES_STAGE_FACTOR);
         NES_TRY(enqueue_factorization(c, sf, b, A->d_theta));
         if (c->nranks > 1) {
@@ -1036,26 +1106,36 @@ int sparse_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x) {
     StageTimer t(c, NES_STAGE_SOLVE);
     const Symbolic& S = sf->S;
     const int m = sf->m;
-    gather_perm_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(m, sf->d_perm, d_x, sf->d_x, 0);
-    NES_CHECK_LAUNCH(c);
-    NES_TRY(run_solve_phase(c, sf, 0, false));
-    if (c->nranks > 1) {
-        for (int q = 0; q < c->nranks; ++q) {
-            const long long cnt = S.xv_off[q + 1] - S.xv_off[q];
-            if (cnt > 0) NES_TRY(dist_broadcast(c, sf->d.uvec + S.xv_off[q], (size_t)cnt, q));
-        }
-    }
-    NES_TRY(run_solve_phase(c, sf, 1, false));
-    NES_TRY(run_solve_phase(c, sf, 1, true));
-    NES_TRY(run_solve_phase(c, sf, 0, true));
-    if (c->nranks > 1) {
-        mf_mask_kernel<<<S.nsuper, 128, 0, c->stream>>>(S.nsuper, sf->d.first, sf->d_owner, c->rank, sf->d_x);
+    auto enqueue = [&]() -> int {
+        gather_perm_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(m, sf->d_perm, d_x, sf->d_x, 0);
         NES_CHECK_LAUNCH(c);
-        NES_TRY(dist_allreduce_sum(c, sf->d_x, (size_t)m));
+        NES_TRY(run_solve_phase(c, sf, 0, false));
+        if (c->nranks > 1) {
+            for (int q = 0; q < c->nranks; ++q) {
+                const long long cnt = S.xv_off[q + 1] - S.xv_off[q];
+                if (cnt > 0) NES_TRY(dist_broadcast(c, sf->d.uvec + S.xv_off[q], (size_t)cnt, q));
+            }
+        }
+        NES_TRY(run_solve_phase(c, sf, 1, false));
+        NES_TRY(run_solve_phase(c, sf, 1, true));
+        NES_TRY(run_solve_phase(c, sf, 0, true));
+        if (c->nranks > 1) {
+            mf_mask_kernel<<<S.nsuper, 128, 0, c->stream>>>(S.nsuper, sf->d.first, sf->d_owner, c->rank, sf->d_x);
+            NES_CHECK_LAUNCH(c);
+            NES_TRY(dist_allreduce_sum(c, sf->d_x, (size_t)m));
+        }
+        gather_perm_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(m, sf->d_perm, sf->d_x, d_x, 1);
+        NES_CHECK_LAUNCH(c);
+        return 0;
+    };
+    SparseFactor::GraphCache* g = nullptr;
+    for (auto& cand : sf->g_solve)
+        if (cand.exec && cand.k0 == d_x) g = &cand;
+    if (!g) {
+        g = &sf->g_solve[sf->g_solve_next];
+        sf->g_solve_next = (sf->g_solve_next + 1) % 4;
     }
-    gather_perm_kernel<<<(m + 255) / 256, 256, 0, c->stream>>>(m, sf->d_perm, sf->d_x, d_x, 1);
-    NES_CHECK_LAUNCH(c);
-    return 0;
+    return run_captured(c, sf, *g, d_x, nullptr, 0.0, enqueue);
 }
 
 // expand the supernodal factor to a dense lower-triangular matrix (testing) + permutation
