@@ -11,6 +11,8 @@
 //   solve-coordinate, approx-iteration (:353-398)   approx_y_kernel, approx_descent_kernel
 //   restart test, project-gradient (:400-423, :441-449)   approx_dot_kernel, approx_apply_kernel
 // Reductions are two-stage (per-CTA partials, combined by one thread in block order): bitwise reproducible.
+#include <cstdlib>
+
 #include "nes_internal.h"
 
 struct nes_approx {
@@ -33,6 +35,10 @@ struct nes_approx {
     // |pg| < accuracy or at the last iteration (:328-333), the max ignores the linear term (:188-190)
     int variant = 0;
     double accuracy = 1e-10;
+    cudaGraphExec_t graph = nullptr;  // one iteration of `approx`, captured per variant
+    int graph_variant = -1;
+    long long graph_launches = 0;
+    bool graph_off = false;
 };
 
 namespace nes {
@@ -223,20 +229,34 @@ __global__ void approx_addlin_kernel(int N, const double* __restrict__ lin, cons
     if (j < N) g[j] += lin[j] + (dense ? dense[j] * red[5] : 0.0);
 }
 
-__global__ void approx_y_kernel(int N, double theta, const double* __restrict__ x, const double* __restrict__ z,
-                                double* __restrict__ y) {
+// theta lives in red[7] on the device so that one iteration is a fixed launch sequence (CUDA graph)
+__global__ void approx_y_kernel(int N, const double* __restrict__ red, const double* __restrict__ x,
+                                const double* __restrict__ z, double* __restrict__ y) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    const double theta = red[7];
     if (j < N) y[j] = (1.0 - theta) * x[j] + theta * z[j];
 }
 
+// theta <- 1 on a restart, else 1/2 (sqrt(theta^4 + 4 theta^2) - theta^2) in the reference's operation
+// order (approx.lisp:393-396 / alm-approx.lisp:258-263), without FMA contraction
+__global__ void approx_theta_kernel(double* __restrict__ red, int variant) {
+    const double t = red[7];
+    const double t2 = __dmul_rn(t, t);
+    const double rad = variant == 1 ? __dmul_rn(__dadd_rn(4.0, t2), t2)
+                                    : __dadd_rn(__dmul_rn(t2, t2), __dmul_rn(4.0, t2));
+    const double next = __dmul_rn(0.5, __dsub_rn(__dsqrt_rn(rad), t2));
+    red[7] = red[2] > 0.0 ? 1.0 : next;
+}
+
 // zp = solve-coordinate (approx.lisp:353-369); x <- y + theta (zp - z) (approx-iteration :390-392)
-__global__ void approx_descent_kernel(int N, double theta, double damping, const double* __restrict__ y,
-                                      const double* __restrict__ z,
+__global__ void approx_descent_kernel(int N, const double* __restrict__ red, double damping,
+                                      const double* __restrict__ y, const double* __restrict__ z,
                                       const double* __restrict__ nu, const double* __restrict__ g,
                                       const double* __restrict__ l, const double* __restrict__ u,
                                       double* __restrict__ zp, double* __restrict__ x) {
     const int j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= N) return;
+    const double theta = red[7];
     const double step = theta * nu[j];
     const double zj = z[j], gj = g[j];
     double best;
@@ -472,6 +492,7 @@ int nes_approx_free(nes_approx** pst, nes_ctx* c) {
                    st->beta, st->nu, st->x, st->z, st->y, st->zp, st->g, st->t, st->rs, st->red, st->dense, st->partr,
                    st->partn};
     for (void* p : all) dev_free(c, p);
+    if (st->graph) cudaGraphExecDestroy(st->graph);
     delete st;
     *pst = nullptr;
     return 1;
@@ -516,20 +537,20 @@ int nes_approx_solve(nes_approx* st, int n_iter, const double* x0, double* z_out
     else NES_CUDA(c, cudaMemsetAsync(st->x, 0, (size_t)N * sizeof(double), c->stream));
     approx_project_kernel<<<nb, 256, 0, c->stream>>>(N, st->l, st->u, st->x, st->z);
     NES_CHECK_LAUNCH(c);
-    double theta = 1.0;
+    approx_fill_kernel<<<1, 32, 0, c->stream>>>(1, 1.0, st->red + 7);  // theta = 1
+    NES_CHECK_LAUNCH(c);
     int nrestart = 0, done_at = n_iter;
     double red[8] = {0};
-    double lin_value = 0.0;
-    for (int i = 0; i < n_iter; ++i) {
-        approx_y_kernel<<<nb, 256, 0, c->stream>>>(N, theta, st->x, st->z, st->y);
+    double lin_value = 0.0, theta = 1.0;
+    // one iteration = a fixed sequence of 19 launches: captured once, replayed (every iteration ends in a
+    // host synchronisation, so the enqueue cost would otherwise sit on the critical path)
+    auto enqueue_iteration = [&]() -> int {
+        approx_y_kernel<<<nb, 256, 0, c->stream>>>(N, st->red, st->x, st->z, st->y);
         NES_CHECK_LAUNCH(c);
         NES_TRY(approx_value_gradient_dev(c, st, st->y));
-        approx_descent_kernel<<<nb, 256, 0, c->stream>>>(N, theta, st->variant == 1 ? 0.95 : 1.0, st->y, st->z, st->nu,
-                                                        st->g, st->l, st->u, st->zp, st->x);
+        approx_descent_kernel<<<nb, 256, 0, c->stream>>>(N, st->red, st->variant == 1 ? 0.95 : 1.0, st->y, st->z,
+                                                        st->nu, st->g, st->l, st->u, st->zp, st->x);
         NES_CHECK_LAUNCH(c);
-        const double t2 = theta * theta;
-        theta = st->variant == 1 ? 0.5 * (sqrt((4.0 + t2) * t2) - t2)    // alm-approx.lisp:258-263
-                                 : 0.5 * (sqrt(t2 * t2 + 4.0 * t2) - t2);  // approx.lisp:393-396
         NES_TRY(approx_value_gradient_dev(c, st, st->zp));
         const int gn = ap_grid(c, N);
         approx_dot_kernel<<<gn, AP_B, 0, c->stream>>>(N, st->g, st->z, st->zp, st->partn);
@@ -541,12 +562,48 @@ int nes_approx_solve(nes_approx* st, int n_iter, const double* x0, double* z_out
         NES_CHECK_LAUNCH(c);
         approx_finish_kernel<<<1, AP_B, 0, c->stream>>>(gn, st->partn, 4, 1, -1, st->red);
         NES_CHECK_LAUNCH(c);
-        NES_TRY(download(c, red, st->red, 7 * sizeof(double)));  // the iteration's only host sync
-        lin_value = red[6];
-        if (red[2] > 0.0) {
-            ++nrestart;
-            theta = 1.0;
+        approx_theta_kernel<<<1, 1, 0, c->stream>>>(st->red, st->variant);
+        NES_CHECK_LAUNCH(c);
+        return 0;
+    };
+    static const bool env_off = getenv("NES_NO_GRAPH") != nullptr;
+    const bool want_graph = !env_off && !st->graph_off && !c->timing;
+    if (want_graph && st->graph && st->graph_variant != st->variant) {
+        cudaGraphExecDestroy(st->graph);
+        st->graph = nullptr;
+    }
+    if (want_graph && !st->graph) {
+        const long long l0 = c->launches;
+        cudaGraph_t graph = nullptr;
+        int rc = -1;
+        if (cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            rc = enqueue_iteration();
+            cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+            if (rc == 0 && e == cudaSuccess && graph && cudaGraphInstantiate(&st->graph, graph, 0) != cudaSuccess)
+                st->graph = nullptr;
+            if (graph) cudaGraphDestroy(graph);
         }
+        st->graph_launches = c->launches - l0;
+        c->launches = l0;
+        if (!st->graph) {
+            cudaGetLastError();
+            st->graph_off = true;
+            c->status = 0;
+        } else {
+            st->graph_variant = st->variant;
+        }
+    }
+    for (int i = 0; i < n_iter; ++i) {
+        if (want_graph && st->graph) {
+            NES_CUDA(c, cudaGraphLaunch(st->graph, c->stream));
+            c->launches += st->graph_launches;
+        } else {
+            NES_TRY(enqueue_iteration());
+        }
+        NES_TRY(download(c, red, st->red, 8 * sizeof(double)));  // the iteration's only host sync
+        lin_value = red[6];
+        theta = red[7];
+        if (red[2] > 0.0) ++nrestart;
         const bool done = st->variant == 1 ? ((i > 10 && red[4] < st->accuracy) || i == n_iter - 1)
                                            : red[4] < 1e-10;
         if (done) {
