@@ -52,7 +52,7 @@ static NcclApi* nccl_api() {
 }
 
 // Distribution block = outer panel width of the distributed factorization.  Wide panels (512) make the
-// trailing updates efficient, which is what bounds the step on 1-2 GPUs; from 4 GPUs on every rank's share of
+// trailing updates efficient, which is what bounds the step on 1-4 GPUs; at 8 GPUs every rank's share of
 // the update is small and the panel chain (owner's column update + panel + broadcast) bounds it, and
 // that chain is shorter per column with 256-wide panels.  NES_DIST_NBO overrides (testing).
 int dense_outer_block(int m, int nranks) {
@@ -61,7 +61,7 @@ int dense_outer_block(int m, int nranks) {
         if (v == 128 || v == 256 || v == 512) return v;
     }
     if (m <= 12288) return 256;
-    return nranks >= 4 ? 256 : 512;
+    return nranks >= 8 ? 256 : 512;  // measured at m = 32768: N=2 206 vs 220 ms, N=4 127 vs 130 ms, N=8 98 vs 94 ms
 }
 
 // Owner of outer block column J.  Plain cyclic ownership always hands rank 0 the longest column of
