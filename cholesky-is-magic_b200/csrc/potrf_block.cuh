@@ -7,6 +7,7 @@
 //   info = {NES_NOT_POSDEF, col_base + column} once and continues with a unit pivot.
 #pragma once
 #include "../../include/nes.h"
+#include "ptx_util.cuh"
 
 namespace nes {
 
@@ -191,19 +192,41 @@ __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb
 // triangular pieces are solved by their owner.  True substitution (no inverse): the factorization's
 // backward-error bound is untouched.  ~3.3x fewer FMAs on the per-row critical path than one thread
 // per row.
-__device__ __forceinline__ void trsm_slab_smem(const double* Ls, double* Xs, const double* dv, int nc,
-                                               int nrows) {
+template <int LP, int XP, bool kMma>
+__device__ __forceinline__ void trsm_slab_smem_t(const double* Ls, double* Xs, const double* dv, int nc,
+                                                 int nrows) {
     const int tid = threadIdx.x, r = tid & 63, q = tid >> 6;
     const bool active = r < nrows;
     for (int cb = 0; cb < nc; cb += 32) {
         const int c0 = cb + 8 * q;  // my 8 columns of this block
+        if (kMma && cb > 0) {
+            // X[:, cb:cb+32] -= X[:, 0:cb] L[cb:cb+32, 0:cb]' on the FP64 tensor cores: warp w owns rows
+            // 8w..8w+7 and the four 8-column tiles; with pitches = 4 (mod 16) the fragment loads are
+            // conflict-free.  (The FMA version of this product needs 5 shared loads per 8 FMAs.)
+            const int lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+            double acc[4][2];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[j][0] = acc[j][1] = 0.0;
+            const double* xa = Xs + t * XP + 8 * warp + g;
+            const double* lb = Ls + (cb + g) + t * LP;
+            for (int k0 = 0; k0 < cb; k0 += 4) {
+                const double a = xa[k0 * XP];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) dmma884(acc[j][0], acc[j][1], a, lb[8 * j + k0 * LP]);
+            }
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) Xs[(cb + 8 * j + 2 * t + e) * XP + 8 * warp + g] -= acc[j][e];
+            __syncthreads();
+        }
         double b8[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) b8[i] = (active && c0 + i < nc) ? Xs[(c0 + i) * 64 + r] : 0.0;
-        if (active) {
+        for (int i = 0; i < 8; ++i) b8[i] = (active && c0 + i < nc) ? Xs[(c0 + i) * XP + r] : 0.0;
+        if (!kMma && active) {
             for (int p = 0; p < cb; ++p) {
-                const double xp = Xs[p * 64 + r];
-                const double2* l2 = reinterpret_cast<const double2*>(Ls + c0 + p * 128);
+                const double xp = Xs[p * XP + r];
+                const double2* l2 = reinterpret_cast<const double2*>(Ls + c0 + p * LP);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     const double2 lv = l2[i];
@@ -222,11 +245,11 @@ __device__ __forceinline__ void trsm_slab_smem(const double* Ls, double* Xs, con
                     b8[i] = xv;
 #pragma unroll
                     for (int i2 = i + 1; i2 < 8; ++i2)
-                        b8[i2] = fma(-xv, Ls[min(s0 + i2, 127) + min(s0 + i, 127) * 128], b8[i2]);
+                        b8[i2] = fma(-xv, Ls[min(s0 + i2, 127) + min(s0 + i, 127) * LP], b8[i2]);
                 }
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
-                    if (s0 + i < nc) Xs[(s0 + i) * 64 + r] = b8[i];
+                    if (s0 + i < nc) Xs[(s0 + i) * XP + r] = b8[i];
             }
             __syncthreads();
             if (q > qq && active && s0 < nc) {
@@ -234,8 +257,8 @@ __device__ __forceinline__ void trsm_slab_smem(const double* Ls, double* Xs, con
                 for (int pp = 0; pp < 8; ++pp) {
                     const int p = s0 + pp;
                     if (p < nc) {
-                        const double xp = Xs[p * 64 + r];
-                        const double2* l2 = reinterpret_cast<const double2*>(Ls + c0 + p * 128);
+                        const double xp = Xs[p * XP + r];
+                        const double2* l2 = reinterpret_cast<const double2*>(Ls + c0 + p * LP);
 #pragma unroll
                         for (int i = 0; i < 4; ++i) {
                             const double2 lv = l2[i];
@@ -247,6 +270,12 @@ __device__ __forceinline__ void trsm_slab_smem(const double* Ls, double* Xs, con
             }
         }
     }
+}
+
+// dense-path layout: L block pitch 128, slab pitch 64 (TMA boxes), FMA product
+__device__ __forceinline__ void trsm_slab_smem(const double* Ls, double* Xs, const double* dv, int nc,
+                                               int nrows) {
+    trsm_slab_smem_t<128, 64, false>(Ls, Xs, dv, nc, nrows);
 }
 
 }  // namespace nes

@@ -291,14 +291,16 @@ mf_potrf_kernel(const MfDesc d, const int* __restrict__ list, int ncmax) {
 // sized by `ncmax` (64 or 128).  L's columns and the slab's columns arrive by bulk copies; the slab
 // leaves the same way (16-row granularity: the layout pads every block to 16 rows).
 constexpr int MF_TR_ROWS = 64;
-static inline int mf_tr_smem(int ncmax) { return (ncmax * CH_NB + MF_TR_ROWS * ncmax + CH_NB) * 8 + 16; }
+constexpr int MF_LP = 132;  // pitch of L's columns in shared memory  } = 4 (mod 16): the DMMA fragment loads
+constexpr int MF_XP = 68;   // pitch of the slab's columns            } of trsm_slab_smem_t are conflict-free
+static inline int mf_tr_smem(int ncmax) { return (ncmax * MF_LP + ncmax * MF_XP + CH_NB) * 8 + 16; }
 
 __global__ void __launch_bounds__(256)
 mf_trsm_kernel(const MfDesc d, const int2* __restrict__ tasks, int ncmax) {
     extern __shared__ __align__(128) double sm[];
-    double* Ls = sm;                        // Ls[c + p*128] = L[c][p]
-    double* Xs = Ls + ncmax * CH_NB;        // Xs[p*64 + row]
-    double* dv = Xs + MF_TR_ROWS * ncmax;
+    double* Ls = sm;                        // Ls[c + p*MF_LP] = L[c][p]
+    double* Xs = Ls + ncmax * MF_LP;        // Xs[p*MF_XP + row]
+    double* dv = Xs + ncmax * MF_XP;
     uint64_t* bar = reinterpret_cast<uint64_t*>(dv + CH_NB);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int s = tasks[blockIdx.x].x, slab = tasks[blockIdx.x].y;
@@ -317,12 +319,12 @@ mf_trsm_kernel(const MfDesc d, const int2* __restrict__ tasks, int ncmax) {
     __syncthreads();
     if (warp == 0) {
         for (int p = lane; p < nc; p += 32) {
-            bulk_load_1d(Ls + p * CH_NB, blk + (long long)p * ld, nb0 * 8, bar);   // rows nc..nb0-1 are zero pad
-            bulk_load_1d(Xs + p * MF_TR_ROWS, slab_g + (long long)p * ld, nrows16 * 8, bar);
+            bulk_load_1d(Ls + p * MF_LP, blk + (long long)p * ld, nb0 * 8, bar);   // rows nc..nb0-1 are zero pad
+            bulk_load_1d(Xs + p * MF_XP, slab_g + (long long)p * ld, nrows16 * 8, bar);
         }
     }
     // columns nc..nb0-1 of Ls (read by the 32-column blocking of trsm_slab_smem) are zero
-    for (int idx = tid; idx < (nb0 - nc) * CH_NB; idx += 256) Ls[nc * CH_NB + idx] = 0.0;
+    for (int idx = tid; idx < (nb0 - nc) * CH_NB; idx += 256) Ls[(nc + (idx >> 7)) * MF_LP + (idx & 127)] = 0.0;
     if (tid < CH_NB) dv[tid] = (tid < nc) ? d.dinv[col0 + tid] : 1.0;
     mbar_wait(bar, 0);
     __syncthreads();
@@ -338,7 +340,7 @@ mf_trsm_kernel(const MfDesc d, const int2* __restrict__ tasks, int ncmax) {
         const int lduc = d.ldu[c];
         __syncthreads();
         if (tid < ihi - ilo) srow[tid] = rl[ilo + tid] - (nc + i0);   // slab-local row (ihi - ilo <= 64)
-        if (tid < cutc) scol[tid] = rl[tid] * MF_TR_ROWS;             // target column offset in Xs
+        if (tid < cutc) scol[tid] = rl[tid] * MF_XP;                  // target column offset in Xs
         __syncthreads();
         const int ni = ihi - ilo;
         // lane owns child rows ilo + lane, ilo + lane + 32; four child columns per step
@@ -363,11 +365,11 @@ mf_trsm_kernel(const MfDesc d, const int2* __restrict__ tasks, int ncmax) {
         }
     }
     __syncthreads();
-    trsm_slab_smem(Ls, Xs, dv, nc, nrows);
+    trsm_slab_smem_t<MF_LP, MF_XP, true>(Ls, Xs, dv, nc, nrows);
     fence_proxy_async();
     __syncthreads();
     if (warp == 0) {
-        for (int p = lane; p < nc; p += 32) bulk_store_1d(slab_g + (long long)p * ld, Xs + p * MF_TR_ROWS, nrows16 * 8);
+        for (int p = lane; p < nc; p += 32) bulk_store_1d(slab_g + (long long)p * ld, Xs + p * MF_XP, nrows16 * 8);
         tma_store_commit_and_wait();
     }
 }
