@@ -109,9 +109,11 @@ def reference_arm(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic",
-        "config": {"workload": f"dense LP m={m} n={n} normal-equation step (BASELINE config 2)",
+        "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"dense LP m={m} n={n} primal-dual affine scaling iteration "
+                               f"(BASELINE config {2 if m == 8192 else 3 if m == 32768 else 'custom'})",
+                   "parallelism": "host CPU threads (restated reference path: scale + dsyrk + dpotrf + dpotrs + 5 gemv)",
                    "sample": f"m={sm} n={sn}", "l2": "inputs larger than L2"},
         "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port",
                          "sample": f"{args.steps} steps of scale+dsyrk+dpotrf+dpotrs+5 gemv at m={sm} n={sn} "
