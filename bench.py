@@ -10,7 +10,8 @@ F(m,n) = m^2 n + m^3/3 + 2 m^2 + 10 m n.
   value     device-resident iterations (state on the GPU, scalars only cross PCIe)
   e2e       the reference-facing C-ABI call nes_kkt_newton with HOST (pinned) vectors: H2D of
             l,u,w,z,e,f,h,g and D2H of dw,dx,dy,dz inside the timed region, A resident
-  roofline  the formation kernel (dmma_nt_kernel<true>): m^2 n flops / its CUDA-event time, against
+  roofline  the formation kernel (dmma_nt_kernel<true>): its flops (m^2 n minus the trailing columns whose
+            formation is deferred into the factorization, nes_get_form_flops) / its CUDA-event time, against
             the measured FP64 DMMA peak (tools/dmma_bench.cu -> profiles/, MEASURED_PEAKS.json has no
             FP64 entry)
   cpu_baseline / --impl reference: oracle/baseline.py on the host cores (restated reference CPU path)
@@ -225,6 +226,9 @@ def main():
         clocks = sampler.stop()
         launches = c.launches - launches0
         stage = c.timing()
+        # flops of the formation launch the "form" stage times: m^2 n, minus the d^2 n of the trailing d
+        # columns of M when the library forms those inside the factorization stage (dense_chol.cu)
+        form_flops = c.form_flops
 
         # ---- e2e: reference-facing call with pinned host vectors --------------------------------
         names = ("l", "u", "w", "z")
@@ -294,7 +298,7 @@ def main():
     form_ms, form_cnt = stage["form"]
     roof = None
     if form_cnt:
-        ach = (float(m) * m * n) / world / (form_ms / form_cnt * 1e-3) / 1e12  # this rank's share
+        ach = form_flops / world / (form_ms / form_cnt * 1e-3) / 1e12  # this rank's share
         roof = {"bound": "tensor", "kernel": "dmma_nt_kernel<true> (fused scale+SYRK)",
                 "achieved": ach, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": ach / FP64_DMMA_PEAK_TFLOPS,
@@ -305,6 +309,8 @@ def main():
                 "traffic_unit": "bytes per launch (DRAM read+write, ncu)",
                 "peak_source": "own DMMA issue-rate microbenchmark (tools/dmma_bench.cu, profiles/r01_dmma_peak_and_syrk_v0.log); "
                                "MEASURED_PEAKS.json has no FP64 figure",
+                "launch_flops": form_flops / world,
+                "deferred_formation_flops": float(m) * m * n - form_flops,
                 "step_frac_of_peak": value / world / 1e3 / FP64_DMMA_PEAK_TFLOPS}
     line = {
         "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,

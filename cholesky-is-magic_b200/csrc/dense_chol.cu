@@ -15,8 +15,11 @@
 //   dmma_nt_kernel      updates C -= P P' on the FP64 tensor cores (lower tiles only)
 // Panels are grouped into outer panels (512 / 256 / 128 columns by remaining size) with look-ahead: see
 // dense_cholesky() below; the multi-GPU variant is dense_cholesky_dist_steps().
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <vector>
 
 #include "dmma_nt.cuh"
 #include "nes_internal.h"
@@ -123,9 +126,164 @@ static int chol_configure(nes_ctx* c) {
     return 0;
 }
 
-int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L) {
-    StageTimer timer(c, NES_STAGE_FORM);
+// Outer panel width by remaining size R = m - j0 (see dense_cholesky): while the trailing matrix is large
+// the updates bound the step (wide panels: fewer passes over C, K = 512 / 256), once it is small the panel
+// chain does (128 columns: no inner narrow updates).  NES_CHOL_SCHED="t512,t256" overrides the thresholds.
+static int chol_width(int m, int j0) {
+    static int t512 = -1, t256 = -1;
+    if (t512 < 0) {
+        t512 = 6144;
+        t256 = 3072;
+        if (const char* e = getenv("NES_CHOL_SCHED")) sscanf(e, "%d,%d", &t512, &t256);
+    }
+    const int R = m - j0;
+    const int w = R > t512 ? 512 : (R > t256 ? 256 : CH_NB);
+    return R < w ? R : w;
+}
+
+static bool chol_lookahead(const nes_ctx* c, int m) { return c->stream_aux && m > 1024; }
+
+// ---- deferred formation (single GPU, experimental, OFF by default) ---------------------------------
+// Once the trailing matrix is small the factorization is bound by its panel chain (diagonal block + TRSM,
+// ~65 us per 128 columns) and most SMs idle, while the formation before it is pure tensor-core work.  With
+// NES_CHOL_DEFER=d the last d columns of M are not formed up front: the region starts at zero and block
+// column J+2 ("strip") receives A diag(theta) A' on the side stream during step J, between the
+// rest-updates, which also accumulate into it (sums commute; everything that writes a tile is ordered on
+// one stream).  A strip has fewer tiles than the GPU has SMs, so every tile is cut into k-ranges that are
+// summed in a fixed order by the last CTA to arrive (dmma_nt split_all: bitwise reproducible).  The strip
+// kernels leave NES_CHOL_RESERVE SMs (default 8) to the panel chain on the high-priority stream.
+// Measured on B200 at m=8192, n=16384 (tools/probe_defer.py, NES_CHOL_TRACE timelines in DESIGN.md):
+// form+factor 41.4 ms without, 41.8 / 42.6 ms with d = 2048 / 4096.  The strips run at 80-93% of the
+// up-front kernel's rate (k-split reduction, reserved SMs) and serialise with the rest-updates on the side
+// stream, which costs more than the ~3.8 ms of idle SM time they fill.  Kept as an opt-in path with its
+// parity tests; the default (0) forms everything up front.
+static int defer_env(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
+static int defer_plan(nes_ctx* c, nes_factor* L, size_t n) {
+    if (L->defer_planned && L->defer_n == n) return 0;
+    cudaStreamSynchronize(c->stream);
+    dev_free(c, L->d_defer_tiles);
+    dev_free(c, L->d_defer_ws);
+    dev_free(c, L->d_defer_counters);
+    L->d_defer_tiles = nullptr;
+    L->d_defer_ws = nullptr;
+    L->d_defer_counters = nullptr;
+    L->defer_strips.clear();
+    L->defer_split = 0;
+    L->defer_ntiles_a = 0;
+    L->defer_planned = 1;
+    L->defer_n = n;
+    const int m = (int)L->m;
+    const int defer = defer_env("NES_CHOL_DEFER", 0);
+    const int min_m = defer_env("NES_CHOL_DEFER_MIN_M", 5120);
+    if (c->nranks > 1 || defer <= 0 || m < min_m || !chol_lookahead(c, m)) return 0;
+    std::vector<int> bounds;  // panel boundaries p_0 = 0 < p_1 < ... < m
+    for (int j0 = 0; j0 < m; j0 += chol_width(m, j0)) bounds.push_back(j0);
+    // the first deferred block column must be the "J+2" of some step: p_k with k >= 2
+    int split = 0;
+    for (size_t k = 2; k < bounds.size(); ++k)
+        if (bounds[k] >= m - defer) {
+            split = bounds[k];
+            break;
+        }
+    if (split <= 0) return 0;
+    const int tm = (m + NT_BM - 1) / NT_BM, cs = split / NT_BM;
+    std::vector<int2> tiles;
+    // up-front tiles (block columns < cs) in the band order of nt_tile_coords: bands of NT_BAND tile rows,
+    // each walked column by column, so a wave of CTAs shares operand rows through L2
+    for (int r0 = 0; r0 < tm; r0 += NT_BAND) {
+        const int r1 = std::min(tm, r0 + NT_BAND);
+        for (int bj = 0; bj < std::min(r1, cs); ++bj)
+            for (int bi = std::max(r0, bj); bi < r1; ++bi) tiles.push_back(make_int2(bi, bj));
+    }
+    L->defer_ntiles_a = (int)tiles.size();
+    const int kchunks = ((int)n + NT_BK - 1) / NT_BK;
+    const int reserve = defer_env("NES_CHOL_RESERVE", 8);
+    const int G = std::max(1, c->num_sms - std::max(0, reserve));
+    size_t ws_tiles = 0;
+    int max_tiles = 0;
+    for (size_t k = 0; k < bounds.size(); ++k) {
+        if (bounds[k] < split) continue;
+        nes_factor::DeferStrip st;
+        st.col0 = bounds[k];
+        st.first = (int)tiles.size();
+        const int c1 = std::min(m, st.col0 + chol_width(m, st.col0));
+        for (int bj = st.col0 / NT_BM; bj * NT_BM < c1; ++bj)
+            for (int bi = bj; bi < tm; ++bi) tiles.push_back(make_int2(bi, bj));
+        st.ntiles = (int)tiles.size() - st.first;
+        // k-ranges per tile: the count that fills whole waves of the G CTAs best (smallest on ties)
+        int best = 1;
+        double best_eff = 0.0;
+        const int smax = std::max(1, std::min(16, kchunks / 8));
+        for (int sp = 1; sp <= smax; ++sp) {
+            const double x = (double)st.ntiles * sp / G;
+            const double eff = x / std::ceil(x);
+            if (eff > best_eff + 1e-9) {
+                best_eff = eff;
+                best = sp;
+            }
+        }
+        st.split = best;
+        if (st.split > 1) ws_tiles = std::max(ws_tiles, (size_t)st.ntiles * st.split);
+        max_tiles = std::max(max_tiles, st.ntiles);
+        L->defer_strips.push_back(st);
+    }
+    L->d_defer_tiles = static_cast<int2*>(dev_alloc(c, (tiles.size() + 1) * sizeof(int2)));
+    if (!L->d_defer_tiles) return c->status;
+    NES_TRY(upload(c, L->d_defer_tiles, tiles.data(), tiles.size() * sizeof(int2)));
+    if (ws_tiles > 0) {
+        L->d_defer_ws = static_cast<double*>(dev_alloc(c, ws_tiles * NT_BM * NT_BN * sizeof(double)));
+        L->d_defer_counters = static_cast<int*>(dev_alloc(c, (max_tiles + 1) * sizeof(int)));
+        if (!L->d_defer_ws || !L->d_defer_counters) return c->status;
+        NES_CUDA(c, cudaMemsetAsync(L->d_defer_counters, 0, (max_tiles + 1) * sizeof(int), c->stream));
+    }
+    L->defer_split = split;
+    return 0;
+}
+
+// strip starting at column col0: M[col0.., col0..col0+w) += A diag(theta) A' on the side stream
+static int defer_form_strip(nes_ctx* c, const nes_matrix* A, nes_factor* L, int col0) {
+    const nes_factor::DeferStrip* st = nullptr;
+    for (const auto& s : L->defer_strips)
+        if (s.col0 == col0) st = &s;
+    if (!st) return fail(c, NES_ERR_INVALID, "deferred formation: no strip at column %d", col0);
     const MatrixBase* b = A->base;
+    NtArgs a{};
+    a.C = L->d_M;
+    a.ldc = (long long)L->ld;
+    a.M = a.N = (int)L->m;
+    a.K = (int)b->n;
+    a.scale = A->d_theta;
+    a.alpha = 1.0;
+    a.beta = 1.0;
+    a.same_operand = 1;
+    a.tile_list = L->d_defer_tiles + st->first;
+    a.ntiles = st->ntiles;
+    if (st->split > 1) {
+        a.split_all = 1;
+        a.split_s = st->split;
+        a.split_ws = L->d_defer_ws;
+        a.split_counters = L->d_defer_counters;
+    }
+    const int G = std::max(1, c->num_sms - std::max(0, defer_env("NES_CHOL_RESERVE", 8)));
+    cudaError_t e = nt_launch(b->map, b->map, a, G, c->stream_aux);
+    ++c->launches;
+    if (e != cudaSuccess)
+        return fail(c, NES_ERR_CUDA, "deferred formation launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L, bool allow_defer) {
+    const MatrixBase* b = A->base;
+    int split = 0;
+    if (allow_defer && c->nranks == 1) {
+        NES_TRY(defer_plan(c, L, b->n));
+        split = L->defer_split;
+    }
+    StageTimer timer(c, NES_STAGE_FORM);
     NtArgs a{};
     a.C = L->d_M;
     a.ldc = (long long)L->ld;
@@ -143,10 +301,23 @@ int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L) {
         a.ntiles = L->ntiles_owned;
         a.lower = 0;
     }
+    {
+        const double dm = (double)b->m, dd = (double)(b->m - (size_t)split);
+        c->form_flops = (split > 0 ? dm * dm - dd * dd : dm * dm) * (double)b->n;
+    }
+    if (split > 0) {
+        // block columns >= split start at zero and are formed inside dense_cholesky
+        const size_t d = b->m - (size_t)split;
+        NES_CUDA(c, cudaMemset2DAsync(L->d_M + split + (size_t)split * L->ld, L->ld * sizeof(double), 0,
+                                      d * sizeof(double), d, c->stream));
+        a.tile_list = L->d_defer_tiles;
+        a.ntiles = L->defer_ntiles_a;
+        a.lower = 0;
+    }
     // balance the partial last wave of the static tile round-robin (6% at m=8192 on 148 SMs)
     {
         const int tm = (a.M + NT_BM - 1) / NT_BM;
-        const int ntiles = (c->nranks > 1) ? L->ntiles_owned : tm * (tm + 1) / 2;
+        const int ntiles = a.tile_list ? a.ntiles : tm * (tm + 1) / 2;
         const int grid = ntiles < c->num_sms ? ntiles : c->num_sms;
         int sr = 0, ss = 0;
         nt_plan_split(ntiles, (a.K + NT_BK - 1) / NT_BK, grid, &sr, &ss);
@@ -372,7 +543,53 @@ static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L) {
     return 0;
 }
 
-int dense_cholesky(nes_ctx* c, nes_factor* L) {
+// NES_CHOL_TRACE=1: CUDA-event timeline of the single-GPU factorization (which kernel ran when, on which
+// stream), printed to stderr after a synchronisation.  Debugging aid; off by default.
+struct CholTrace {
+    struct Span {
+        const char* what;
+        int col;
+        cudaEvent_t a, b;
+    };
+    bool on = false;
+    cudaEvent_t base = nullptr;
+    std::vector<Span> spans;
+    void begin(cudaStream_t s) {
+        on = getenv("NES_CHOL_TRACE") != nullptr;
+        if (!on) return;
+        cudaEventCreate(&base);
+        cudaEventRecord(base, s);
+    }
+    int open(const char* what, int col, cudaStream_t s) {
+        if (!on) return -1;
+        Span sp{what, col, nullptr, nullptr};
+        cudaEventCreate(&sp.a);
+        cudaEventCreate(&sp.b);
+        cudaEventRecord(sp.a, s);
+        spans.push_back(sp);
+        return (int)spans.size() - 1;
+    }
+    void close(int id, cudaStream_t s) {
+        if (id >= 0) cudaEventRecord(spans[id].b, s);
+    }
+    void dump(cudaStream_t s) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        for (auto& sp : spans) {
+            float t0 = 0.f, t1 = 0.f;
+            cudaEventElapsedTime(&t0, base, sp.a);
+            cudaEventElapsedTime(&t1, base, sp.b);
+            fprintf(stderr, "chol-trace %-6s col %5d  %9.3f -> %9.3f  (%7.3f ms)\n", sp.what, sp.col, t0, t1,
+                    t1 - t0);
+            cudaEventDestroy(sp.a);
+            cudaEventDestroy(sp.b);
+        }
+        cudaEventDestroy(base);
+        spans.clear();
+    }
+};
+
+int dense_cholesky(nes_ctx* c, nes_factor* L, const nes_matrix* A) {
     StageTimer timer(c, NES_STAGE_FACTOR);
     NES_TRY(chol_configure(c));
     const int m = (int)L->m;
@@ -388,20 +605,10 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
         // updates with 147 SMs idle.  Hazards: (1) of step J+1 touches columns the rest-update J writes,
         // so `stream` waits for ev_update; rest-update J+1 needs panel J+1 (ev_panel) and follows
         // rest-update J in stream order.
-        // Panel width by remaining size R = m - j0: while the trailing matrix is large the updates bound
-        // the step (wide panels: fewer passes over C, K = 512 / 256), once it is small the panel chain
-        // does (128 columns: no inner narrow updates).  NES_CHOL_SCHED="t512,t256" overrides the thresholds.
-        static int t512 = -1, t256 = -1;
-        if (t512 < 0) {
-            t512 = 6144;
-            t256 = 3072;
-            if (const char* e = getenv("NES_CHOL_SCHED")) sscanf(e, "%d,%d", &t512, &t256);
-        }
-        auto width = [&](int j0) {
-            const int R = m - j0;
-            const int w = R > t512 ? 512 : (R > t256 ? 256 : CH_NB);
-            return R < w ? R : w;
-        };
+        // Panel width by remaining size: chol_width().  Deferred formation (defer_plan): block column J+2
+        // is formed on the side stream at the head of step J, before the rest-update that needs panel J.
+        auto width = [&](int j0) { return chol_width(m, j0); };
+        const int defer = (A && L->defer_planned) ? L->defer_split : 0;
         auto factor_panel = [&](int j0, int jbo) -> int {
             for (int i0 = j0; i0 < j0 + jbo; i0 += CH_NB) {
                 const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
@@ -419,7 +626,13 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
             }
             return 0;
         };
-        const bool lookahead = c->stream_aux && m > 1024;
+        const bool lookahead = chol_lookahead(c, m);
+        CholTrace tr;
+        tr.begin(c->stream);
+        if (defer > 0) {  // the side stream starts after the up-front formation and the zero fill
+            NES_CUDA(c, cudaEventRecord(c->ev_panel, c->stream));
+            NES_CUDA(c, cudaStreamWaitEvent(c->stream_aux, c->ev_panel, 0));
+        }
         int jbo = width(0);
         NES_TRY(factor_panel(0, jbo));
         bool pending_update = false;
@@ -437,18 +650,30 @@ int dense_cholesky(nes_ctx* c, nes_factor* L) {
             const int r1 = r0 + jbn;
             NES_CUDA(c, cudaEventRecord(c->ev_panel, c->stream));                  // panel J is final
             if (pending_update) NES_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_update, 0));
+            int t = tr.open("colupd", r0, c->stream);
             NES_TRY(chol_update(c, L, r0, r0, m - r0, jbn, j0, jbo, 0));           // (1) block column J+1
+            tr.close(t, c->stream);
             if (r1 < m) {                                                          // (2) the rest, side stream
+                if (defer > 0 && r1 >= defer) {
+                    t = tr.open("strip", r1, c->stream_aux);
+                    NES_TRY(defer_form_strip(c, A, L, r1));
+                    tr.close(t, c->stream_aux);
+                }
                 NES_CUDA(c, cudaStreamWaitEvent(c->stream_aux, c->ev_panel, 0));
+                t = tr.open("rest", r1, c->stream_aux);
                 NES_TRY(chol_update(c, L, r1, r1, m - r1, m - r1, j0, jbo, 1, c->stream_aux, true));
+                tr.close(t, c->stream_aux);
                 NES_CUDA(c, cudaEventRecord(c->ev_update, c->stream_aux));
                 pending_update = true;
             }
+            t = tr.open("panel", r0, c->stream);
             NES_TRY(factor_panel(r0, jbn));
+            tr.close(t, c->stream);
             j0 = r0;
             jbo = jbn;
         }
         if (pending_update) NES_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_update, 0));
+        tr.dump(c->stream);
     }
     if (L->d_Winv) {  // block inverses for the solve phase (off the factorization's critical path)
         trtri_diag_kernel<<<(m + CH_NB - 1) / CH_NB, CH_NB, TI_SMEM, c->stream>>>(L->d_M, ld, m, L->d_dinv,

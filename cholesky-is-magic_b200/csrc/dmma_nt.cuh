@@ -66,6 +66,7 @@ struct NtArgs {
     // into `split_s` k-ranges each; partial tiles go to split_ws and the last CTA to arrive sums them
     // in k-range order (fixed order => bitwise reproducible, no floating-point atomics).
     int split_r, split_s;
+    int split_all;        // every tile is split (launches with fewer tiles than SMs); split_r is then ntiles
     double* split_ws;     // split_r * split_s * 128*128 doubles
     int* split_counters;  // split_r ints, zero on entry, reset to zero by the last arriver
     // explicit tile list (multi-GPU ownership): tile t is (tile_list[t].x, tile_list[t].y) in absolute
@@ -333,18 +334,33 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
             __syncthreads();
             if (!s_last) continue;
             __threadfence();
-            const double* base = p.split_ws + (size_t)slot * p.split_s * (NT_BM * NT_BN);
+            // k-range order for every element (fixed => reproducible); 16 independent loads per batch so
+            // the reduction is not a chain of dependent L2 round trips
+            const double* base = p.split_ws + (size_t)slot * p.split_s * (NT_BM * NT_BN) + threadIdx.x;
 #pragma unroll
             for (int i = 0; i < 8; ++i)
 #pragma unroll
-                for (int j = 0; j < 4; ++j)
+                for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+            for (int sp = 0; sp < p.split_s; ++sp) {
+                const double* q = base + (size_t)sp * (NT_BM * NT_BN);
 #pragma unroll
-                    for (int c = 0; c < 2; ++c) {
-                        double sum = 0.0;
-                        const double* q = base + ((i * 4 + j) * 2 + c) * NT_THREADS + threadIdx.x;
-                        for (int sp = 0; sp < p.split_s; ++sp) sum += __ldcg(q + (size_t)sp * (NT_BM * NT_BN));
-                        acc[i][j][c] = sum;
-                    }
+                for (int i = 0; i < 8; i += 2) {
+                    double v[2][4][2];
+#pragma unroll
+                    for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c)
+                                v[ii][j][c] = __ldcg(q + (((i + ii) * 4 + j) * 2 + c) * NT_THREADS);
+#pragma unroll
+                    for (int ii = 0; ii < 2; ++ii)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+#pragma unroll
+                            for (int c = 0; c < 2; ++c) acc[i + ii][j][c] += v[ii][j][c];
+                }
+            }
         }
 
         // epilogue: registers -> global (column-major).  Lane holds rows g (+8i), cols 2*t4, 2*t4+1.
@@ -465,9 +481,14 @@ inline cudaError_t nt_launch(const CUtensorMap& mapX, const CUtensorMap& mapY, N
         a.ntiles = a.lower ? tm * (tm + 1) / 2 : tm * tn;
     }
     if (a.ntiles <= 0) return cudaSuccess;
-    const int grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
-    if (a.split_ws == nullptr || a.split_counters == nullptr) a.split_r = a.split_s = 0;
-    if (a.split_r > 0) {
+    int grid = a.ntiles < max_ctas ? a.ntiles : max_ctas;
+    if (a.split_ws == nullptr || a.split_counters == nullptr || a.split_s < 2)
+        a.split_r = a.split_s = a.split_all = 0;
+    if (a.split_all) {
+        a.split_r = a.ntiles;
+        const long long items = (long long)a.ntiles * a.split_s;
+        grid = items < max_ctas ? (int)items : max_ctas;
+    } else if (a.split_r > 0) {
         // caller proposes; validate against this grid
         const int r = a.ntiles % grid;
         if (r != a.split_r || a.split_s < 2 || a.split_r * a.split_s > grid) a.split_r = a.split_s = 0;

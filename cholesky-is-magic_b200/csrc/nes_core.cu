@@ -345,6 +345,7 @@ int nes_timing_get(nes_ctx* c, int stage, double* ms, long long* count) {
 }
 
 long long nes_get_launch_count(const nes_ctx* c) { return c ? c->launches : 0; }
+double nes_get_form_flops(const nes_ctx* c) { return c ? c->form_flops : 0.0; }
 int nes_set_ordering_leaf(nes_ctx* c, int leaf) {
     if (!c) return 0;
     const int old = c->nd_leaf;

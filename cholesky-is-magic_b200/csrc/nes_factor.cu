@@ -16,8 +16,8 @@ int factorize_dev(nes_ctx* c, nes_matrix* A, nes_factor* L) {
     c->status = 0;  // the Lisp does cholmod_set_status 0 before every factorize (:418, :511, :541)
     if (!L->dense) return sparse_factorize(c, A, L);
     L->factorized = 0;
-    NES_TRY(dense_form_normal(c, A, L));
-    return dense_cholesky(c, L);
+    NES_TRY(dense_form_normal(c, A, L, true));
+    return dense_cholesky(c, L, A);
 }
 
 int solve_dev(nes_ctx* c, nes_factor* L, double* d_x) {
@@ -131,6 +131,9 @@ static void nes_free_factor_impl(nes_factor* L, nes_ctx* c) {
     dev_free(c, L->d_Winv);
     dev_free(c, L->d_tile_list);
     dev_free(c, L->d_stage);
+    dev_free(c, L->d_defer_tiles);
+    dev_free(c, L->d_defer_ws);
+    dev_free(c, L->d_defer_counters);
 }
 
 int nes_free_factor(nes_factor** L, nes_ctx* c) {

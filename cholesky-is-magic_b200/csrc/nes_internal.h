@@ -41,6 +41,7 @@ struct nes_ctx {
     cudaEvent_t ev_panel = nullptr, ev_update = nullptr, ev_aux = nullptr;
     char err[512] = {0};
     long long launches = 0;
+    double form_flops = 0;  // algorithmic flops of the last up-front formation launch (nes_get_form_flops)
 
     // multi-GPU (one process per GPU; 1 x Q block-cyclic column distribution of M, see nes_dist.cu)
     int nranks = 1, rank = 0;
@@ -188,15 +189,34 @@ struct nes_factor {
     int ntiles_owned = 0;
     std::vector<int> tile_first;
     double* d_stage = nullptr;   // packed panel for ncclBroadcast (+ dinv tail)
+    // deferred formation (single GPU, dense_chol.cu): the tiles of M in block columns >= defer_split are
+    // not formed up front but strip by strip inside the factorization, where they fill the SMs the
+    // panel chain leaves idle.  Planned once per (m, n); 0 = everything is formed up front.
+    struct DeferStrip {
+        int col0;    // first column of the strip (a panel boundary)
+        int first;   // its tiles: d_defer_tiles[first .. first + ntiles)
+        int ntiles;
+        int split;   // k-ranges per tile (1 = whole tiles)
+    };
+    int defer_planned = 0;
+    size_t defer_n = 0;
+    int defer_split = 0;
+    int defer_ntiles_a = 0;          // up-front tiles: d_defer_tiles[0 .. defer_ntiles_a)
+    int2* d_defer_tiles = nullptr;
+    double* d_defer_ws = nullptr;    // partial tiles of the k-split strips
+    int* d_defer_counters = nullptr; // arrival counters (zero between launches)
+    std::vector<DeferStrip> defer_strips;
 };
 
 namespace nes {
 
 // ---- kernels / stage drivers (one per .cu) ------------------------------------------------------
 // K1: M(lower) = A diag(theta) A'  (dense_form.cu)
-int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L);
+// allow_defer: leave the block columns >= L->defer_split to dense_cholesky (which then needs A)
+int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L, bool allow_defer = false);
 // K2: in-place blocked Cholesky of L->d_M (dense_chol.cu); sets c->status / c->minor
-int dense_cholesky(nes_ctx* c, nes_factor* L);
+// A != nullptr: the deferred block columns of M are still to be formed from A (see dense_form_normal)
+int dense_cholesky(nes_ctx* c, nes_factor* L, const nes_matrix* A = nullptr);
 // K5: x <- (L L')^{-1} x, x device vector of length m (dense_solve.cu)
 int dense_solve_inplace(nes_ctx* c, nes_factor* L, double* d_x);
 // K6: y <- alpha op(A diag(s)) x + beta y on device vectors (gemv.cu); handles dense and CSC

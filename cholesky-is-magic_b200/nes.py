@@ -114,6 +114,7 @@ def _prototypes(lib):
     fn("nes_timing_reset", C.c_int, _vp)
     fn("nes_timing_get", C.c_int, _vp, C.c_int, _dp, C.POINTER(C.c_longlong))
     fn("nes_get_launch_count", C.c_longlong, _vp)
+    fn("nes_get_form_flops", C.c_double, _vp)
     fn("nes_comm_unique_id", C.c_int, C.c_char_p)
     fn("nes_comm_init", C.c_int, _vp, C.c_int, C.c_int, C.c_char_p)
     fn("nes_comm_finalize", C.c_int, _vp)
@@ -304,6 +305,11 @@ class Common:
     @property
     def launches(self):
         return self.lib.nes_get_launch_count(self.ptr)
+
+    @property
+    def form_flops(self):
+        """Algorithmic flops of the last formation launch timed as stage "form"."""
+        return self.lib.nes_get_form_flops(self.ptr)
 
 
 class Matrix:

@@ -299,6 +299,9 @@ int nes_timing_reset(nes_ctx* c);
 /* accumulated milliseconds and number of timed intervals for a stage since the last reset */
 int nes_timing_get(nes_ctx* c, int stage, double* ms, long long* count);
 long long nes_get_launch_count(const nes_ctx* c);     /* kernels launched by this context */
+/* algorithmic flops of the last dense formation launch timed as NES_STAGE_FORM: m^2 n, minus the d^2 n of
+ * the last d columns of M when their formation is deferred into the factorization stage (dense_chol.cu) */
+double nes_get_form_flops(const nes_ctx* c);
 /* whole-region device timing: nes_mark_begin records a CUDA event on the library's stream,
  * nes_mark_end records a second one, waits for it and returns the elapsed milliseconds. */
 int nes_mark_begin(nes_ctx* c);

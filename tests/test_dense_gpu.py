@@ -75,6 +75,52 @@ def test_cholesky_residual_and_solve(common, m, n):
     Ad.free()
 
 
+@pytest.mark.parametrize("m,n,defer", [(1536, 2048, 640), (1400, 1700, 512), (2048, 2304, 4096)])
+def test_deferred_formation_matches_upfront_formation(common, m, n, defer, monkeypatch):
+    """Opt-in path of dense_chol.cu (NES_CHOL_DEFER): the last columns of M are formed strip by strip
+    inside the factorization (k-split tiles, accumulated with the trailing updates).  Same gates as the
+    default path, and the two factors agree to rounding."""
+    rng = np.random.default_rng(m + n)
+    A = rng.random((m, n)) + np.eye(m, n)
+    s = np.sqrt(0.1 + 10 * rng.random(n))
+    b = rng.random(m)
+    M = ons.normal_matrix(A, s)
+    Ad = nes.Matrix.from_dense(common, A)
+    Ad.scale(s)
+    out = {}
+    for mode, env in (("plain", {"NES_CHOL_DEFER": "0"}),
+                      ("deferred", {"NES_CHOL_DEFER": str(defer), "NES_CHOL_DEFER_MIN_M": "0"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        L = nes.Factor(common, Ad)              # the plan is made at the first factorization
+        assert L.factorize(Ad)
+        deferred_cols = round(max(0.0, m * m - common.form_flops / n) ** 0.5)
+        assert (deferred_cols > 0) == (mode == "deferred"), (mode, deferred_cols)
+        Lh = L.to_dense()
+        assert relerr(Lh @ Lh.T, M) <= 1e-12
+        x = L.solve(b)
+        assert np.linalg.norm(M @ x - b) / np.linalg.norm(b) <= 1e-10
+        assert L.factorize(Ad)                  # bitwise reproducible (fixed summation order)
+        np.testing.assert_array_equal(L.to_dense(), Lh)
+        out[mode] = Lh
+        L.free()
+    assert relerr(out["deferred"], out["plain"]) <= 1e-11
+    Ad.free()
+
+
+def test_deferred_formation_reports_a_failed_pivot(common, monkeypatch):
+    monkeypatch.setenv("NES_CHOL_DEFER", "512")
+    monkeypatch.setenv("NES_CHOL_DEFER_MIN_M", "0")
+    rng = np.random.default_rng(9)
+    B = rng.random((1300, 1250))                # m > n: B B' singular, the pivot fails in the deferred part
+    Ad = nes.Matrix.from_dense(common, B)
+    L = nes.Factor(common, Ad)
+    L.factorize(Ad)
+    assert common.status == nes.NES_NOT_POSDEF and 1240 <= common.minor <= 1300
+    L.free()
+    Ad.free()
+
+
 def test_solve_dense_like_reference(common):
     """solve-dense (sparse-cholesky.lisp:409-431)."""
     rng = np.random.default_rng(11)

@@ -32,6 +32,14 @@ def test_config2_normal_equations_m8192_n16384(common):
     Ah = lpgen.dense_matrix(k, n, 0)           # first k rows of the generated matrix
     M = (Ah * s ** 2) @ Ah.T
     assert np.linalg.norm(Lh @ Lh.T - M) / np.linalg.norm(M) <= 1e-12
+    # and on the trailing block (last panels of the look-ahead schedule)
+    assert common.form_flops == float(m) * m * n
+    rows = np.arange(m - k, m, dtype=np.uint64)[:, None]
+    At = lpgen.dense_entry(0, rows, np.arange(n, dtype=np.uint64)[None, :])
+    At[np.arange(k), np.arange(m - k, m)] += 1.0
+    Mt = (At * s ** 2) @ At.T
+    Lt = L.to_dense()[m - k:, :]
+    assert np.linalg.norm(Lt @ Lt.T - Mt) / np.linalg.norm(Mt) <= 1e-12
     L.free()
     A.free()
 
