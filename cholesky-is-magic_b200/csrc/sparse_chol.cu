@@ -13,10 +13,11 @@
 //                     update matrices into it, in-smem Cholesky (potrf_block.cuh), write back
 //   mf_trsm_kernel    one CTA per 64-row slab of the rows below: slab to shared memory, extend-add,
 //                     X L' = B by substitution, write back
-//   mf_syrk_kernel    persistent, one CTA per SM, 128 x 128 tiles of the update matrix
-//                     U_s = -L21 L21' on the FP64 tensor cores (DMMA m8n8k4, operands by TMA from a
-//                     per-supernode tensor map, 3-stage mbarrier pipeline), then the extend-add of the
-//                     children's update matrices into the tile
+//   mf_syrk_kernel    persistent, two CTAs per SM, 128 x 64 tiles of the update matrix
+//                     U_s = -L21 L21' on the FP64 tensor cores (DMMA m8n8k4, operands by TMA from
+//                     per-supernode tensor maps, 2-stage mbarrier pipeline), then the extend-add of the
+//                     children's update matrices into the tile (one CTA's epilogue overlaps the other's
+//                     tensor work)
 // Extend-add is OWNER-COMPUTES: the CTA that owns a piece of the parent's front pulls the matching
 // sub-rectangle of every child's update matrix (children in ascending order, coalesced along the
 // child's columns, rows scattered through the parent-relative map), so there are no atomics and the
@@ -73,7 +74,8 @@ struct MfDesc {
     const int* nb0;
     const int* tbptr;
     const int* tb;
-    const CUtensorMap* maps;
+    const CUtensorMap* maps;    // per supernode block: 132 x 32 boxes
+    const CUtensorMap* maps68;  // 68 x 32 boxes (B operand of the 128 x 64 SYRK tiles)
     int* info;
     double dbound;
 };
@@ -103,7 +105,7 @@ struct Phase {
     std::vector<int> psplit, tsplit;    // per level: tasks [ptr, split) have nc <= 64, [split, next) are wider
     int* d_potrf = nullptr;             // supernode ids, level by level
     int2* d_trsm = nullptr;             // (supernode, 64-row slab)
-    int4* d_syrk = nullptr;             // (supernode, tile row, tile column, nc)
+    int4* d_syrk = nullptr;             // (supernode, tile row, column block of syrk_bn() columns, nc)
     std::vector<int> fptr, bptr;        // nlevels + 1 offsets into the solve task arrays
     int2* d_ftail = nullptr;            // forward sweep: (supernode, 512-row chunk of its rows below)
     int2* d_bdots = nullptr;            // backward sweep: (supernode, group of 16 columns)
@@ -374,32 +376,52 @@ mf_trsm_kernel(const MfDesc d, const int2* __restrict__ tasks, int ncmax) {
     }
 }
 
-// Update matrices of a level on the FP64 tensor cores.  Task = (supernode, tile row bi, tile column
-// bj <= bi, nc): U(bi, bj) = -L21[bi] L21[bj]' with K = nc <= 128, plus the children's contributions.
-// Same pipeline as dmma_nt_kernel (thread 0 doubles as the TMA producer, 8 DMMA warps of 64 x 32, 132-row
-// boxes so the fragment loads are conflict-free); the tensor map of the supernode's block comes from
-// a device array, rows past the block and columns past nc are zero-filled by TMA.
-// Extend-add happens IN REGISTERS: for every child the tile's 128 rows and 128 columns get an inverse
-// map in shared memory (tile row -> row of the child's update matrix, from the slab table of the
-// symbolic phase, no searching), and every lane gathers the child's entries that fall on its own
-// accumulator elements (independent loads, no read-modify-write of global memory, one store per element).
-constexpr int MF_SY_SMEM = NT_SMEM_BYTES + 2 * NT_BM * 4;
+// Update matrices of a level on the FP64 tensor cores.  Task = (supernode, tile row bi, column block cb,
+// nc): the 128 x BN tile U(128 bi.., BN cb..) = -L21[rows] L21[cols]' with K = nc <= 128, plus the
+// children's contributions; only tiles that touch the lower triangle are listed.
+// Same pipeline as dmma_nt_kernel (thread 0 doubles as the TMA producer, DMMA warps of 64 x 32, row
+// pitches 132 / 68 so the fragment loads are conflict-free); the tensor maps of the supernode's block
+// come from device arrays, rows past the block and columns past nc are zero-filled by TMA.
+// Extend-add happens IN REGISTERS: for every child the tile's rows and columns get an inverse map in
+// shared memory (tile row -> row of the child's update matrix, from the slab table of the symbolic
+// phase, no searching), and every lane gathers the child's entries that fall on its own accumulator
+// elements (independent loads, no read-modify-write of global memory, one store per element).
+// With K <= 128 a tile is 4 k-chunks of tensor work (18 us) followed by an epilogue of gathers and
+// stores that takes twice as long, during which the DMMA pipe of a one-CTA-per-SM kernel idles.  The
+// default is therefore BN = 64: 128 x 64 tiles, 4 warps, 2 stages (100 KB) -- TWO CTAs per SM, so one
+// CTA's epilogue overlaps the other's mainloop.  BN = 128 (8 warps, 3 stages, one CTA per SM) is kept
+// for comparison (NES_SYRK_TILE=128).
+template <int BN>
+struct SyrkCfg {
+    static constexpr int WN = BN / 32;                 // warps along the columns
+    static constexpr int WARPS = 2 * WN;
+    static constexpr int THREADS = 32 * WARPS;
+    static constexpr int BPITCH = BN + 4;              // 132 or 68: == 4 mod 16
+    static constexpr int B_BYTES = BPITCH * NT_BK * 8;
+    static constexpr int STAGE_BYTES = NT_TILE_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 128) ? 3 : 2;
+    static constexpr int SMEM = STAGES * STAGE_BYTES + 2 * STAGES * 8 + 16 + (NT_BM + BN) * 4 + 128;
+    static constexpr int CTAS_PER_SM = (BN == 128) ? 1 : 2;
+};
 
-__global__ void __launch_bounds__(NT_THREADS, 1)
+template <int BN>
+__global__ void __launch_bounds__(SyrkCfg<BN>::THREADS, SyrkCfg<BN>::CTAS_PER_SM)
 mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
+    using Cfg = SyrkCfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw) + 127) & ~static_cast<uintptr_t>(127));
-    uint64_t* full = reinterpret_cast<uint64_t*>(smem + NT_STAGES * NT_STAGE_BYTES);
-    uint64_t* empty = full + NT_STAGES;
-    int* inv_r = reinterpret_cast<int*>(empty + NT_STAGES + 2);
+    uint64_t* full = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+    uint64_t* empty = full + STAGES;
+    int* inv_r = reinterpret_cast<int*>(empty + STAGES + 2);
     int* inv_c = inv_r + NT_BM;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const bool is_producer = (threadIdx.x == 0);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < NT_STAGES; ++s) {
+        for (int s = 0; s < STAGES; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], NT_CONSUMER_WARPS);
+            mbar_init(&empty[s], Cfg::WARPS);
         }
         fence_mbar_init();
     }
@@ -417,18 +439,23 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
     }
     auto produce = [&]() {
         if (!p_valid) return;
-        const int st_i = p_it % NT_STAGES;
-        const uint32_t ph = (p_it / NT_STAGES) & 1;
+        const int st_i = p_it % STAGES;
+        const uint32_t ph = (p_it / STAGES) & 1;
         mbar_wait(&empty[st_i], ph ^ 1);
-        const bool diag = (pt.y == pt.z);
-        uint8_t* st = smem + st_i * NT_STAGE_BYTES;
-        mbar_expect_tx(&full[st_i], diag ? NT_TILE_BYTES : 2 * NT_TILE_BYTES);
+        const int col0 = pt.z * BN;
+        const bool diag = (col0 / NT_BM == pt.y);  // the column block lies inside the row tile: one load
+        uint8_t* st = smem + st_i * Cfg::STAGE_BYTES;
+        mbar_expect_tx(&full[st_i], diag ? NT_TILE_BYTES : NT_TILE_BYTES + Cfg::B_BYTES);
         const CUtensorMap* mp = d.maps + pt.x;
-        if (p_kc == 0) fence_tensormap_acquire(mp);
+        const CUtensorMap* mpb = (BN == 128 ? d.maps : d.maps68) + pt.x;
+        if (p_kc == 0) {
+            fence_tensormap_acquire(mp);
+            if (BN != 128) fence_tensormap_acquire(mpb);
+        }
         // (the box must start on a 16-byte boundary: an odd row coordinate of an 8-byte type is an illegal
         // instruction, measured with tools/tma_gmem_probe.cu -- the layout keeps nb0 a multiple of 32)
         tma_load_2d(st, mp, p_nb0 + pt.y * NT_BM, p_kc * NT_BK, &full[st_i]);
-        if (!diag) tma_load_2d(st + NT_TILE_BYTES, mp, p_nb0 + pt.z * NT_BN, p_kc * NT_BK, &full[st_i]);
+        if (!diag) tma_load_2d(st + NT_TILE_BYTES, mpb, p_nb0 + col0, p_kc * NT_BK, &full[st_i]);
         ++p_it;
         if (++p_kc >= p_kch) {
             p_task += gridDim.x;
@@ -442,18 +469,20 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
         }
     };
     if (is_producer)
-        for (int i = 0; i < NT_STAGES - 1; ++i) produce();
+        for (int i = 0; i < STAGES - 1; ++i) produce();
 
     const int g = lane >> 2, t4 = lane & 3;
-    const int wm = warp >> 2, wn = warp & 3;
+    const int wm = warp / Cfg::WN, wn = warp % Cfg::WN;
     const int a_off = t4 * NT_PITCH + wm * 64 + g;
-    const int b_off = t4 * NT_PITCH + wn * 32 + g;
     uint32_t it = 0;
     for (int t = blockIdx.x; t < ntasks; t += gridDim.x) {
         const int4 tk = tasks[t];
-        const int s = tk.x, bi = tk.y, bj = tk.z, nc = tk.w;
+        const int s = tk.x, bi = tk.y, col0 = tk.z * BN, nc = tk.w;
         const int kch = (nc + NT_BK - 1) / NT_BK;
-        const bool diag = (bi == bj);
+        const bool diag = (col0 / NT_BM == bi);
+        // B fragments: own tile (pitch BPITCH), or rows col0 - 128 bi .. of the A tile on diagonal tiles
+        const int bpitch = diag ? NT_PITCH : Cfg::BPITCH;
+        const int b_off = t4 * bpitch + (diag ? col0 - bi * NT_BM : 0) + wn * 32 + g;
         double acc[8][4][2];
 #pragma unroll
         for (int i = 0; i < 8; ++i)
@@ -462,10 +491,10 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
         for (int kc = 0; kc < kch; ++kc, ++it) {
             if (is_producer) produce();
             __syncwarp();
-            const int st_i = it % NT_STAGES;
-            const uint32_t ph = (it / NT_STAGES) & 1;
+            const int st_i = it % STAGES;
+            const uint32_t ph = (it / STAGES) & 1;
             mbar_wait(&full[st_i], ph);
-            const double* sA = reinterpret_cast<const double*>(smem + st_i * NT_STAGE_BYTES);
+            const double* sA = reinterpret_cast<const double*>(smem + st_i * Cfg::STAGE_BYTES);
             const double* sB = diag ? sA : sA + NT_PITCH * NT_BK;
             const double* ap = sA + a_off;
             const double* bp = sB + b_off;
@@ -475,7 +504,7 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) af[i] = ap[ks * 4 * NT_PITCH + i * 8];
 #pragma unroll
-                for (int j = 0; j < 4; ++j) bf[j] = bp[ks * 4 * NT_PITCH + j * 8];
+                for (int j = 0; j < 4; ++j) bf[j] = bp[ks * 4 * bpitch + j * 8];
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
@@ -485,24 +514,23 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
             if (lane == 0) mbar_arrive(&empty[st_i]);
         }
         const int nu = d.nr[s] - nc, ldu = d.ldu[s];
+        const int nslab = (nu + 63) >> 6;
         const int lr0 = wm * 64 + g;        // my rows inside the tile: lr0 + 8 i
         const int lc0 = wn * 32 + 2 * t4;   // my columns: lc0 + 8 j + c2
         // ---- extend-add in registers: acc holds +L21 L21', children are SUBTRACTED, the store negates
         for (int q = d.childptr[s]; q < d.childptr[s + 1]; ++q) {
             const int c = d.child[q];
             const int* tb = d.tb + d.tbptr[c];
-            const int jlo = tb[2 * bj], jhi = tb[min(2 * bj + 2, (nu + 63) >> 6)];
-            const int ilo = tb[2 * bi], ihi = tb[min(2 * bi + 2, (nu + 63) >> 6)];
+            const int jlo = tb[col0 >> 6], jhi = tb[min((col0 >> 6) + BN / 64, nslab)];
+            const int ilo = tb[2 * bi], ihi = tb[min(2 * bi + 2, nslab)];
             if (ihi <= ilo || jhi <= jlo) continue;  // uniform over the CTA
             const int* rl = d.rel + d.relptr[c];
             __syncthreads();  // the previous child's maps are no longer read
-            if (threadIdx.x < NT_BM) {
-                inv_r[threadIdx.x] = -1;
-                inv_c[threadIdx.x] = -1;
-            }
+            if (threadIdx.x < NT_BM) inv_r[threadIdx.x] = -1;
+            if (threadIdx.x < BN) inv_c[threadIdx.x] = -1;
             __syncthreads();
-            for (int i = ilo + (int)threadIdx.x; i < ihi; i += NT_THREADS) inv_r[rl[i] - nc - bi * NT_BM] = i;
-            for (int j = jlo + (int)threadIdx.x; j < jhi; j += NT_THREADS) inv_c[rl[j] - nc - bj * NT_BN] = j;
+            for (int i = ilo + (int)threadIdx.x; i < ihi; i += Cfg::THREADS) inv_r[rl[i] - nc - bi * NT_BM] = i;
+            for (int j = jlo + (int)threadIdx.x; j < jhi; j += Cfg::THREADS) inv_c[rl[j] - nc - col0] = j;
             __syncthreads();
             const double* Uc = d.U + d.uoff[c];
             const int lduc = d.ldu[c];
@@ -524,7 +552,7 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
         // ---- store U tile = -acc (whole tile inside the matrix; only i >= j is ever read)
         double* Us = d.U + d.uoff[s];
         const int row_base = bi * NT_BM + lr0;
-        const int col_base = bj * NT_BN + lc0;
+        const int col_base = col0 + lc0;
 #pragma unroll
         for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -540,6 +568,16 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
                 }
             }
     }
+}
+
+// column block width of mf_syrk_kernel: 64 (two CTAs per SM) unless NES_SYRK_TILE=128
+static int syrk_bn() {
+    static int v = 0;
+    if (v == 0) {
+        const char* e = getenv("NES_SYRK_TILE");
+        v = (e && atoi(e) == 128) ? 128 : 64;
+    }
+    return v;
 }
 
 // W_s = L_ss^-1 for the listed supernodes, one CTA each, thread j = column j (forward substitution).
@@ -773,7 +811,12 @@ static int sparse_configure(nes_ctx* c) {
     if (done) return 0;
     NES_CUDA(c, cudaFuncSetAttribute(mf_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mf_diag_smem(CH_NB)));
     NES_CUDA(c, cudaFuncSetAttribute(mf_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mf_tr_smem(CH_NB)));
-    NES_CUDA(c, cudaFuncSetAttribute(mf_syrk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_SY_SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_syrk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SyrkCfg<128>::SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_syrk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     SyrkCfg<64>::SMEM));
+    NES_CUDA(c, cudaFuncSetAttribute(mf_syrk_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                     cudaSharedmemCarveoutMaxShared));
     NES_CUDA(c, cudaFuncSetAttribute(mf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_TI_SMEM));
     done = true;
     return 0;
@@ -833,9 +876,10 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
                     if (!mine || (nc > 64) != (wide == 1)) continue;
                     potrf.push_back(s);
                     for (int k = 0; k * MF_TR_ROWS < nu; ++k) trsm.push_back(make_int2(s, k));
-                    const int tn = (nu + NT_BM - 1) / NT_BM;
-                    for (int bi = 0; bi < tn; ++bi)
-                        for (int bj = 0; bj <= bi; ++bj) syrk.push_back(make_int4(s, bi, bj, nc));
+                    const int tn = (nu + NT_BM - 1) / NT_BM, bn = syrk_bn();
+                    for (int bi = 0; bi < tn; ++bi)   // column blocks of width bn up to the end of the diagonal tile
+                        for (int cb = 0; cb * bn < std::min(nu, (bi + 1) * NT_BM); ++cb)
+                            syrk.push_back(make_int4(s, bi, cb, nc));
                     for (int k = 0; k * MS_FWD_ROWS < nu; ++k) ftail.push_back(make_int2(s, k));
                     if (nu > 0)
                         for (int k = 0; k * MS_BWD_COLS < nc; ++k) bdots.push_back(make_int2(s, k));
@@ -914,21 +958,24 @@ int sparse_analyze(nes_ctx* c, nes_matrix* A, nes_factor* L) {
 
     // one tensor map per supernode block (132 x 32 boxes, OOB rows / columns read as zero)
     {
-        std::vector<CUtensorMap> maps(ns);
+        std::vector<CUtensorMap> maps(2 * (size_t)ns);  // [0, ns): 132-row boxes, [ns, 2 ns): 68-row boxes
         for (int s = 0; s < ns; ++s) {
             const int nc = S.first[s + 1] - S.first[s];
             if (S.nr[s] == nc) {
                 memset(&maps[s], 0, sizeof(CUtensorMap));
+                memset(&maps[ns + s], 0, sizeof(CUtensorMap));
                 continue;
             }
-            if (make_operand_map(&maps[s], d.Lv + S.off[s], S.nb0[s] + S.nr[s] - nc, nc, S.ld[s]) != 0)
+            if (make_operand_map(&maps[s], d.Lv + S.off[s], S.nb0[s] + S.nr[s] - nc, nc, S.ld[s]) != 0 ||
+                make_operand_map(&maps[ns + s], d.Lv + S.off[s], S.nb0[s] + S.nr[s] - nc, nc, S.ld[s], 68, NT_BK) != 0)
                 return fail(c, NES_ERR_CUDA, "cuTensorMapEncodeTiled failed for supernode %d (%d x %d)", s, S.nr[s], nc);
         }
-        CUtensorMap* dm = static_cast<CUtensorMap*>(dev_alloc(c, (size_t)(ns + 1) * sizeof(CUtensorMap)));
+        CUtensorMap* dm = static_cast<CUtensorMap*>(dev_alloc(c, (2 * (size_t)ns + 1) * sizeof(CUtensorMap)));
         if (!dm) return c->status;
         sf->owned.push_back(dm);
-        NES_TRY(upload(c, dm, maps.data(), (size_t)ns * sizeof(CUtensorMap)));
+        NES_TRY(upload(c, dm, maps.data(), 2 * (size_t)ns * sizeof(CUtensorMap)));
         d.maps = dm;
+        d.maps68 = dm + ns;
     }
     c->anz = (double)S.anz;
     c->aatfl = S.aatfl;
@@ -989,8 +1036,15 @@ static int run_factor_phase(nes_ctx* c, SparseFactor* sf, int ph) {
         }
         const int ny = P.yptr[l + 1] - P.yptr[l];
         if (ny > 0) {
-            const int grid = ny < c->num_sms ? ny : c->num_sms;
-            mf_syrk_kernel<<<grid, NT_THREADS, MF_SY_SMEM, c->stream>>>(sf->d, P.d_syrk + P.yptr[l], ny);
+            if (syrk_bn() == 128) {
+                const int grid = ny < c->num_sms ? ny : c->num_sms;
+                mf_syrk_kernel<128><<<grid, SyrkCfg<128>::THREADS, SyrkCfg<128>::SMEM, c->stream>>>(
+                    sf->d, P.d_syrk + P.yptr[l], ny);
+            } else {
+                const int grid = ny < 2 * c->num_sms ? ny : 2 * c->num_sms;
+                mf_syrk_kernel<64><<<grid, SyrkCfg<64>::THREADS, SyrkCfg<64>::SMEM, c->stream>>>(
+                    sf->d, P.d_syrk + P.yptr[l], ny);
+            }
             MF_LAUNCHED(c, "mf_syrk_kernel");
         }
     }
