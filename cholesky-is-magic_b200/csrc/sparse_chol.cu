@@ -537,17 +537,28 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
             int ci[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) ci[i] = inv_r[lr0 + 8 * i];
+            // two batches of 32 independent loads (4 columns x 8 rows), then the subtractions: two memory
+            // round trips per child instead of one per column (entries outside the child contribute 0.0,
+            // which leaves the accumulator bit-identical)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int jh = 0; jh < 4; jh += 2) {
+                double v[2][2][8];
 #pragma unroll
-                for (int c2 = 0; c2 < 2; ++c2) {
-                    const int cj = inv_c[lc0 + 8 * j + c2];
-                    if (cj < 0) continue;
-                    const double* ucol = Uc + (long long)cj * lduc;
+                for (int jj = 0; jj < 2; ++jj)
 #pragma unroll
-                    for (int i = 0; i < 8; ++i)
-                        if (ci[i] >= cj) acc[i][j][c2] -= ucol[ci[i]];
-                }
+                    for (int c2 = 0; c2 < 2; ++c2) {
+                        const int cj = inv_c[lc0 + 8 * (jh + jj) + c2];
+                        const double* ucol = Uc + (long long)max(cj, 0) * lduc;
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) v[jj][c2][i] = (cj >= 0 && ci[i] >= cj) ? ucol[ci[i]] : 0.0;
+                    }
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj)
+#pragma unroll
+                    for (int c2 = 0; c2 < 2; ++c2)
+#pragma unroll
+                        for (int i = 0; i < 8; ++i) acc[i][jh + jj][c2] -= v[jj][c2][i];
+            }
         }
         // ---- store U tile = -acc (whole tile inside the matrix; only i >= j is ever read)
         double* Us = d.U + d.uoff[s];
