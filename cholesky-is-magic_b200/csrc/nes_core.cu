@@ -218,6 +218,9 @@ int nes_start(nes_ctx* c) {
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // lo = least urgent (numerically greatest)
     if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->stream_aux, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->stream_b, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_update, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_aux, cudaEventDisableTiming) != cudaSuccess) {
@@ -272,6 +275,11 @@ int nes_finish(nes_ctx* c) {
     if (c->ev_update) cudaEventDestroy(c->ev_update);
     if (c->ev_aux) cudaEventDestroy(c->ev_aux);
     c->ev_panel = c->ev_update = c->ev_aux = nullptr;
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
+    c->ev_fork = c->ev_join = nullptr;
+    if (c->stream_b) cudaStreamDestroy(c->stream_b);
+    c->stream_b = nullptr;
     if (c->stream_aux) cudaStreamDestroy(c->stream_aux);
     c->stream_aux = nullptr;
     if (c->stream) cudaStreamDestroy(c->stream);

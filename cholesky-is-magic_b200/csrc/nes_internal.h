@@ -39,6 +39,10 @@ struct nes_ctx {
     // panel J overlaps the factorization of panel J+1, which runs on `stream` at high priority)
     cudaStream_t stream_aux = nullptr;
     cudaEvent_t ev_panel = nullptr, ev_update = nullptr, ev_aux = nullptr;
+    // second high-priority stream: the narrow supernodes of a sparse level (potrf -> trsm) run beside the
+    // wide ones instead of in front of them (sparse_chol.cu: run_factor_phase)
+    cudaStream_t stream_b = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     char err[512] = {0};
     long long launches = 0;
     double form_flops = 0;  // algorithmic flops of the last up-front formation launch (nes_get_form_flops)

@@ -1020,12 +1020,34 @@ static int run_factor_phase(nes_ctx* c, SparseFactor* sf, int ph) {
     int trtri_done = 0;  // supernodes [0, trtri_done) of this phase's list have their inverse enqueued
     for (int l = 0; l < S.nlevels; ++l) {
         if (P.pptr[l + 1] == P.pptr[l]) continue;
+        // Narrow (nc <= 64) and wide supernodes launch separately (different shared-memory footprints) and
+        // do not depend on each other: when a level has both, the narrow chain potrf -> trsm runs on the
+        // second stream beside the wide chain and joins before the SYRK (the level's critical path is one
+        // potrf + one trsm instead of two of each; this is what bounds the narrow top of the tree).
+        static const bool fork_off = getenv("NES_SPARSE_NO_FORK") != nullptr;  // comparison runs
+        const bool fork = c->stream_b && !fork_off && P.psplit[l] > P.pptr[l] && P.pptr[l + 1] > P.psplit[l] &&
+                          !sparse_sync_debug();
+        if (fork) {
+            NES_CUDA(c, cudaEventRecord(c->ev_fork, c->stream));
+            NES_CUDA(c, cudaStreamWaitEvent(c->stream_b, c->ev_fork, 0));
+        }
         for (int wide = 0; wide < 2; ++wide) {
-            const int a = wide ? P.psplit[l] : P.pptr[l], b = wide ? P.pptr[l + 1] : P.psplit[l];
-            if (b <= a) continue;
+            cudaStream_t st = (fork && !wide) ? c->stream_b : c->stream;
             const int ncmax = wide ? CH_NB : 64;
-            mf_potrf_kernel<<<b - a, 256, mf_diag_smem(ncmax), c->stream>>>(sf->d, P.d_potrf + a, ncmax);
-            MF_LAUNCHED(c, "mf_potrf_kernel");
+            const int a = wide ? P.psplit[l] : P.pptr[l], b = wide ? P.pptr[l + 1] : P.psplit[l];
+            if (b > a) {
+                mf_potrf_kernel<<<b - a, 256, mf_diag_smem(ncmax), st>>>(sf->d, P.d_potrf + a, ncmax);
+                MF_LAUNCHED(c, "mf_potrf_kernel");
+            }
+            const int ta = wide ? P.tsplit[l] : P.tptr[l], tb = wide ? P.tptr[l + 1] : P.tsplit[l];
+            if (tb > ta) {
+                mf_trsm_kernel<<<tb - ta, 256, mf_tr_smem(ncmax), st>>>(sf->d, P.d_trsm + ta, ncmax);
+                MF_LAUNCHED(c, "mf_trsm_kernel");
+            }
+        }
+        if (fork) {
+            NES_CUDA(c, cudaEventRecord(c->ev_join, c->stream_b));
+            NES_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_join, 0));
         }
         // block inverses: held back while the levels are wide (they would take SMs from the factorization),
         // released in one go when the tree narrows to <= 32 supernodes per level and the SMs are mostly idle
@@ -1037,13 +1059,6 @@ static int run_factor_phase(nes_ctx* c, SparseFactor* sf, int ph) {
             mf_trtri_kernel<<<P.pptr[l + 1] - from, CH_NB, MF_TI_SMEM, c->stream_aux>>>(sf->d, P.d_potrf + from);
             NES_CHECK_LAUNCH(c);
             trtri_done = P.pptr[l + 1];
-        }
-        for (int wide = 0; wide < 2; ++wide) {
-            const int a = wide ? P.tsplit[l] : P.tptr[l], b = wide ? P.tptr[l + 1] : P.tsplit[l];
-            if (b <= a) continue;
-            const int ncmax = wide ? CH_NB : 64;
-            mf_trsm_kernel<<<b - a, 256, mf_tr_smem(ncmax), c->stream>>>(sf->d, P.d_trsm + a, ncmax);
-            MF_LAUNCHED(c, "mf_trsm_kernel");
         }
         const int ny = P.yptr[l + 1] - P.yptr[l];
         if (ny > 0) {
