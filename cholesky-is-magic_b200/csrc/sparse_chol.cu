@@ -250,30 +250,30 @@ mf_potrf_kernel(const MfDesc d, const int* __restrict__ list, int ncmax) {
         const int lduc = d.ldu[c];
         if (tid < cutc) srl[tid] = d.rel[d.relptr[c] + tid];
         __syncthreads();
-        // lane owns rows lane + 32k of the child's leading cutc x cutc triangle; two columns per step so
-        // that eight independent loads are in flight per lane
-        for (int j = warp; j < cutc; j += 16) {
-            const int j2 = j + 8;
-            const double* u1 = Uc + (long long)j * lduc;
-            const double* u2 = Uc + (long long)min(j2, cutc - 1) * lduc;
-            double v1[4], v2[4];
+        // lane owns rows lane + 32k of the child's leading cutc x cutc triangle; four columns per step so
+        // that sixteen independent loads are in flight per lane (the gathers are a chain of L2 round trips)
+        for (int j = warp; j < cutc; j += 32) {
+            double v[4][4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = lane + 32 * k;
-                v1[k] = (i >= j && i < cutc) ? u1[i] : 0.0;
-                v2[k] = (i >= j2 && i < cutc) ? u2[i] : 0.0;
-            }
-            const int t1 = srl[j] * CH_P, t2 = srl[min(j2, cutc - 1)] * CH_P;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-                const int i = lane + 32 * k;
-                if (i >= j && i < cutc) S[srl[i] + t1] += v1[k];
-            }
-            if (j2 < cutc) {
+            for (int t = 0; t < 4; ++t) {
+                const int jj = j + 8 * t;
+                const double* u = Uc + (long long)min(jj, cutc - 1) * lduc;
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const int i = lane + 32 * k;
-                    if (i >= j2 && i < cutc) S[srl[i] + t2] += v2[k];
+                    v[t][k] = (jj < cutc && i >= jj && i < cutc) ? u[i] : 0.0;
+                }
+            }
+#pragma unroll
+            for (int t = 0; t < 4; ++t) {
+                const int jj = j + 8 * t;
+                if (jj < cutc) {
+                    const int tcol = srl[jj] * CH_P;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const int i = lane + 32 * k;
+                        if (i >= jj && i < cutc) S[srl[i] + tcol] += v[t][k];
+                    }
                 }
             }
         }
@@ -663,6 +663,20 @@ mf_fwd_head_kernel(const MfDesc d, const int* __restrict__ list, double* __restr
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     if (t < nc) {
         int cc = c_lo;
+        // sixteen loads in flight per step (W comes from L2: the product is a chain of round trips otherwise);
+        // the four accumulators receive their columns in the same order as in the 4-wide loop below
+        for (; cc + 15 < c_hi; cc += 16) {
+            double w[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u) w[u] = Wb[t + (cc + u) * nc];
+#pragma unroll
+            for (int u = 0; u < 16; u += 4) {
+                a0 = fma(w[u + 0], rhs[cc + u + 0], a0);
+                a1 = fma(w[u + 1], rhs[cc + u + 1], a1);
+                a2 = fma(w[u + 2], rhs[cc + u + 2], a2);
+                a3 = fma(w[u + 3], rhs[cc + u + 3], a3);
+            }
+        }
         for (; cc + 3 < c_hi; cc += 4) {
             a0 = fma(Wb[t + (cc + 0) * nc], rhs[cc + 0], a0);
             a1 = fma(Wb[t + (cc + 1) * nc], rhs[cc + 1], a1);
@@ -694,13 +708,26 @@ mf_fwd_tail_kernel(const MfDesc d, const int2* __restrict__ tasks, const double*
     double a[MS_FWD_ROWS / 32];
 #pragma unroll
     for (int k = 0; k < MS_FWD_ROWS / 32; ++k) a[k] = 0.0;
-    for (int cc = warp; cc < nc; cc += 8) {
+    // two columns (sixteen loads) per step; every a[k] still receives its columns in ascending order
+    for (int cc = warp; cc < nc; cc += 16) {
+        const int c2 = cc + 8;
         const double* bc = B + (long long)cc * ld;
-        const double y = ys[cc];
+        const double* bd = B + (long long)min(c2, nc - 1) * ld;
+        const double y = ys[cc], y2 = (c2 < nc) ? ys[c2] : 0.0;
+        double v[MS_FWD_ROWS / 32], v2[MS_FWD_ROWS / 32];
 #pragma unroll
         for (int k = 0; k < MS_FWD_ROWS / 32; ++k) {
             const int i = lane + 32 * k;
-            if (i0 + i < i1) a[k] = fma(bc[i], y, a[k]);
+            v[k] = (i0 + i < i1) ? bc[i] : 0.0;
+            v2[k] = (i0 + i < i1 && c2 < nc) ? bd[i] : 0.0;
+        }
+#pragma unroll
+        for (int k = 0; k < MS_FWD_ROWS / 32; ++k) {
+            const int i = lane + 32 * k;
+            if (i0 + i < i1) {
+                a[k] = fma(v[k], y, a[k]);
+                if (c2 < nc) a[k] = fma(v2[k], y2, a[k]);
+            }
         }
     }
 #pragma unroll
@@ -784,13 +811,37 @@ mf_bwd_finish_kernel(const MfDesc d, const int* __restrict__ list, double* __res
     if (tid < CH_NB) rhs[tid] = (tid < nc) ? x[col0 + tid] - (nu > 0 ? dots[col0 + tid] : 0.0) : 0.0;
     __syncthreads();
     const double* Wb = d.W + d.woff[s];
-    for (int t = warp; t < nc; t += 8) {   // z_t = sum_{cc >= t} W(cc, t) rhs[cc]
-        const double* wc = Wb + (long long)t * nc;
-        double a = 0.0;
-        for (int cc = t + lane; cc < nc; cc += 32) a = fma(wc[cc], rhs[cc], a);
+    // z_t = sum_{cc >= t} W(cc, t) rhs[cc]; four columns per step so their loads and shuffle trees overlap
+    for (int t0 = warp; t0 < nc; t0 += 32) {
+        double a[4], w[4][4];   // nc <= 128: at most four 32-row steps per column
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) a += __shfl_xor_sync(0xffffffffu, a, o);
-        if (lane == 0) x[col0 + t] = a;
+        for (int u = 0; u < 4; ++u) {
+            const int t = t0 + 8 * u;
+            const double* wc = Wb + (long long)min(t, nc - 1) * nc;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int cc = t + lane + 32 * it;
+                w[u][it] = (cc < nc) ? wc[cc] : 0.0;
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            a[u] = 0.0;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int cc = t0 + 8 * u + lane + 32 * it;
+                if (cc < nc) a[u] = fma(w[u][it], rhs[cc], a[u]);
+            }
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] += __shfl_xor_sync(0xffffffffu, a[u], o);
+        if (lane == 0) {
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (t0 + 8 * u < nc) x[col0 + t0 + 8 * u] = a[u];
+        }
     }
 }
 
