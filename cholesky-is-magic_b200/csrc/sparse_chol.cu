@@ -345,18 +345,18 @@ mf_trsm_kernel(const MfDesc d, const int2* __restrict__ tasks, int ncmax) {
         if (tid < cutc) scol[tid] = rl[tid] * MF_XP;                  // target column offset in Xs
         __syncthreads();
         const int ni = ihi - ilo;
-        // lane owns child rows ilo + lane, ilo + lane + 32; four child columns per step
-        for (int j = warp; j < cutc; j += 32) {
-            double v[4][2];
+        // lane owns child rows ilo + lane, ilo + lane + 32; eight child columns (sixteen loads) per step
+        for (int j = warp; j < cutc; j += 64) {
+            double v[8][2];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 8; ++k) {
                 const int jj = min(j + 8 * k, cutc - 1);
                 const double* ucol = Uc + (long long)jj * lduc + ilo;
                 v[k][0] = (lane < ni) ? ucol[lane] : 0.0;
                 v[k][1] = (lane + 32 < ni) ? ucol[lane + 32] : 0.0;
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 8; ++k) {
                 const int jj = j + 8 * k;
                 if (jj < cutc) {
                     double* xcol = Xs + scol[jj];
@@ -775,6 +775,18 @@ mf_bwd_dots_kernel(const MfDesc d, const int2* __restrict__ tasks, const double*
             const double* bd = B + base + (long long)min(cb, nc - 1) * ld;
             double a0 = 0.0, a1 = 0.0, b0 = 0.0, b1 = 0.0;
             int i = lane;
+            for (; i + 96 < len; i += 128) {   // eight loads in flight; same accumulation order as below
+                const double p0 = bc[i], q0 = bd[i], p1 = bc[i + 32], q1 = bd[i + 32];
+                const double p2 = bc[i + 64], q2 = bd[i + 64], p3 = bc[i + 96], q3 = bd[i + 96];
+                a0 = fma(p0, zr[i], a0);
+                b0 = fma(q0, zr[i], b0);
+                a1 = fma(p1, zr[i + 32], a1);
+                b1 = fma(q1, zr[i + 32], b1);
+                a0 = fma(p2, zr[i + 64], a0);
+                b0 = fma(q2, zr[i + 64], b0);
+                a1 = fma(p3, zr[i + 96], a1);
+                b1 = fma(q3, zr[i + 96], b1);
+            }
             for (; i + 32 < len; i += 64) {
                 a0 = fma(bc[i], zr[i], a0);
                 b0 = fma(bd[i], zr[i], b0);
