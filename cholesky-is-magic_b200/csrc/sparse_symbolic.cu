@@ -187,33 +187,30 @@ struct Orderer {
             rcm(verts, lab, out);
             return;
         }
-        if (!connected) {  // connected components are independent subtrees of the elimination forest
-            std::vector<int> order;
-            std::vector<std::vector<int>> comps;
-            size_t seen = 0;
-            for (int s : verts) {
-                if (lev[s] >= 0) continue;
-                bfs(s, lab, order);
-                seen += order.size();
-                comps.push_back(order);
-                if (comps.size() == 1 && seen == verts.size()) break;
-            }
-            for (auto& cvec : comps) clear_lev(cvec);
-            if (comps.size() > 1) {
-                for (auto& cvec : comps) {
-                    const int l2 = next_label++;
-                    for (int v : cvec) part[v] = l2;
-                    dissect(std::move(cvec), l2, depth + 1, true, 0, out);
-                }
-                return;
-            }
-        }
         // pseudo-peripheral start: min degree, then the far end of its level structure
         int start = verts[0];
         for (int v : verts)
             if (deg[v] < deg[start]) start = v;
         std::vector<int> order;
         int h = bfs(start, lab, order);
+        if (!connected && order.size() != verts.size()) {
+            // more than one component: they are independent subtrees of the elimination forest
+            // (enumerated in the order of `verts`, as before the first search doubled as the connectivity test)
+            clear_lev(order);
+            std::vector<std::vector<int>> comps;
+            for (int s : verts) {
+                if (lev[s] >= 0) continue;
+                bfs(s, lab, order);
+                comps.push_back(order);
+            }
+            for (auto& cvec : comps) clear_lev(cvec);
+            for (auto& cvec : comps) {
+                const int l2 = next_label++;
+                for (int v : cvec) part[v] = l2;
+                dissect(std::move(cvec), l2, depth + 1, true, 0, out);
+            }
+            return;
+        }
         {
             const int far = order.back();
             clear_lev(order);

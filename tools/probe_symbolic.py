@@ -17,3 +17,5 @@ for l in range(int(s["nlevels"])):
     nu = nrs - ncs
     fl = (ncs.astype(float)**3/3 + nu.astype(float)*ncs**2 + nu.astype(float)**2*ncs).sum()
     print(f"level {l:2d}: {b-a:4d} supernodes  nc {ncs.min():3d}..{ncs.max():3d}  rows below {nu.min():5d}..{nu.max():5d}  flops {fl:.3g}")
+import hashlib
+print("perm sha1", hashlib.sha1(s["perm"].tobytes()).hexdigest(), "first sha1", hashlib.sha1(s["first"].tobytes()).hexdigest())
