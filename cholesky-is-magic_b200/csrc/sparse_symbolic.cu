@@ -85,6 +85,7 @@ void aat_pattern(int m, int n, const int* cp, const int* ri, const std::vector<i
         for (int i = b; i < e; ++i) {
             const size_t start = out.size();
             mark[i] = i;
+            int lo = m, hi = -1;
             for (int q = rp[i]; q < rp[i + 1]; ++q) {
                 const int kk = cj[q];
                 for (int t = cp[kk]; t < cp[kk + 1]; ++t) {
@@ -92,20 +93,29 @@ void aat_pattern(int m, int n, const int* cp, const int* ri, const std::vector<i
                     if (mark[r] != i) {
                         mark[r] = i;
                         out.push_back(r);
+                        lo = std::min(lo, r);
+                        hi = std::max(hi, r);
                     }
                 }
             }
-            std::sort(out.begin() + start, out.end());
-            ap[i + 1] = (int)(out.size() - start);
+            const int cnt = (int)(out.size() - start);
+            if (cnt > 32 && hi - lo + 1 <= 4 * cnt) {
+                // the neighbours fill a short index range (banded / clustered rows): reading the marks of
+                // that range in order is cheaper than sorting
+                size_t w = start;
+                for (int r = lo; r <= hi; ++r)
+                    if (mark[r] == i && r != i) out[w++] = r;
+            } else {
+                std::sort(out.begin() + start, out.end());
+            }
+            ap[i + 1] = cnt;
         }
     });
     for (int i = 0; i < m; ++i) ap[i + 1] += ap[i];
     ai.resize(ap[m]);
-    size_t w = 0;
-    for (int k = 0; k < nch; ++k) {
-        std::copy(part[k].begin(), part[k].end(), ai.begin() + w);
-        w += part[k].size();
-    }
+    parallel_chunks(m, nch, [&](int k, int b, int) {  // same chunk boundaries: chunk k starts at row b
+        std::copy(part[k].begin(), part[k].end(), ai.begin() + ap[b]);
+    });
 }
 
 // ---- ordering ---------------------------------------------------------------------------------------
