@@ -569,42 +569,68 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
     S->rowptr.assign(ns + 1, 0);
     S->off.assign(ns + 1, 0);
     {
-        std::vector<int> mark(m, -1), tmp;
-        for (int s = 0; s < ns; ++s) {
-            const int f = first[s], l = first[s + 1] - 1, nc = l - f + 1;
-            tmp.clear();
-            for (int j = f; j <= l; ++j) {
-                const int oj = perm[j];
-                for (int q = ap[oj]; q < ap[oj + 1]; ++q) {
-                    const int i = iperm[ai[q]];
-                    if (i > l && mark[i] != s) {
-                        mark[i] = s;
-                        tmp.push_back(i);
+        // The supernodes of a level only read the structures of lower levels: levels with many supernodes
+        // are split over host threads (one mark array each), the results are appended in supernode order.
+        const int nth = host_threads();
+        std::vector<std::vector<int>> marks(nth);
+        std::vector<std::vector<int>> below(ns);  // sorted rows below the columns of every supernode
+        auto structure_of = [&](int k, int sa, int sb) {
+            std::vector<int>& mark = marks[k];
+            if (mark.empty()) mark.assign(m, -1);
+            for (int s = sa; s < sb; ++s) {
+                const int f = first[s], l = first[s + 1] - 1;
+                std::vector<int>& tmp = below[s];
+                for (int j = f; j <= l; ++j) {
+                    const int oj = perm[j];
+                    for (int q = ap[oj]; q < ap[oj + 1]; ++q) {
+                        const int i = iperm[ai[q]];
+                        if (i > l && mark[i] != s) {
+                            mark[i] = s;
+                            tmp.push_back(i);
+                        }
                     }
                 }
-            }
-            for (int q = S->childptr[s]; q < S->childptr[s + 1]; ++q) {
-                const int c = S->child[q];
-                const int cnc = first[c + 1] - first[c];
-                for (int p = S->rowptr[c] + cnc; p < S->rowptr[c + 1]; ++p) {
-                    const int i = S->rows[p];
-                    if (i > l && mark[i] != s) {
-                        mark[i] = s;
-                        tmp.push_back(i);
+                for (int q = S->childptr[s]; q < S->childptr[s + 1]; ++q) {
+                    const int c = S->child[q];
+                    const int cnc = first[c + 1] - first[c];
+                    for (int p = S->rowptr[c] + cnc; p < S->rowptr[c + 1]; ++p) {
+                        const int i = S->rows[p];
+                        if (i > l && mark[i] != s) {
+                            mark[i] = s;
+                            tmp.push_back(i);
+                        }
                     }
                 }
+                std::sort(tmp.begin(), tmp.end());
             }
-            std::sort(tmp.begin(), tmp.end());
-            if ((int)tmp.size() != cnew[l] - 1)
-                return set_err(err, errlen, "symbolic analysis: structure of supernode %d disagrees with its column count",
-                               s, 0);
-            for (int j = f; j <= l; ++j) S->rows.push_back(j);
-            S->rows.insert(S->rows.end(), tmp.begin(), tmp.end());
-            S->nr[s] = nc + (int)tmp.size();
-            S->nb0[s] = (nc + 31) & ~31;
-            S->ld[s] = S->nb0[s] + (((int)tmp.size() + 15) & ~15);
-            S->rowptr[s + 1] = (int)S->rows.size();
-            S->off[s + 1] = S->off[s] + (long long)S->ld[s] * nc;
+        };
+        for (int lv = 0; lv < S->nlevels; ++lv) {
+            const int sa = S->lvlptr[lv], sb = S->lvlptr[lv + 1];
+            if (nth > 1 && sb - sa >= 4 * nth) {
+                std::vector<std::thread> th;
+                for (int k = 0; k < nth; ++k) {
+                    const int b = sa + (int)((long long)(sb - sa) * k / nth), e = sa + (int)((long long)(sb - sa) * (k + 1) / nth);
+                    th.emplace_back([&structure_of, k, b, e]() { structure_of(k, b, e); });
+                }
+                for (auto& t : th) t.join();
+            } else {
+                structure_of(0, sa, sb);
+            }
+            for (int s = sa; s < sb; ++s) {
+                const int f = first[s], l = first[s + 1] - 1, nc = l - f + 1;
+                std::vector<int>& tmp = below[s];
+                if ((int)tmp.size() != cnew[l] - 1)
+                    return set_err(err, errlen, "symbolic analysis: structure of supernode %d disagrees with its column count",
+                                   s, 0);
+                for (int j = f; j <= l; ++j) S->rows.push_back(j);
+                S->rows.insert(S->rows.end(), tmp.begin(), tmp.end());
+                S->nr[s] = nc + (int)tmp.size();
+                S->nb0[s] = (nc + 31) & ~31;
+                S->ld[s] = S->nb0[s] + (((int)tmp.size() + 15) & ~15);
+                S->rowptr[s + 1] = (int)S->rows.size();
+                S->off[s + 1] = S->off[s] + (long long)S->ld[s] * nc;
+                std::vector<int>().swap(tmp);
+            }
         }
     }
     S->lsize = S->off[ns];

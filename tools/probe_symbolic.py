@@ -19,3 +19,4 @@ for l in range(int(s["nlevels"])):
     print(f"level {l:2d}: {b-a:4d} supernodes  nc {ncs.min():3d}..{ncs.max():3d}  rows below {nu.min():5d}..{nu.max():5d}  flops {fl:.3g}")
 import hashlib
 print("perm sha1", hashlib.sha1(s["perm"].tobytes()).hexdigest(), "first sha1", hashlib.sha1(s["first"].tobytes()).hexdigest())
+print("rows sha1", hashlib.sha1(s["rows"].tobytes()).hexdigest(), "edest sha1", hashlib.sha1(s["edest"].tobytes()).hexdigest())
