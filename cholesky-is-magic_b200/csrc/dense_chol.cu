@@ -24,6 +24,7 @@
 #include "dmma_nt.cuh"
 #include "nes_internal.h"
 #include "potrf_block.cuh"
+#include "trtri_block.cuh"
 
 namespace nes {
 
@@ -397,39 +398,26 @@ static int chol_update(nes_ctx* c, nes_factor* L, int r0, int c0, int nrows, int
 constexpr int TI_P = 129;
 constexpr int TI_SMEM = (CH_NB * TI_P + CH_NB) * 8;
 
-__global__ void __launch_bounds__(CH_NB)
+__global__ void __launch_bounds__(TRTRI_THREADS)
 trtri_diag_kernel(const double* __restrict__ M, long long ld, int m, const double* __restrict__ dinv_g,
                   double* __restrict__ Winv) {
     // one shared array holds both triangles: L strictly below the diagonal at S[r + c*P] (r > c) and
-    // W' on and above it, W(r, j) at S[j + r*P] (r >= j), so thread j walks its column with unit stride
+    // W' on and above it, W(r, j) at S[j + r*P] (r >= j); four lanes per column (trtri_block.cuh)
     extern __shared__ double S[];
     double* dv = S + CH_NB * TI_P;
-    const int j = threadIdx.x;
+    const int tid = threadIdx.x;
     const int j0 = blockIdx.x * CH_NB;
     const int jb = min(CH_NB, m - j0);
-    for (int idx = j; idx < jb * jb; idx += CH_NB) {
+    for (int idx = tid; idx < jb * jb; idx += TRTRI_THREADS) {
         const int cc = idx / jb, r = idx - cc * jb;
         if (r > cc) S[r + cc * TI_P] = M[(j0 + r) + (long long)(j0 + cc) * ld];
     }
-    dv[j] = (j < jb) ? dinv_g[j0 + j] : 1.0;
+    if (tid < CH_NB) dv[tid] = (tid < jb) ? dinv_g[j0 + tid] : 1.0;
     __syncthreads();
-    if (j < jb) {
-        double* w = S + j;  // w[c] = w[c * TI_P]
-        w[j * TI_P] = dv[j];
-        for (int r = j + 1; r < jb; ++r) {
-            double s0 = 0.0, s1 = 0.0;
-            int cc = j;
-            for (; cc + 1 < r; cc += 2) {
-                s0 = fma(S[r + cc * TI_P], w[cc * TI_P], s0);
-                s1 = fma(S[r + (cc + 1) * TI_P], w[(cc + 1) * TI_P], s1);
-            }
-            if (cc < r) s0 = fma(S[r + cc * TI_P], w[cc * TI_P], s0);
-            w[r * TI_P] = -(s0 + s1) * dv[r];
-        }
-    }
+    trtri_columns_smem<TI_P>(S, dv, jb);
     __syncthreads();
     double* Wg = Winv + (size_t)blockIdx.x * CH_NB * CH_NB;  // column-major 128 x 128, zero upper part
-    for (int idx = j; idx < CH_NB * CH_NB; idx += CH_NB) {
+    for (int idx = tid; idx < CH_NB * CH_NB; idx += TRTRI_THREADS) {
         const int cc = idx >> 7, r = idx & 127;
         Wg[idx] = (r >= cc && r < jb && cc < jb) ? S[cc + r * TI_P] : 0.0;
     }
@@ -676,7 +664,7 @@ int dense_cholesky(nes_ctx* c, nes_factor* L, const nes_matrix* A) {
         tr.dump(c->stream);
     }
     if (L->d_Winv) {  // block inverses for the solve phase (off the factorization's critical path)
-        trtri_diag_kernel<<<(m + CH_NB - 1) / CH_NB, CH_NB, TI_SMEM, c->stream>>>(L->d_M, ld, m, L->d_dinv,
+        trtri_diag_kernel<<<(m + CH_NB - 1) / CH_NB, TRTRI_THREADS, TI_SMEM, c->stream>>>(L->d_M, ld, m, L->d_dinv,
                                                                                   L->d_Winv);
         NES_CHECK_LAUNCH(c);
     }

@@ -44,6 +44,7 @@
 #include "dmma_nt.cuh"
 #include "nes_internal.h"
 #include "potrf_block.cuh"
+#include "trtri_block.cuh"
 #include "sparse_symbolic.h"
 
 namespace nes {
@@ -591,39 +592,26 @@ static int syrk_bn() {
     return v;
 }
 
-// W_s = L_ss^-1 for the listed supernodes, one CTA each, thread j = column j (forward substitution).
+// W_s = L_ss^-1 for the listed supernodes, one CTA each (forward substitution per column, four lanes per column).
 constexpr int MF_TI_SMEM = (CH_NB * 129 + CH_NB) * 8;
-__global__ void __launch_bounds__(CH_NB)
+__global__ void __launch_bounds__(TRTRI_THREADS)
 mf_trtri_kernel(const MfDesc d, const int* __restrict__ list) {
     constexpr int P = 129;
     extern __shared__ double S[];   // L strictly below the diagonal at S[r + c*P]; W' on/above it
     double* dv = S + CH_NB * P;
-    const int s = list[blockIdx.x], j = threadIdx.x;
+    const int s = list[blockIdx.x], tid = threadIdx.x;
     const int col0 = d.first[s], nc = d.first[s + 1] - col0, ld = d.ld[s];
     const double* blk = d.Lv + d.off[s];
-    for (int idx = j; idx < nc * nc; idx += CH_NB) {
+    for (int idx = tid; idx < nc * nc; idx += TRTRI_THREADS) {
         const int cc = idx / nc, r = idx - cc * nc;
         if (r > cc) S[r + cc * P] = blk[r + (long long)cc * ld];
     }
-    dv[j] = (j < nc) ? d.dinv[col0 + j] : 1.0;
+    if (tid < CH_NB) dv[tid] = (tid < nc) ? d.dinv[col0 + tid] : 1.0;
     __syncthreads();
-    if (j < nc) {
-        double* w = S + j;
-        w[j * P] = dv[j];
-        for (int r = j + 1; r < nc; ++r) {
-            double s0 = 0.0, s1 = 0.0;
-            int cc = j;
-            for (; cc + 1 < r; cc += 2) {
-                s0 = fma(S[r + cc * P], w[cc * P], s0);
-                s1 = fma(S[r + (cc + 1) * P], w[(cc + 1) * P], s1);
-            }
-            if (cc < r) s0 = fma(S[r + cc * P], w[cc * P], s0);
-            w[r * P] = -(s0 + s1) * dv[r];
-        }
-    }
+    trtri_columns_smem<P>(S, dv, nc);   // four lanes per column (trtri_block.cuh)
     __syncthreads();
     double* Wg = d.W + d.woff[s];   // column-major nc x nc, zero above the diagonal
-    for (int idx = j; idx < nc * nc; idx += CH_NB) {
+    for (int idx = tid; idx < nc * nc; idx += TRTRI_THREADS) {
         const int cc = idx / nc, r = idx - cc * nc;
         Wg[idx] = (r >= cc) ? S[cc + r * P] : 0.0;
     }
@@ -1119,7 +1107,7 @@ static int run_factor_phase(nes_ctx* c, SparseFactor* sf, int ph) {
             NES_CUDA(c, cudaEventRecord(c->ev_panel, c->stream));
             NES_CUDA(c, cudaStreamWaitEvent(c->stream_aux, c->ev_panel, 0));
             const int from = trtri_done;
-            mf_trtri_kernel<<<P.pptr[l + 1] - from, CH_NB, MF_TI_SMEM, c->stream_aux>>>(sf->d, P.d_potrf + from);
+            mf_trtri_kernel<<<P.pptr[l + 1] - from, TRTRI_THREADS, MF_TI_SMEM, c->stream_aux>>>(sf->d, P.d_potrf + from);
             NES_CHECK_LAUNCH(c);
             trtri_done = P.pptr[l + 1];
         }
