@@ -870,6 +870,11 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
     {
         // columns are independent: count the entries of every column, prefix-sum, fill in parallel
         std::vector<long long> cstart(m + 1, 0);
+        // the three output arrays (anz entries each, 320 MB at config 4) are value-initialised by resize():
+        // that sequential fill runs on its own threads beside the counting pass
+        std::thread fill_i([&]() { S->ei.resize(S->anz); });
+        std::thread fill_j([&]() { S->ej.resize(S->anz); });
+        std::thread fill_d([&]() { S->edest.resize(S->anz); });
         parallel_chunks(m, host_threads(), [&](int, int b, int e) {
             for (int j = b; j < e; ++j) {
                 const int oj = perm[j];
@@ -879,11 +884,11 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
             }
         });
         for (int j = 0; j < m; ++j) cstart[j + 1] += cstart[j];
+        fill_i.join();
+        fill_j.join();
+        fill_d.join();
         if (cstart[m] != S->anz)
             return set_err(err, errlen, "symbolic analysis: assembled %d entries, expected %d", (int)cstart[m], (int)S->anz);
-        S->ei.resize(S->anz);
-        S->ej.resize(S->anz);
-        S->edest.resize(S->anz);
         std::atomic<int> bad{-1};
         parallel_chunks(m, host_threads(), [&](int, int b, int e) {
             std::vector<int> col;
