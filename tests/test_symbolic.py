@@ -206,3 +206,38 @@ def test_symbolic_degenerate_shapes():
         m = A.shape[0]
         assert sorted(S["perm"].tolist()) == list(range(m))
         assert S["first"][-1] == m and S["lnz"] >= m
+
+
+_THREAD_PROBE = r"""
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, {root!r})
+import _pkg; _pkg.load()
+from cholesky_is_magic_b200 import lpgen, nes
+import scipy.sparse as sp
+sf = lpgen.sparse_lp(12000, 30000, nnz_per_col=8, bandwidth=120, seed=3)
+A = sp.csc_matrix((sf.A.value, (sf.A.row, sf.A.col)), shape=(12000, 30000)); A.sort_indices()
+S = nes.symbolic_analyze(A.indptr, A.indices, 12000, 30000, 1, 0)
+h = hashlib.sha1()
+for k in ("perm", "first", "rows", "rowptr", "level", "child", "rel", "tb", "ei", "ej", "edest", "off", "uoff"):
+    h.update(np.ascontiguousarray(S[k]).tobytes())
+print(h.hexdigest(), int(S["nsuper"]), int(S["nlevels"]), S["lnz"])
+"""
+
+
+def test_analysis_does_not_depend_on_the_number_of_host_threads():
+    """Pattern, dissection branches, row structures and the assembly map run on host threads
+    (NES_HOST_THREADS, read once per process): every thread count must give the same arrays."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    outs = []
+    for nth in ("1", "3", "8"):
+        env = dict(os.environ, NES_HOST_THREADS=nth)
+        r = subprocess.run([sys.executable, "-c", _THREAD_PROBE.format(root=root)], env=env, capture_output=True,
+                           text=True, timeout=300)
+        assert r.returncode == 0, r.stderr
+        outs.append(r.stdout.strip().splitlines()[-1])
+    assert outs[0] == outs[1] == outs[2], outs
+    assert int(outs[0].split()[2]) > 3        # a real tree, not a chain of one level
