@@ -21,6 +21,7 @@
 #include <cmath>
 #include <cstdio>
 #include <chrono>
+#include <climits>
 #include <cstdlib>
 #include <atomic>
 #include <numeric>
@@ -126,6 +127,7 @@ struct Orderer {
     std::vector<int> part;   // label of the vertex set a vertex currently belongs to (-1: removed)
     std::vector<int> deg;
     std::vector<int> lev;    // scratch: BFS level (sets being dissected concurrently are disjoint)
+    std::vector<int> claim;  // scratch of bfs_parallel (INT_MAX between searches)
     std::atomic<int> next_label{1};
     int leaf;
 
@@ -156,6 +158,92 @@ struct Orderer {
     }
     void clear_lev(const std::vector<int>& order) {
         for (int v : order) lev[v] = -1;
+    }
+
+    // The same search on `nth` host threads, level by level, with EXACTLY the visit order of bfs(): a vertex
+    // belongs to the first frontier vertex (in queue order) that reaches it and is appended at its place in
+    // that vertex's adjacency list.  Pass 1 lets every frontier vertex claim its unvisited neighbours
+    // (minimum of the queue positions), pass 2 emits the neighbours a vertex won, in adjacency order, into
+    // per-thread lists that are concatenated in thread (= queue) order.  Two passes over the edges instead
+    // of one, but on all threads: the top-level searches of the dissection walk the whole graph (4e7 edges
+    // at config 4) and were the longest sequential piece of the analysis.
+    int bfs_parallel(int start, int lab, std::vector<int>& order, int nth) {
+        if (claim.empty()) claim.assign(m, INT_MAX);
+        order.clear();
+        order.push_back(start);
+        lev[start] = 0;
+        struct Shared {
+            std::atomic<int> arrived{0}, phase{0};
+            size_t fb = 0, fe = 1;   // current frontier = order[fb, fe)
+            int level = 0;
+            bool done = false;
+        } sh;
+        std::vector<std::vector<int>> found(nth);
+        auto barrier = [&](int& my_phase) {
+            ++my_phase;
+            if (sh.arrived.fetch_add(1, std::memory_order_acq_rel) == nth - 1) {
+                sh.arrived.store(0, std::memory_order_relaxed);
+                sh.phase.store(my_phase, std::memory_order_release);
+            } else {
+                int spins = 0;
+                while (sh.phase.load(std::memory_order_acquire) != my_phase)
+                    if (++spins > 2000) std::this_thread::yield();
+            }
+        };
+        auto worker = [&](int t) {
+            int my_phase = 0;
+            for (;;) {
+                const size_t fb = sh.fb, fe = sh.fe, nf = fe - fb;
+                const size_t a = fb + nf * t / nth, b = fb + nf * (t + 1) / nth;
+                for (size_t p = a; p < b; ++p) {   // pass 1: claim
+                    const int v = order[p];
+                    for (int q = ap[v]; q < ap[v + 1]; ++q) {
+                        const int u = ai[q];
+                        if (part[u] != lab || lev[u] >= 0) continue;
+                        int cur = __atomic_load_n(&claim[u], __ATOMIC_RELAXED);
+                        while ((int)p < cur &&
+                               !__atomic_compare_exchange_n(&claim[u], &cur, (int)p, true, __ATOMIC_RELAXED, __ATOMIC_RELAXED)) {
+                        }
+                    }
+                }
+                barrier(my_phase);
+                std::vector<int>& mine = found[t];
+                mine.clear();
+                for (size_t p = a; p < b; ++p) {   // pass 2: emit what this vertex won, in adjacency order
+                    const int v = order[p];
+                    for (int q = ap[v]; q < ap[v + 1]; ++q) {
+                        const int u = ai[q];
+                        if (part[u] == lab && lev[u] < 0 && claim[u] == (int)p) mine.push_back(u);
+                    }
+                }
+                barrier(my_phase);
+                if (t == 0) {                      // next frontier, in queue order
+                    for (int k = 0; k < nth; ++k)
+                        for (int u : found[k]) {
+                            lev[u] = sh.level + 1;
+                            claim[u] = INT_MAX;
+                            order.push_back(u);
+                        }
+                    sh.fb = fe;
+                    sh.fe = order.size();
+                    if (sh.fe > sh.fb) ++sh.level;
+                    sh.done = sh.fe == sh.fb;
+                }
+                barrier(my_phase);
+                if (sh.done) return;
+            }
+        };
+        std::vector<std::thread> th;
+        for (int t = 1; t < nth; ++t) th.emplace_back(worker, t);
+        worker(0);
+        for (auto& x : th) x.join();
+        return sh.level + 1;
+    }
+    // top-level searches (no other dissection branch is running yet) use all host threads
+    int bfs_top(int start, int lab, std::vector<int>& order, int depth, size_t nverts) {
+        const int nth = host_threads();
+        if (depth == 0 && nth > 1 && nverts >= 20000) return bfs_parallel(start, lab, order, nth);
+        return bfs(start, lab, order);
     }
 
     // reverse Cuthill-McKee of the vertices carrying label `lab` (they are relabelled -1 = done),
@@ -202,7 +290,7 @@ struct Orderer {
         for (int v : verts)
             if (deg[v] < deg[start]) start = v;
         std::vector<int> order;
-        int h = bfs(start, lab, order);
+        int h = bfs_top(start, lab, order, depth, verts.size());
         if (!connected && order.size() != verts.size()) {
             // more than one component: they are independent subtrees of the elimination forest
             // (enumerated in the order of `verts`, as before the first search doubled as the connectivity test)
@@ -224,7 +312,7 @@ struct Orderer {
         {
             const int far = order.back();
             clear_lev(order);
-            h = bfs(far, lab, order);
+            h = bfs_top(far, lab, order, depth, verts.size());
         }
         const int nv = (int)verts.size();
         if (h < 3) {

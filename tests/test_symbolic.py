@@ -215,9 +215,9 @@ sys.path.insert(0, {root!r})
 import _pkg; _pkg.load()
 from cholesky_is_magic_b200 import lpgen, nes
 import scipy.sparse as sp
-sf = lpgen.sparse_lp(12000, 30000, nnz_per_col=8, bandwidth=120, seed=3)
-A = sp.csc_matrix((sf.A.value, (sf.A.row, sf.A.col)), shape=(12000, 30000)); A.sort_indices()
-S = nes.symbolic_analyze(A.indptr, A.indices, 12000, 30000, 1, 0)
+sf = lpgen.sparse_lp(24000, 60000, nnz_per_col=8, bandwidth=120, seed=3)
+A = sp.csc_matrix((sf.A.value, (sf.A.row, sf.A.col)), shape=(24000, 60000)); A.sort_indices()
+S = nes.symbolic_analyze(A.indptr, A.indices, 24000, 60000, 1, 0)
 h = hashlib.sha1()
 for k in ("perm", "first", "rows", "rowptr", "level", "child", "rel", "tb", "ei", "ej", "edest", "off", "uoff"):
     h.update(np.ascontiguousarray(S[k]).tobytes())
@@ -227,7 +227,8 @@ print(h.hexdigest(), int(S["nsuper"]), int(S["nlevels"]), S["lnz"])
 
 def test_analysis_does_not_depend_on_the_number_of_host_threads():
     """Pattern, dissection branches, row structures and the assembly map run on host threads
-    (NES_HOST_THREADS, read once per process): every thread count must give the same arrays."""
+    (NES_HOST_THREADS, read once per process), and so do the top-level searches of the dissection once
+    a vertex set has 20 000 vertices: every thread count must give the same arrays."""
     import os
     import subprocess
     import sys
