@@ -132,7 +132,7 @@ struct Orderer {
     int leaf;
 
     Orderer(int m_, const std::vector<int>& ap_, const std::vector<int>& ai_, int leaf_)
-        : m(m_), ap(ap_), ai(ai_), part(m_, 0), deg(m_), lev(m_, -1), leaf(leaf_) {
+        : m(m_), ap(ap_), ai(ai_), part(m_, 0), deg(m_), lev(m_, -1), claim(m_, INT_MAX), leaf(leaf_) {
         for (int i = 0; i < m; ++i) deg[i] = ap[i + 1] - ap[i];
     }
 
@@ -168,7 +168,6 @@ struct Orderer {
     // of one, but on all threads: the top-level searches of the dissection walk the whole graph (4e7 edges
     // at config 4) and were the longest sequential piece of the analysis.
     int bfs_parallel(int start, int lab, std::vector<int>& order, int nth) {
-        if (claim.empty()) claim.assign(m, INT_MAX);
         order.clear();
         order.push_back(start);
         lev[start] = 0;
@@ -239,10 +238,11 @@ struct Orderer {
         for (auto& x : th) x.join();
         return sh.level + 1;
     }
-    // top-level searches (no other dissection branch is running yet) use all host threads
-    int bfs_top(int start, int lab, std::vector<int>& order, int depth, size_t nverts) {
-        const int nth = host_threads();
-        if (depth == 0 && nth > 1 && nverts >= 20000) return bfs_parallel(start, lab, order, nth);
+    // A branch of the dissection that may still fork `par_depth` more times owns 2^par_depth host threads:
+    // its searches use them while the vertex set is large (the top-level ones walk the whole graph).
+    int bfs_top(int start, int lab, std::vector<int>& order, int par_depth, size_t nverts) {
+        const int nth = std::min(host_threads(), 1 << std::min(par_depth, 10));
+        if (nth > 1 && nverts >= 20000) return bfs_parallel(start, lab, order, nth);
         return bfs(start, lab, order);
     }
 
@@ -290,7 +290,7 @@ struct Orderer {
         for (int v : verts)
             if (deg[v] < deg[start]) start = v;
         std::vector<int> order;
-        int h = bfs_top(start, lab, order, depth, verts.size());
+        int h = bfs_top(start, lab, order, par_depth, verts.size());
         if (!connected && order.size() != verts.size()) {
             // more than one component: they are independent subtrees of the elimination forest
             // (enumerated in the order of `verts`, as before the first search doubled as the connectivity test)
@@ -312,7 +312,7 @@ struct Orderer {
         {
             const int far = order.back();
             clear_lev(order);
-            h = bfs_top(far, lab, order, depth, verts.size());
+            h = bfs_top(far, lab, order, par_depth, verts.size());
         }
         const int nv = (int)verts.size();
         if (h < 3) {
