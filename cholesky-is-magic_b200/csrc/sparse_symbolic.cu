@@ -33,6 +33,24 @@ namespace {
 
 constexpr int SN_MAX_COLS = 128;
 
+// The two adjacency arrays (A A' and its permuted copy, 4e7 ints each at config 4) are written in full
+// right after they are sized: resize() must not value-initialise them first (a sequential 160 MB fill).
+template <class T>
+struct default_init_alloc : std::allocator<T> {
+    template <class U>
+    struct rebind {
+        using other = default_init_alloc<U>;
+    };
+    template <class U, class... Args>
+    void construct(U* p, Args&&... args) {
+        if constexpr (sizeof...(Args) == 0)
+            ::new (static_cast<void*>(p)) U;
+        else
+            ::new (static_cast<void*>(p)) U(std::forward<Args>(args)...);
+    }
+};
+using adj_vec = std::vector<int, default_init_alloc<int>>;
+
 int host_threads() {
     static int n = 0;
     if (n == 0) {
@@ -71,7 +89,7 @@ void csc_to_csr(int m, int n, const int* cp, const int* ri, std::vector<int>& rp
 // full symmetric adjacency of A A' (without the diagonal), sorted per row; rows are independent, so
 // chunks of rows are built by host threads and concatenated
 void aat_pattern(int m, int n, const int* cp, const int* ri, const std::vector<int>& rp,
-                 const std::vector<int>& cj, std::vector<int>& ap, std::vector<int>& ai, double& aatfl) {
+                 const std::vector<int>& cj, std::vector<int>& ap, adj_vec& ai, double& aatfl) {
     ap.assign(m + 1, 0);
     aatfl = 0;
     for (int j = 0; j < n; ++j) {
@@ -123,7 +141,7 @@ void aat_pattern(int m, int n, const int* cp, const int* ri, const std::vector<i
 struct Orderer {
     int m;
     const std::vector<int>& ap;
-    const std::vector<int>& ai;
+    const adj_vec& ai;
     std::vector<int> part;   // label of the vertex set a vertex currently belongs to (-1: removed)
     std::vector<int> deg;
     std::vector<int> lev;    // scratch: BFS level (sets being dissected concurrently are disjoint)
@@ -131,7 +149,7 @@ struct Orderer {
     std::atomic<int> next_label{1};
     int leaf;
 
-    Orderer(int m_, const std::vector<int>& ap_, const std::vector<int>& ai_, int leaf_)
+    Orderer(int m_, const std::vector<int>& ap_, const adj_vec& ai_, int leaf_)
         : m(m_), ap(ap_), ai(ai_), part(m_, 0), deg(m_), lev(m_, -1), claim(m_, INT_MAX), leaf(leaf_) {
         for (int i = 0; i < m; ++i) deg[i] = ap[i + 1] - ap[i];
     }
@@ -388,7 +406,7 @@ struct Orderer {
     }
 };
 
-void order_nd(int m, const std::vector<int>& ap, const std::vector<int>& ai, int leaf, std::vector<int>& perm) {
+void order_nd(int m, const std::vector<int>& ap, const adj_vec& ai, int leaf, std::vector<int>& perm) {
     Orderer o(m, ap, ai, leaf);
     const double thresh = std::max(16.0, 10.0 * std::sqrt((double)m));
     std::vector<int> sparse_rows, dense_rows;
@@ -409,8 +427,8 @@ void order_nd(int m, const std::vector<int>& ap, const std::vector<int>& ai, int
 }
 
 // adjacency in the permuted numbering (unsorted)
-void permute_graph(int m, const std::vector<int>& ap, const std::vector<int>& ai, const std::vector<int>& perm,
-                   const std::vector<int>& iperm, std::vector<int>& pp, std::vector<int>& pi) {
+void permute_graph(int m, const std::vector<int>& ap, const adj_vec& ai, const std::vector<int>& perm,
+                   const std::vector<int>& iperm, std::vector<int>& pp, adj_vec& pi) {
     pp.assign(m + 1, 0);
     pi.resize(ai.size());
     for (int j = 0; j < m; ++j) pp[j + 1] = pp[j] + (ap[perm[j] + 1] - ap[perm[j]]);
@@ -422,7 +440,7 @@ void permute_graph(int m, const std::vector<int>& ap, const std::vector<int>& ai
     });
 }
 
-void etree(int m, const std::vector<int>& pp, const std::vector<int>& pi, std::vector<int>& parent) {
+void etree(int m, const std::vector<int>& pp, const adj_vec& pi, std::vector<int>& parent) {
     parent.assign(m, -1);
     std::vector<int> anc(m, -1);
     for (int j = 0; j < m; ++j) {
@@ -474,7 +492,7 @@ void postorder(int m, const std::vector<int>& parent, std::vector<int>& post) {
 // For every row subtree T_i (the vertices j < i with L_ij != 0) only its leaves are new entries of
 // their columns; the overlap of consecutive leaves is removed at their least common ancestor, found
 // with a path-compressed disjoint-set forest.
-void column_counts(int m, const std::vector<int>& pp, const std::vector<int>& pi, const std::vector<int>& parent,
+void column_counts(int m, const std::vector<int>& pp, const adj_vec& pi, const std::vector<int>& parent,
                    std::vector<int>& cc) {
     std::vector<int> firstdesc(m, -1), maxfirst(m, -1), prevleaf(m, -1), anc(m), delta(m, 0);
     for (int k = 0; k < m; ++k) {
@@ -528,7 +546,8 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
     };
     *S = Symbolic();
     S->m = m;
-    std::vector<int> rp, cj, ap, ai;
+    std::vector<int> rp, cj, ap;
+    adj_vec ai;
     csc_to_csr(m, n, cp, ri, rp, cj);
     aat_pattern(m, n, cp, ri, rp, cj, ap, ai, S->aatfl);
     S->anz = (long long)m + (long long)ai.size() / 2;
@@ -536,7 +555,8 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
 
     // ---- ordering, etree, postorder, column counts ---------------------------------------------------
     const int leaf = opt.nd_leaf > 0 ? opt.nd_leaf : std::max(256, m / 128);
-    std::vector<int> perm, iperm(m), pp, pi, parent, cc;
+    std::vector<int> perm, iperm(m), pp, parent, cc;
+    adj_vec pi;
     order_nd(m, ap, ai, leaf, perm);
     lap("nested dissection ordering");
     if ((int)perm.size() != m) return set_err(err, errlen, "ordering lost vertices (%d of %d)", (int)perm.size(), m);
