@@ -999,29 +999,49 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
             return set_err(err, errlen, "symbolic analysis: assembled %d entries, expected %d", (int)cstart[m], (int)S->anz);
         std::atomic<int> bad{-1};
         parallel_chunks(m, host_threads(), [&](int, int b, int e) {
-            std::vector<int> col;
+            // the entries of a column leave in row order without sorting: every neighbour is flagged at its
+            // position in the supernode's (sorted) row list, then the flags are read in order
+            std::vector<int> pos(m, -1), owner_sn(m, -1);
+            std::vector<unsigned char> flag;
+            int cur = -1;
             for (int j = b; j < e; ++j) {
                 const int s = col2sn[j];
                 const int* R = S->rows.data() + S->rowptr[s];
                 const int nrs = S->nr[s], ncs = first[s + 1] - first[s];
+                if (s != cur) {
+                    cur = s;
+                    for (int p = 0; p < nrs; ++p) {
+                        pos[R[p]] = p;
+                        owner_sn[R[p]] = s;
+                    }
+                    flag.assign(nrs, 0);
+                }
                 const long long base = S->off[s] + (long long)(j - first[s]) * S->ld[s];
-                col.clear();
-                col.push_back(j);
                 const int oj = perm[j];
+                const int pj = j - first[s];
+                flag[pj] = 1;
+                int lo = pj, hi = pj;
+                bool ok = true;
                 for (int q = ap[oj]; q < ap[oj + 1]; ++q) {
                     const int i = iperm[ai[q]];
-                    if (i > j) col.push_back(i);
-                }
-                std::sort(col.begin(), col.end());
-                long long w = cstart[j];
-                int p = 0;
-                for (int i : col) {
-                    while (p < nrs && R[p] < i) ++p;
-                    if (p >= nrs) {
-                        bad = j;
+                    if (i <= j) continue;
+                    if (owner_sn[i] != s) {
+                        ok = false;
                         break;
                     }
-                    S->ei[w] = perm[i];
+                    flag[pos[i]] = 1;
+                    hi = std::max(hi, pos[i]);
+                }
+                if (!ok) {
+                    bad = j;
+                    for (int p = lo; p < nrs; ++p) flag[p] = 0;
+                    continue;
+                }
+                long long w = cstart[j];
+                for (int p = lo; p <= hi; ++p) {
+                    if (!flag[p]) continue;
+                    flag[p] = 0;
+                    S->ei[w] = perm[R[p]];
                     S->ej[w] = oj;
                     S->edest[w] = base + (p < ncs ? p : p + S->nb0[s] - ncs);
                     ++w;
