@@ -460,6 +460,30 @@ void etree(int m, const std::vector<int>& pp, const adj_vec& pi, std::vector<int
     }
 }
 
+// The same tree straight from A (CSR: rp, cj), without walking the 4e7 entries of the pattern of A A':
+// the rows of A that share column c form a clique of A A', and for the elimination tree a clique is as
+// good as the chain of its rows in elimination order, so linking every row to the previous row of each of
+// its columns (prev[c]) gives the tree of A A' in O(nnz(A) alpha) (the "column elimination tree" of A').
+void etree_of_aat(int m, int n, const std::vector<int>& rp, const std::vector<int>& cj, const std::vector<int>& perm,
+                  std::vector<int>& parent) {
+    parent.assign(m, -1);
+    std::vector<int> anc(m, -1), prev(n, -1);
+    for (int k = 0; k < m; ++k) {
+        const int row = perm[k];
+        for (int q = rp[row]; q < rp[row + 1]; ++q) {
+            const int c = cj[q];
+            int i = prev[c];
+            while (i != -1 && i < k) {
+                const int nx = anc[i];
+                anc[i] = k;
+                if (nx == -1) parent[i] = k;
+                i = nx;
+            }
+            prev[c] = k;
+        }
+    }
+}
+
 // post[k] = k-th vertex of a depth-first postorder (children visited in ascending order)
 void postorder(int m, const std::vector<int>& parent, std::vector<int>& post) {
     std::vector<int> head(m, -1), next(m, -1);
@@ -561,8 +585,13 @@ int symbolic_analyze(int m, int n, const int* cp, const int* ri, const SymbolicO
     lap("nested dissection ordering");
     if ((int)perm.size() != m) return set_err(err, errlen, "ordering lost vertices (%d of %d)", (int)perm.size(), m);
     for (int i = 0; i < m; ++i) iperm[perm[i]] = i;
-    permute_graph(m, ap, ai, perm, iperm, pp, pi);
-    etree(m, pp, pi, parent);
+    etree_of_aat(m, n, rp, cj, perm, parent);
+    if (getenv("NES_SYMBOLIC_CHECK")) {  // the tree from the full pattern of A A' (what this replaced) must be the same
+        std::vector<int> parent_ref;
+        permute_graph(m, ap, ai, perm, iperm, pp, pi);
+        etree(m, pp, pi, parent_ref);
+        if (parent_ref != parent) return set_err(err, errlen, "elimination tree from A differs from the tree of the pattern of A A'");
+    }
     {
         std::vector<int> post;
         postorder(m, parent, post);

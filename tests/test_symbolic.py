@@ -242,3 +242,19 @@ def test_analysis_does_not_depend_on_the_number_of_host_threads():
         outs.append(r.stdout.strip().splitlines()[-1])
     assert outs[0] == outs[1] == outs[2], outs
     assert int(outs[0].split()[2]) > 3        # a real tree, not a chain of one level
+
+
+def test_elimination_tree_from_A_equals_the_tree_of_the_pattern_of_AAt(monkeypatch):
+    """The analysis builds the elimination tree from the rows of A (column elimination tree of A',
+    O(nnz(A))) instead of walking the pattern of A A'.  NES_SYMBOLIC_CHECK makes it compute both and fail
+    on any difference."""
+    monkeypatch.setenv("NES_SYMBOLIC_CHECK", "1")
+    rng = np.random.default_rng(17)
+    cases = list(_edge_matrices().values())
+    cases += [banded(rng, 700, 1600, 24, 5), banded(rng, 2500, 5200, 9, 4),
+              sp.random(400, 900, density=0.01, random_state=3, format="csc") + sp.eye(400, 900, format="csc"),
+              sp.csc_matrix(np.array([[1.0, 2.0, 0.0], [0.0, 0.0, 0.0], [0.0, 1.0, 1.0]]))]
+    for A in cases:
+        for leaf in (0, 64):
+            S = analyze(A, leaf=leaf)      # raises NesError if the two trees differ
+            assert sorted(S["perm"].tolist()) == list(range(A.shape[0]))
