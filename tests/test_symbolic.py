@@ -245,9 +245,9 @@ def test_analysis_does_not_depend_on_the_number_of_host_threads():
 
 
 def test_elimination_tree_from_A_equals_the_tree_of_the_pattern_of_AAt(monkeypatch):
-    """The analysis builds the elimination tree from the rows of A (column elimination tree of A',
-    O(nnz(A))) instead of walking the pattern of A A'.  NES_SYMBOLIC_CHECK makes it compute both and fail
-    on any difference."""
+    """The analysis builds the elimination tree and the column counts from A itself (column elimination
+    tree of A' and the A'A variant of the skeleton counts, O(nnz(A))) instead of walking the pattern of
+    A A'.  NES_SYMBOLIC_CHECK makes it compute both ways and fail on any difference."""
     monkeypatch.setenv("NES_SYMBOLIC_CHECK", "1")
     rng = np.random.default_rng(17)
     cases = list(_edge_matrices().values())
