@@ -1,5 +1,7 @@
-"""Small end-to-end pass over the dense, sparse and batched paths, sized for compute-sanitizer
-(memcheck / racecheck / synccheck): tools run the kernels 10-100x slower."""
+"""Small end-to-end pass over the dense (two-stream look-ahead), KKT, sparse and PDAS paths in a few
+seconds: a quick check after a kernel change, sized so that it would also run under compute-sanitizer
+(closed on this pool: the tool answers that it stays closed, so bounds and races are checked by the
+parity tests instead)."""
 import sys, numpy as np
 sys.path.insert(0, "."); import _pkg; _pkg.load()
 from cholesky_is_magic_b200 import lpgen, nes, newton_solve, pdas
