@@ -26,6 +26,9 @@
 #include <atomic>
 #include <numeric>
 #include <thread>
+#ifdef __linux__
+#include <sched.h>
+#endif
 
 namespace nes {
 
@@ -55,6 +58,16 @@ int host_threads() {
     static int n = 0;
     if (n == 0) {
         n = (int)std::thread::hardware_concurrency();
+#ifdef __linux__
+        {   // a cpuset smaller than the machine (containers): more threads than CPUs only slow the barriers down
+            cpu_set_t set;
+            CPU_ZERO(&set);
+            if (sched_getaffinity(0, sizeof(set), &set) == 0) {
+                const int allowed = CPU_COUNT(&set);
+                if (allowed > 0 && allowed < n) n = allowed;
+            }
+        }
+#endif
         if (const char* e = getenv("NES_HOST_THREADS")) n = atoi(e);
         n = n < 1 ? 1 : (n > 32 ? 32 : n);
     }
