@@ -1,8 +1,9 @@
 #!/usr/bin/env python
 """bench.py -- FP64 GFLOP/s of the IPM normal-equation step (A diag(theta) A' + Cholesky + solve).
 
-One "step" = one primal-dual affine scaling iteration on the synthetic dense LP of BASELINE config 2
-(m=8192, n=16384): violation (2 GEMV), fused scale+SYRK formation, blocked DMMA Cholesky, two
+Main line, at EVERY N: BASELINE config 3, the dense LP m=32768, n=65536 the north star names (A 17.2 GB +
+M 8.6 GB fit one B200), so 1 -> 2 -> 4 -> 8 GPUs is strong scaling of one LP.  One "step" = one primal-dual
+affine scaling iteration: violation (2 GEMV), fused scale+SYRK formation, blocked DMMA Cholesky, two
 triangular solves, the fused forward GEMV and the transposed GEMV of solve-kkt-newton, the fused
 elementwise passes and the step-length reductions, apply-step.  Algorithmic flops per step
 F(m,n) = m^2 n + m^3/3 + 2 m^2 + 10 m n.
@@ -10,11 +11,14 @@ F(m,n) = m^2 n + m^3/3 + 2 m^2 + 10 m n.
   value     device-resident iterations (state on the GPU, scalars only cross PCIe)
   e2e       the reference-facing C-ABI call nes_kkt_newton with HOST (pinned) vectors: H2D of
             l,u,w,z,e,f,h,g and D2H of dw,dx,dy,dz inside the timed region, A resident
-  roofline  the formation kernel (dmma_nt_kernel<true>): its flops (m^2 n minus the trailing columns whose
-            formation is deferred into the factorization, nes_get_form_flops) / its CUDA-event time, against
-            the measured FP64 DMMA peak (tools/dmma_bench.cu -> profiles/, MEASURED_PEAKS.json has no
-            FP64 entry)
-  cpu_baseline / --impl reference: oracle/baseline.py on the host cores (restated reference CPU path)
+  roofline  the formation kernel (dmma_nt_kernel<true>): its flops / its CUDA-event time, against the
+            measured FP64 DMMA peak (tools/dmma_bench.cu -> profiles/; MEASURED_PEAKS.json has no FP64 entry)
+  residual  after the timed region: ||(As)(As)' x - b|| / ||b|| for a fresh factorization + solve, the
+            products through nes_sdmult -- every line carries the proof that what it timed was correct
+  cpu_baseline / --impl reference: oracle/baseline.py on ALL host cores of the affinity mask (restated
+            reference CPU path); for config 3 each step is an exact 1/32 cut of every stage at full m
+At N=1 the line also carries config2 (m=8192, n=16384: the harder case, + whole-LP seconds), config4
+(sparse m=100k) and config5 (1024 batched LPs of m=256); --config picks one of them as the main line.
 """
 import argparse
 import json
@@ -22,7 +26,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -30,6 +33,9 @@ sys.path.insert(0, ROOT)
 
 METRIC = "FP64 GFLOP/s of ADA^T+Cholesky+solve per IPM iteration"
 FP64_DMMA_PEAK_TFLOPS = 37.1  # measured on this pool's B200 by tools/dmma_bench.cu (profiles/r01_*)
+HBM_PEAK_GBS_FALLBACK = 6551.0
+CPU_SAMPLE_F = 32              # config 3 on the host: 1/32 of every stage per sample (oracle/baseline.py)
+CONFIG_SIZES = {2: (8192, 16384), 3: (32768, 65536)}
 
 
 def flops_step(m, n):
@@ -39,6 +45,18 @@ def flops_step(m, n):
 def flops_kkt(m, n):
     # nes_kkt_newton alone: no violation products (3 GEMV-equivalents instead of 5)
     return float(m) * m * n + float(m) ** 3 / 3.0 + 2.0 * m * m + 6.0 * m * n
+
+
+def hbm_peak():
+    try:
+        return float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"]), "MEASURED_PEAKS.json"
+    except Exception:
+        return HBM_PEAK_GBS_FALLBACK, "fallback (B200_PROFILING.md)"
+
+
+def workload_name(m, n):
+    cfg = {v: k for k, v in CONFIG_SIZES.items()}.get((m, n), "custom")
+    return f"dense LP m={m} n={n} primal-dual affine scaling iteration (BASELINE config {cfg})"
 
 
 class ClockSampler:
@@ -95,54 +113,373 @@ class ClockSampler:
         return out
 
 
+# ------------------------------------------------------------------------------------------------------
+# CPU side (the only place that touches oracle/)
+# ------------------------------------------------------------------------------------------------------
+def cpu_dense_rate(m, n, steps, warmup):
+    """GFLOP/s of the restated reference CPU path for the dense step (m, n) on all host cores.
+    Config 2 runs whole steps; config 3 runs the 1/32 sample.  Returns (value, ms per step, cb dict)."""
+    from oracle import baseline
+    cores = baseline.use_all_host_threads()
+    if float(m) * m * n > 2e12:
+        times, f = baseline.time_sample(m, n, CPU_SAMPLE_F, steps, warmup)
+        sample = baseline.sample_description(m, n, CPU_SAMPLE_F)
+    else:
+        times, f = baseline.time_steps(m, n, steps, warmup)
+        sample = f"whole steps of scale+dsyrk+dpotrf+dpotrs+5 gemv at m={m} n={n}"
+    total = sum(times)
+    val = f * len(times) / total / 1e9
+    cb = {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port",
+          "sample": f"{len(times)} timed samples after {warmup} warm-up: {sample} (oracle/baseline.py, SciPy OpenBLAS; "
+                    f"{f:.4g} flops and {1e3 * total / len(times):.0f} ms per sample)"}
+    return val, 1e3 * total / len(times), cb
+
+
 def reference_arm(args):
-    """The reference's CPU path restated (oracle/baseline.py), all host threads."""
+    """The reference's CPU path restated (oracle/baseline.py), all host threads, rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    from oracle import baseline
+    # torchrun exports OMP_NUM_THREADS=1: BLAS is not imported yet, give it the whole affinity mask
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    for k in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[k] = str(ncpu)
     m, n = args.m, args.n
-    sm, sn, _ = baseline.pick_sample(m, n, budget_s=args.cpu_budget)
-    times, f = baseline.time_steps(sm, sn, args.steps, args.warmup)
-    total = sum(times)
-    val = f * len(times) / total / 1e9
-    cores = baseline.host_threads()
+    val, ms, cb = cpu_dense_rate(m, n, args.steps, args.warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "GFLOP/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times),
-        "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong", "vs_baseline": None,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"dense LP m={m} n={n} primal-dual affine scaling iteration "
-                               f"(BASELINE config {2 if m == 8192 else 3 if m == 32768 else 'custom'})",
-                   "parallelism": "host CPU threads (restated reference path: scale + dsyrk + dpotrf + dpotrs + 5 gemv)",
-                   "sample": f"m={sm} n={sn}", "l2": "inputs larger than L2"},
-        "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": "port",
-                         "sample": f"{args.steps} steps of scale+dsyrk+dpotrf+dpotrs+5 gemv at m={sm} n={sn} "
-                                   "(oracle/baseline.py, SciPy OpenBLAS)"},
+        "config": {"workload": workload_name(m, n),
+                   "parallelism": f"{cb['cores']} host CPU threads (restated reference path: scale + dsyrk + dpotrf "
+                                  "+ dpotrs + 5 gemv); the host does not change with --gpus",
+                   "sample": cb["sample"], "l2": "inputs larger than L2"},
+        "cpu_baseline": cb,
         "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------------
+def run_dense(c, m, n, K, W, seed, world, barrier, local, lp_solve):
+    """Device-resident PDAS iterations (`value`), nes_kkt_newton with pinned host vectors (`e2e`), the
+    post-run residual and optionally the whole LP solve.  Returns a dict of raw measurements."""
+    import ctypes as C
+    import gc
+
+    import numpy as np
+    import torch
+
+    from cholesky_is_magic_b200 import lpgen, nes, pdas
+    from cholesky_is_magic_b200.pdas import free_pdas_A
+    from cholesky_is_magic_b200.standard_form import StandardForm
+
+    # problem: generated on the device (replicated on every rank), b and c through the library's own GEMV
+    A = nes.Matrix.generate_dense(c, m, n, seed)
+    xs, ys, zs = lpgen.aux_vectors(m, n, seed)
+    b = A.sdmult(xs)
+    cvec = A.sdmult(ys, transpose=True) + zs
+    A.free()
+    sf = StandardForm(nvars=n, ncons=m, c=list(enumerate(cvec.tolist())), A=None, b=b,
+                      l=np.zeros(n), u=np.full(n, np.inf), initial_vars=n)
+    st = pdas.make_pdas(sf, scale=True, generated_seed=seed)
+    h = st.handle()
+    out9 = (C.c_double * 9)()
+
+    def one_iteration(repair):
+        rc = c.lib.nes_pdas_one_iteration(h, 1 if repair else 0, out9, c.ptr)
+        if rc != 0:
+            raise SystemExit(f"nes_pdas_one_iteration failed: {rc} {c.error()}")
+        step = out9[2]
+        return (step == step) and step < 1e-6
+
+    gc.collect()
+    gc.disable()  # no collector pauses inside the timed regions
+    repair = False
+    for _ in range(W):
+        repair = one_iteration(repair)
+    c.timing_reset()
+    launches0 = c.launches
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    c.mark_begin()
+    for _ in range(K):
+        repair = one_iteration(repair)
+    ms_total = c.mark_end()
+    barrier()
+    clocks = sampler.stop()
+    launches = c.launches - launches0
+    stage = c.timing()
+    form_flops = c.form_flops
+
+    # ---- e2e: reference-facing call with pinned host vectors -------------------------------------
+    names = ("l", "u", "w", "z")
+    c.lib.nes_pdas_violation(h, (C.c_double * 8)(), c.ptr)
+    host = {k: st.get(k) for k in names}
+    host["e"], host["f"] = host["w"] * host["u"], host["z"] * host["l"]
+    host["g"], host["h"] = st.get("p"), st.get("d")
+    pinned = {k: torch.empty(len(v), dtype=torch.float64).pin_memory() for k, v in host.items()}
+    for k, v in host.items():
+        pinned[k].numpy()[:] = v
+    outs = {k: torch.empty(n if k != "dy" else m, dtype=torch.float64).pin_memory()
+            for k in ("dw", "dx", "dy", "dz")}
+    ptr = lambda t: C.cast(t.data_ptr(), nes._dp)
+    Ak = st.A()            # the state's resident (row-scaled) matrix
+    Lk = nes.Factor(c, Ak)
+
+    def kkt_call():
+        rc = c.lib.nes_kkt_newton(Ak.ptr, Lk.ptr, 0, ptr(pinned["l"]), ptr(pinned["u"]), ptr(pinned["w"]),
+                                  ptr(pinned["z"]), ptr(pinned["e"]), ptr(pinned["f"]), ptr(pinned["g"]),
+                                  ptr(pinned["h"]), ptr(outs["dw"]), ptr(outs["dx"]), ptr(outs["dy"]),
+                                  ptr(outs["dz"]), c.ptr)
+        if rc != 0:
+            raise SystemExit(f"nes_kkt_newton failed: {rc} {c.error()}")
+
+    for _ in range(min(W, 3)):
+        kkt_call()
+    c.timing_reset()
+    barrier()
+    c.mark_begin()
+    t0 = time.perf_counter()
+    e2e_calls = []
+    for _ in range(K):
+        tc = time.perf_counter()
+        kkt_call()
+        e2e_calls.append(round((time.perf_counter() - tc) * 1e3, 3))
+    ms_e2e = c.mark_end()
+    wall_e2e = (time.perf_counter() - t0) * 1e3
+    ms_e2e = max(ms_e2e, wall_e2e)  # host copies are synchronous: wall clock covers them
+    barrier()
+    stage_e2e = c.timing()
+
+    # ---- residual of a fresh factorization + solve with the current theta, through the GEMV kernels ----
+    theta = 1.0 / (host["z"] / host["l"] + host["w"] / host["u"])
+    Ak.scale(np.sqrt(theta))
+    ok = Lk.factorize(Ak)
+    rhs = np.random.default_rng(seed + 7).random(m)
+    x = Lk.solve(rhs)
+    r = Ak.sdmult(Ak.sdmult(x, transpose=True)) - rhs
+    residual = float(np.linalg.norm(r) / np.linalg.norm(rhs)) if ok else float("nan")
+    Ak.unscale()
+    Lk.free()
+    free_pdas_A(st)
+
+    solve_s = solve_iters = solve_obj = solve_gap = None
+    if lp_solve:
+        st2 = pdas.make_pdas(sf, scale=True, generated_seed=seed)
+        st2.handle()
+        c.synchronize()
+        t0 = time.perf_counter()
+        solve_obj, solve_gap, solve_iters = pdas.pdas(st2, 300, native_loop=True)
+        solve_s = time.perf_counter() - t0
+    gc.enable()
+
+    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = t.tolist()
+    F = flops_step(m, n)
+    value = F * K / (ms_total * 1e-3) / 1e9  # one LP distributed over the ranks: F per step whatever N is
+    e2e_val = flops_kkt(m, n) * K / (ms_e2e * 1e-3) / 1e9
+    form_ms, form_cnt = stage["form"]
+    roof = None
+    if form_cnt:
+        ach = form_flops / world / (form_ms / form_cnt * 1e-3) / 1e12  # this rank's share
+        traffic, traffic_source = None, None
+        if (m, n, world) == (8192, 16384, 1):
+            traffic = 6.81e9
+            traffic_source = ("ncu --set full capture profiles/r01_ncu_full_formation_dmma_nt_m8192.details.txt "
+                              "(dram read+write of one launch), not measured in this run; algorithmic 1.34e9")
+        roof = {"bound": "tensor", "kernel": "dmma_nt_kernel<true> (fused scale+SYRK)",
+                "achieved": ach, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                "frac": ach / FP64_DMMA_PEAK_TFLOPS, "traffic": traffic, "traffic_source": traffic_source,
+                "peak_source": "own DMMA issue-rate microbenchmark (tools/dmma_bench.cu, "
+                               "profiles/r01_dmma_peak_and_syrk_v0.log) = 148 SM x 128 flop/clk x 1.965 GHz; "
+                               "MEASURED_PEAKS.json has no FP64 figure; vendor comparator: profiles/r02_vendor_fp64.log",
+                "launch_flops": form_flops / world, "launch_ms": form_ms / form_cnt,
+                "step_frac_of_peak": value / world / 1e3 / FP64_DMMA_PEAK_TFLOPS}
+    return {
+        "value": value, "ms_per_step": ms_total / K, "e2e_value": e2e_val, "ms_e2e": ms_e2e / K,
+        "e2e_calls": e2e_calls, "launches": int(launches), "clocks": clocks, "roofline": roof,
+        "stage_ms_per_step": {k: v[0] / K for k, v in stage.items()},
+        "e2e_stage_ms_per_step": {k: v[0] / K for k, v in stage_e2e.items()},
+        "residual": residual,
+        "lp_solve": {"seconds": solve_s, "iterations": solve_iters, "objective": solve_obj, "gap": solve_gap,
+                     "converged": (solve_gap is not None and solve_gap < 1e-4)},
+    }
+
+
+def dist_label(c, m, world):
+    if world == 1:
+        return "single GPU"
+    import ctypes as C
+    nbo, P, Q = C.c_int(0), C.c_int(1), C.c_int(world)
+    c.lib.nes_dist_layout(c.ptr, m, C.byref(nbo), C.byref(P), C.byref(Q))
+    return (f"M and L 2D block-cyclic by {nbo.value}-column/row blocks over {world} GPUs ({P.value} x {Q.value} "
+            "process grid), NCCL panel broadcasts over NVLink; A and vectors replicated, GEMVs split by columns")
+
+
+def run_sparse(c, K, W, with_cpu):
+    """BASELINE config 4: sparse LP m=100k, n=250k, ~10 nnz/col (banded, bandwidth 400).  Step = one PDAS
+    iteration through nes_pdas_one_iteration (violation SpMVs, assembly, supernodal factorization, solves)."""
+    import ctypes as C
+
+    import numpy as np
+
+    from cholesky_is_magic_b200 import lpgen, pdas
+    m, n, bw = 100000, 250000, 400
+    sf = lpgen.sparse_lp(m, n, nnz_per_col=10, bandwidth=bw, seed=0)
+    nnz = len(sf.A.value)
+    out = {"workload": f"sparse LP m={m} n={n} nnz={nnz} (banded, bandwidth {bw}) primal-dual affine scaling "
+                       "iteration with the supernodal sparse Cholesky (BASELINE config 4)"}
+    dbound = 1e-8
+    c.set("dbound", dbound)
+    try:
+        st = pdas.make_pdas(sf)
+        t0 = time.perf_counter()
+        h = st.handle()                     # upload; the symbolic analysis happens in the first iteration
+        out9 = (C.c_double * 9)()
+        t1 = time.perf_counter()
+        rc = c.lib.nes_pdas_one_iteration(h, 0, out9, c.ptr)
+        c.synchronize()
+        out["first_iteration_s_incl_analysis"] = time.perf_counter() - t1
+        if rc != 0:
+            raise SystemExit(f"config 4: nes_pdas_one_iteration failed: {rc} {c.error()}")
+        anz, aatfl, lnz, fl = c.anz, c.aatfl, c.lnz, c.fl
+        repair = False
+        for _ in range(W):
+            c.lib.nes_pdas_one_iteration(h, 0, out9, c.ptr)
+        c.timing_reset()
+        l0 = c.launches
+        c.synchronize()
+        c.mark_begin()
+        for _ in range(K):
+            rc = c.lib.nes_pdas_one_iteration(h, 0, out9, c.ptr)
+            if rc != 0:
+                raise SystemExit(f"config 4: nes_pdas_one_iteration failed: {rc} {c.error()}")
+        ms = c.mark_end() / K
+        stage = {k: v[0] / K for k, v in c.timing().items()}
+        F = aatfl + fl + 4.0 * lnz + 10.0 * nnz
+        Bt = 8.0 * (2.0 * lnz + anz) + 12.0 * nnz
+        peak_hbm, src = hbm_peak()
+        out.update({
+            "value": F / (ms * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": ms, "steps": K,
+            "stage_ms_per_step": stage, "gpu_launches_per_step": (c.launches - l0) / K,
+            "counters": {"anz": anz, "aatfl": aatfl, "lnz": lnz, "fl": fl, "nnz": nnz},
+            "flops_per_step": F, "bytes_per_step": Bt,
+            "roofline_tensor": {"achieved": F / (ms * 1e-3) / 1e12, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
+                                "frac": F / (ms * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS},
+            "roofline_hbm": {"achieved": Bt / (ms * 1e-3) / 1e9, "peak": peak_hbm, "unit": "GB/s",
+                             "frac": Bt / (ms * 1e-3) / 1e9 / peak_hbm, "peak_source": src},
+            "factor_only": {"ms": stage.get("factor"), "gflops": (fl / (stage["factor"] * 1e-3) / 1e9) if stage.get("factor") else None},
+        })
+        pdas.free_pdas_A(st)
+        st2 = pdas.make_pdas(sf)
+        c.synchronize()
+        t0 = time.perf_counter()
+        try:
+            obj, gap, it = pdas.pdas(st2, 400, native_loop=True)
+            out["lp_solve"] = {"seconds": time.perf_counter() - t0, "iterations": it, "objective": obj, "gap": gap,
+                               "converged": gap < 1e-4, "dbound": dbound,
+                               "note": "dbound=1e-8 is NOT the reference's setting (0, wrapper.c:34 never set): with 0 "
+                                       "the normal matrix turns numerically indefinite before the 1e-4 gap is reached"}
+        except Exception as e:  # reported, never masked
+            out["lp_solve"] = {"error": str(e), "dbound": dbound}
+    finally:
+        c.set("dbound", 0.0)
+    if with_cpu:
+        from oracle import baseline
+        cores = baseline.use_all_host_threads()
+        theta = 0.1 + 10 * np.random.default_rng(0).random(n)
+        r = baseline.sparse_step_cpu(sf.A.row, sf.A.col, sf.A.value, m, n, theta, np.random.default_rng(1).random(m))
+        r.update({"kind": "port", "cores": cores,
+                  "what": "one normal-equation step: scipy.sparse A diag(theta) A' + SuperLU (symmetric mode) "
+                          "factor + solve; sequential library code, the reference's CHOLMOD is not in this image"})
+        out["cpu_baseline"] = r
+    return out
+
+
+def run_batched(c, K, W, with_cpu):
+    """BASELINE config 5: 1024 independent dense LPs of m=256 (n=512): step = one batched normal-equation
+    solve through nes_batch_normal_solve (HOST scale/rhs in, HOST solutions out)."""
+    import numpy as np
+
+    from cholesky_is_magic_b200 import batched
+    B, m, n = 1024, 256, 512
+    rng = np.random.default_rng(0)
+    A = rng.random((B, m, n))
+    A[:, np.arange(m), np.arange(m)] += 1.0
+    xs = 0.1 + 10 * rng.random((B, n))
+    b = np.einsum("bmn,bn->bm", A, xs)
+    ys = rng.uniform(-1, 1, (B, m))
+    zs = 0.1 + 10 * rng.random((B, n))
+    cc = np.einsum("bmn,bm->bn", A, ys) + zs
+    bt = batched.Batch(A, c=cc, b=b, l=np.zeros((B, n)), u=np.full((B, n), np.inf), x=np.ones((B, n)))
+    s = np.sqrt(0.1 + 10 * rng.random((B, n)))
+    rhs = rng.random((B, m))
+    F = (float(m) * m * n + m ** 3 / 3.0 + 2.0 * m * m) * B
+    for _ in range(W):
+        x, stt = bt.normal_solve(s, rhs)
+    c.timing_reset()
+    l0 = c.launches
+    t0 = time.perf_counter()
+    for _ in range(K):
+        x, stt = bt.normal_solve(s, rhs)
+    wall = (time.perf_counter() - t0) / K * 1e3
+    stage = {k: v[0] / K for k, v in c.timing().items()}
+    dev = sum(stage.values())
+    k0 = 7
+    M = (A[k0] * s[k0] ** 2) @ A[k0].T
+    res = float(np.linalg.norm(M @ x[k0] - rhs[k0]) / np.linalg.norm(rhs[k0]))
+    out = {"workload": f"{B} independent dense LPs m={m} n={n}: batched normal-equation solve (BASELINE config 5)",
+           "value": F / (dev * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": dev, "steps": K,
+           "flops_per_step": F, "stage_ms_per_step": stage, "gpu_launches_per_step": (c.launches - l0) / K,
+           "roofline": {"bound": "tensor", "achieved": F / (dev * 1e-3) / 1e12, "peak": FP64_DMMA_PEAK_TFLOPS,
+                        "unit": "TFLOP/s", "frac": F / (dev * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS,
+                        "factor_frac": (B * m ** 3 / 3.0 / (stage["factor"] * 1e-3) / 1e12 / FP64_DMMA_PEAK_TFLOPS)
+                        if stage.get("factor") else None},
+           "e2e": {"value": F / (wall * 1e-3) / 1e9, "unit": "GFLOP/s", "ms_per_step": wall,
+                   "h2d_bytes_per_step": 8 * B * (n + m), "d2h_bytes_per_step": 8 * B * m + 4 * B},
+           "residual_problem_7": res, "failed_problems": int(stt.sum())}
+    t0 = time.perf_counter()
+    obj, xx, rr, iters = bt.affine_scaling(3000)
+    out["lp_solve"] = {"seconds": time.perf_counter() - t0, "max_iterations": int(iters.max()),
+                       "mean_iterations": float(iters.mean()), "max_residual": float(rr.max()),
+                       "what": "batched affine-scaling of all 1024 LPs (affine-scaling.lisp:265-297)"}
+    bt.free()
+    if with_cpu:
+        from oracle import baseline
+        cores = baseline.use_all_host_threads()
+        baseline.batch_step_cpu(A[:64], s[:64], rhs[:64])
+        sec = baseline.batch_step_cpu(A, s, rhs)
+        out["cpu_baseline"] = {"value": F / sec / 1e9, "unit": "GFLOP/s", "cores": cores, "kind": "port",
+                               "sample": f"one pass over the {B} problems: scale + dsyrk + dpotrf + dpotrs each (oracle/baseline.py)"}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--m", type=int, default=None, help="rows (default: 8192 on 1 GPU, 32768 on N>1)")
+    ap.add_argument("--config", type=int, default=3, choices=[2, 3, 4, 5],
+                    help="BASELINE config of the main line (default 3: m=32768, n=65536, at every N)")
+    ap.add_argument("--m", type=int, default=None, help="rows of a custom dense LP")
     ap.add_argument("--n", type=int, default=None, help="columns (default 2m)")
     ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU work per baseline step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-solve", action="store_true", help="skip the whole-LP-solve timing")
+    ap.add_argument("--no-solve", action="store_true", help="skip the whole-LP-solve timings")
+    ap.add_argument("--no-extras", action="store_true", help="N=1: skip the config2/config4/config5 objects")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
-    world_env = int(os.environ.get("WORLD_SIZE", "1"))
     if args.m is None:
-        # N = 1: BASELINE config 2 (the configuration the metric is quoted on); N > 1: config 3, the
-        # one BASELINE.json distributes over 2/4/8 GPUs (strong scaling of one LP)
-        args.m = 8192 if max(world_env, args.gpus) == 1 else 32768
+        args.m = CONFIG_SIZES.get(args.config, CONFIG_SIZES[3])[0]
     if args.n is None:
         args.n = 2 * args.m
 
@@ -150,13 +487,12 @@ def main():
         reference_arm(args)
         return
 
-    import numpy as np
     import torch
     import torch.distributed as dist
 
     import _pkg
     _pkg.load()
-    from cholesky_is_magic_b200 import lpgen, nes, pdas
+    from cholesky_is_magic_b200 import nes
     from cholesky_is_magic_b200.sparse_cholesky import with_cholmod
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -169,6 +505,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     m, n, K, W = args.m, args.n, args.steps, args.warmup
+    with_cpu = (rank == 0 and world == 1 and not args.no_cpu_baseline)
 
     def barrier():
         if world > 1:
@@ -184,165 +521,64 @@ def main():
                 idt.copy_(torch.frombuffer(bytearray(nes.unique_id()), dtype=torch.uint8))
             dist.broadcast(idt, 0)
             c.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
-        # ---- problem: generated on the device (replicated on every rank), b and c through the
-        # library's own GEMV ----------
-        A = nes.Matrix.generate_dense(c, m, n, args.seed)
-        xs, ys, zs = lpgen.aux_vectors(m, n, args.seed)
-        b = A.sdmult(xs)
-        cvec = A.sdmult(ys, transpose=True) + zs
-        A.free()
-        from cholesky_is_magic_b200.standard_form import StandardForm
-        sf = StandardForm(nvars=n, ncons=m, c=list(enumerate(cvec.tolist())), A=None, b=b,
-                          l=np.zeros(n), u=np.full(n, np.inf), initial_vars=n)
-        st = pdas.make_pdas(sf, scale=True, generated_seed=args.seed)
-        h = st.handle()
-        import ctypes as C
-        out9 = (C.c_double * 9)()
 
-        def one_iteration(repair):
-            rc = c.lib.nes_pdas_one_iteration(h, 1 if repair else 0, out9, c.ptr)
-            if rc != 0:
-                raise SystemExit(f"nes_pdas_one_iteration failed: {rc} {c.error()}")
-            step = out9[2]
-            return (step == step) and step < 1e-6
+        if args.config in (4, 5):
+            if world > 1:
+                raise SystemExit("--config 4/5 main lines are single-GPU measurements")
+            r = (run_sparse if args.config == 4 else run_batched)(c, K, W, with_cpu)
+            line = {"metric": METRIC, "value": r["value"], "unit": "GFLOP/s", "n_gpus": 1, "steps": K, "warmup": W,
+                    "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                    "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": {"workload": r["workload"], "parallelism": "single GPU"},
+                    "gpu_launches": int(r["gpu_launches_per_step"] * K), "detail": r}
+            print(json.dumps(line), flush=True)
+            return
 
-        # ---- device-resident iterations: `value` -------------------------------------------------
-        import gc
-        gc.collect()
-        gc.disable()  # no collector pauses inside the timed regions
-        repair = False
-        for _ in range(W):
-            repair = one_iteration(repair)
-        c.timing_reset()
-        launches0 = c.launches
-        sampler = ClockSampler(local)
-        barrier()
-        sampler.start()
-        c.mark_begin()
-        for _ in range(K):
-            repair = one_iteration(repair)
-        ms_total = c.mark_end()
-        barrier()
-        clocks = sampler.stop()
-        launches = c.launches - launches0
-        stage = c.timing()
-        # flops of the formation launch the "form" stage times: m^2 n, minus the d^2 n of the trailing d
-        # columns of M when the library forms those inside the factorization stage (dense_chol.cu)
-        form_flops = c.form_flops
-
-        # ---- e2e: reference-facing call with pinned host vectors --------------------------------
-        names = ("l", "u", "w", "z")
-        c.lib.nes_pdas_violation(h, (C.c_double * 8)(), c.ptr)
-        host = {k: st.get(k) for k in names}
-        host["e"], host["f"] = host["w"] * host["u"], host["z"] * host["l"]
-        host["g"], host["h"] = st.get("p"), st.get("d")
-        pinned = {k: torch.empty(len(v), dtype=torch.float64).pin_memory() for k, v in host.items()}
-        for k, v in host.items():
-            pinned[k].numpy()[:] = v
-        outs = {k: torch.empty(n if k != "dy" else m, dtype=torch.float64).pin_memory()
-                for k in ("dw", "dx", "dy", "dz")}
-        ptr = lambda t: C.cast(t.data_ptr(), nes._dp)
-        Ak = st.A()            # the state's resident (row-scaled) matrix
-        Lk = nes.Factor(c, Ak)
-
-        def kkt_call():
-            rc = c.lib.nes_kkt_newton(Ak.ptr, Lk.ptr, 0, ptr(pinned["l"]), ptr(pinned["u"]), ptr(pinned["w"]),
-                                      ptr(pinned["z"]), ptr(pinned["e"]), ptr(pinned["f"]), ptr(pinned["g"]),
-                                      ptr(pinned["h"]), ptr(outs["dw"]), ptr(outs["dx"]), ptr(outs["dy"]),
-                                      ptr(outs["dz"]), c.ptr)
-            if rc != 0:
-                raise SystemExit(f"nes_kkt_newton failed: {rc} {c.error()}")
-
-        for _ in range(3):
-            kkt_call()
-        c.timing_reset()
-        barrier()
-        c.mark_begin()
-        t0 = time.perf_counter()
-        e2e_calls = []
-        for _ in range(K):
-            tc = time.perf_counter()
-            kkt_call()
-            e2e_calls.append(round((time.perf_counter() - tc) * 1e3, 3))
-        ms_e2e = c.mark_end()
-        wall_e2e = (time.perf_counter() - t0) * 1e3
-        ms_e2e = max(ms_e2e, wall_e2e)  # host copies are synchronous: wall clock covers them
-        barrier()
-        stage_e2e = c.timing()
-        Lk.free()
-
-        # ---- whole LP solve (second half of the BASELINE metric) --------------------------------
-        solve_s, solve_iters = None, None
-        if not args.no_solve and world == 1 and m <= 8192:
-            from cholesky_is_magic_b200.pdas import free_pdas_A
-            free_pdas_A(st)
-            st2 = pdas.make_pdas(sf, scale=True, generated_seed=args.seed)
-            st2.handle()
-            c.synchronize()
-            t0 = time.perf_counter()
-            obj, gap, solve_iters = pdas.pdas(st2, 200, native_loop=True)
-            solve_s = time.perf_counter() - t0
-        else:
-            from cholesky_is_magic_b200.pdas import free_pdas_A
-            free_pdas_A(st)
-
-    # ---- reduce over ranks (max time), one JSON line from rank 0 --------------------------------
-    t = torch.tensor([ms_total, ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = t.tolist()
-    F = flops_step(m, n)
-    # one LP distributed over the ranks: the job's flops are F per step whatever N is
-    value = F * K / (ms_total * 1e-3) / 1e9
-    e2e_val = flops_kkt(m, n) * K / (ms_e2e * 1e-3) / 1e9
-    form_ms, form_cnt = stage["form"]
-    roof = None
-    if form_cnt:
-        ach = form_flops / world / (form_ms / form_cnt * 1e-3) / 1e12  # this rank's share
-        roof = {"bound": "tensor", "kernel": "dmma_nt_kernel<true> (fused scale+SYRK)",
-                "achieved": ach, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
-                "frac": ach / FP64_DMMA_PEAK_TFLOPS,
-                # dram__bytes_read.sum + dram__bytes_write.sum of this kernel at m=8192, n=16384 from
-                # profiles/r01_ncu_full_formation_dmma_nt_m8192.details.txt (ncu --set full); algorithmic
-                # bytes are 8mn + 4m^2 = 1.34e9
-                "traffic": 6.81e9 if (m, n, world) == (8192, 16384, 1) else None,
-                "traffic_unit": "bytes per launch (DRAM read+write, ncu)",
-                "peak_source": "own DMMA issue-rate microbenchmark (tools/dmma_bench.cu, profiles/r01_dmma_peak_and_syrk_v0.log); "
-                               "MEASURED_PEAKS.json has no FP64 figure",
-                "launch_flops": form_flops / world,
-                "deferred_formation_flops": float(m) * m * n - form_flops,
-                "step_frac_of_peak": value / world / 1e3 / FP64_DMMA_PEAK_TFLOPS}
-    line = {
-        "metric": METRIC, "value": value, "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
-        "ms_per_step": ms_total / K, "higher_is_better": True,
-        "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": f"dense LP m={m} n={n} primal-dual affine scaling iteration "
-                               f"(BASELINE config {2 if m == 8192 else 3 if m == 32768 else 'custom'})",
-                   "parallelism": (f"M and L block-cyclic by {256 if m <= 12288 else 512}-column panels over "
-                                   f"{world} GPUs (1 x {world} grid), ncclBroadcast per panel; A and vectors replicated")
-                   if world > 1 else "single GPU",
-                   "l2": f"inputs larger than L2 (A {8e-9 * m * n:.2f} GB, M {8e-9 * m * m:.2f} GB vs 126 MB)"},
-        "e2e": {"value": e2e_val, "unit": "GFLOP/s", "ms_per_step": ms_e2e / K,
-                "h2d_bytes_per_step": 8 * (7 * n + m), "d2h_bytes_per_step": 8 * (3 * n + m),
-                "call": "nes_kkt_newton (solve-kkt-newton) with pinned host vectors, A resident",
-                "calls_ms": e2e_calls},
-        "gpu_launches": int(launches),
-        "clocks": clocks,
-        "roofline": roof,
-        "stage_ms_per_step": {k: v[0] / K for k, v in stage.items()},
-        "e2e_stage_ms_per_step": {k: v[0] / K for k, v in stage_e2e.items()},
-        "lp_solve": {"seconds": solve_s, "iterations": solve_iters},
-    }
-    if rank == 0:
-        if world == 1 and not args.no_cpu_baseline:
-            from oracle import baseline
-            sm_, sn_, _ = baseline.pick_sample(m, n, budget_s=args.cpu_budget)
-            times, f = baseline.time_steps(sm_, sn_, 1, 1)
-            line["cpu_baseline"] = {
-                "value": f / times[0] / 1e9, "unit": "GFLOP/s", "cores": baseline.host_threads(), "kind": "port",
-                "sample": f"1 step of scale+dsyrk+dpotrf+dpotrs+5 gemv at m={sm_} n={sn_} (oracle/baseline.py)"}
-        print(json.dumps(line), flush=True)
+        label = dist_label(c, m, world)
+        d = run_dense(c, m, n, K, W, args.seed, world, barrier, local,
+                      lp_solve=(not args.no_solve and world == 1 and m <= 8192))
+        line = {
+            "metric": METRIC, "value": d["value"], "unit": "GFLOP/s", "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": d["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(m, n), "parallelism": label,
+                       "l2": f"inputs larger than L2 (A {8e-9 * m * n:.2f} GB, M {8e-9 * m * m:.2f} GB vs 126 MB)"},
+            "e2e": {"value": d["e2e_value"], "unit": "GFLOP/s", "ms_per_step": d["ms_e2e"],
+                    "h2d_bytes_per_step": 8 * (7 * n + m), "d2h_bytes_per_step": 8 * (3 * n + m),
+                    "call": "nes_kkt_newton (solve-kkt-newton) with pinned host vectors, A resident",
+                    "calls_ms": d["e2e_calls"]},
+            "gpu_launches": d["launches"], "clocks": d["clocks"], "roofline": d["roofline"],
+            "residual": d["residual"],
+            "residual_what": "||(As)(As)'x - b|| / ||b|| of a fresh factorization + solve after the timed region, "
+                             "products through nes_sdmult",
+            "stage_ms_per_step": d["stage_ms_per_step"], "e2e_stage_ms_per_step": d["e2e_stage_ms_per_step"],
+        }
+        if d["lp_solve"]["seconds"] is not None:
+            line["lp_solve"] = d["lp_solve"]
+        if rank == 0 and world == 1:
+            if with_cpu:
+                _, _, line["cpu_baseline"] = cpu_dense_rate(m, n, 3, 1)
+            if not args.no_extras and args.config == 3 and (m, n) == CONFIG_SIZES[3]:
+                m2, n2 = CONFIG_SIZES[2]
+                d2 = run_dense(c, m2, n2, max(K, 10), W, args.seed, 1, barrier, local, lp_solve=not args.no_solve)
+                c2 = {"workload": workload_name(m2, n2), "value": d2["value"], "unit": "GFLOP/s",
+                      "ms_per_step": d2["ms_per_step"], "steps": max(K, 10),
+                      "e2e": {"value": d2["e2e_value"], "ms_per_step": d2["ms_e2e"]},
+                      "roofline": d2["roofline"], "residual": d2["residual"],
+                      "stage_ms_per_step": d2["stage_ms_per_step"], "lp_solve": d2["lp_solve"]}
+                if with_cpu:
+                    v2, ms2, cb2 = cpu_dense_rate(m2, n2, 3, 1)
+                    c2["cpu_baseline"] = cb2
+                    if d2["lp_solve"]["iterations"]:
+                        c2["lp_solve"]["cpu_seconds"] = d2["lp_solve"]["iterations"] * ms2 * 1e-3
+                        c2["lp_solve"]["cpu_seconds_how"] = (
+                            f"estimated: {d2['lp_solve']['iterations']} iterations x {ms2:.0f} ms per restated CPU step "
+                            f"on {cb2['cores']} cores (a whole CPU solve was run once: profiles/r02_cpu_whole_solve_config2.log)")
+                line["config2"] = c2
+                line["config4"] = run_sparse(c, max(K, 10), W, with_cpu)
+                line["config5"] = run_batched(c, max(K, 10), W, with_cpu)
+        if rank == 0:
+            print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -174,6 +174,16 @@ int nes_comm_finalize(nes_ctx* c) {
     return 0;
 }
 
+// Layout the dense factorization uses for an m x m normal matrix on this context's ranks: distribution
+// block (= outer panel width) and the P x Q process grid.
+int nes_dist_layout(const nes_ctx* c, int m, int* nbo, int* P, int* Q) {
+    const int nr = c ? c->nranks : 1;
+    if (nbo) *nbo = dense_outer_block(m, nr);
+    if (P) *P = 1;
+    if (Q) *Q = nr;
+    return 0;
+}
+
 int nes_comm_rank(const nes_ctx* c) { return c ? c->rank : 0; }
 int nes_comm_nranks(const nes_ctx* c) { return c ? c->nranks : 1; }
 

@@ -121,6 +121,7 @@ def _prototypes(lib):
     fn("nes_comm_rank", C.c_int, _vp)
     fn("nes_comm_nranks", C.c_int, _vp)
     fn("nes_dist_plan", C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int)
+    fn("nes_dist_layout", C.c_int, _vp, C.c_int, _ip, _ip, _ip)
     fn("nes_mark_begin", C.c_int, _vp)
     fn("nes_mark_end", C.c_int, _vp, _dp)
     fn("nes_approx_create", _vp, _vp, _dp, _dp, _dp, _dp, _ip, _ip, _dp, _ip, C.c_int, _dp, C.c_double, C.c_int,

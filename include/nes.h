@@ -234,6 +234,8 @@ int nes_comm_nranks(const nes_ctx* c);
 /* host-only: the 128x128 tiles of tril(M) owned by `rank` (m rows, `nranks` ranks); returns the count
  * and fills up to `cap` (tile row, tile column) pairs. */
 int nes_dist_plan(int m, int nranks, int rank, int* tile_rows, int* tile_cols, int cap);
+/* distribution block and P x Q process grid the dense factorization of an m x m matrix uses on c's ranks */
+int nes_dist_layout(const nes_ctx* c, int m, int* nbo, int* P, int* Q);
 
 /* ---- first-order solver of approx.lisp (APPROX on the penalised primal-dual LP) ---------------------
  * K: sparse matrix with one row per `quadratic` constraint (approx.lisp:36-58, built by make-approx
