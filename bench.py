@@ -264,6 +264,7 @@ def run_dense(c, m, n, K, W, seed, world, barrier, local, lp_solve):
     x = Lk.solve(rhs)
     r = Ak.sdmult(Ak.sdmult(x, transpose=True)) - rhs
     residual = float(np.linalg.norm(r) / np.linalg.norm(rhs)) if ok else float("nan")
+    chol_residual = Lk.residual(Ak) if ok else float("nan")   # ||L L' - M||_F / ||M||_F, whole matrix, on the device
     Ak.unscale()
     Lk.free()
     free_pdas_A(st)
@@ -308,7 +309,7 @@ def run_dense(c, m, n, K, W, seed, world, barrier, local, lp_solve):
         "e2e_calls": e2e_calls, "launches": int(launches), "clocks": clocks, "roofline": roof,
         "stage_ms_per_step": {k: v[0] / K for k, v in stage.items()},
         "e2e_stage_ms_per_step": {k: v[0] / K for k, v in stage_e2e.items()},
-        "residual": residual,
+        "residual": residual, "chol_residual": chol_residual,
         "lp_solve": {"seconds": solve_s, "iterations": solve_iters, "objective": solve_obj, "gap": solve_gap,
                      "converged": (solve_gap is not None and solve_gap < 1e-4)},
     }
@@ -548,7 +549,8 @@ def main():
                     "call": "nes_kkt_newton (solve-kkt-newton) with pinned host vectors, A resident",
                     "calls_ms": d["e2e_calls"]},
             "gpu_launches": d["launches"], "clocks": d["clocks"], "roofline": d["roofline"],
-            "residual": d["residual"],
+            "residual": d["residual"], "chol_residual": d["chol_residual"],
+            "chol_residual_what": "||L L' - M||_F / ||M||_F over the whole matrix on the device (nes_factor_residual; gate 1e-12)",
             "residual_what": "||(As)(As)'x - b|| / ||b|| of a fresh factorization + solve after the timed region, "
                              "products through nes_sdmult",
             "stage_ms_per_step": d["stage_ms_per_step"], "e2e_stage_ms_per_step": d["e2e_stage_ms_per_step"],
@@ -564,7 +566,7 @@ def main():
                 c2 = {"workload": workload_name(m2, n2), "value": d2["value"], "unit": "GFLOP/s",
                       "ms_per_step": d2["ms_per_step"], "steps": max(K, 10),
                       "e2e": {"value": d2["e2e_value"], "ms_per_step": d2["ms_e2e"]},
-                      "roofline": d2["roofline"], "residual": d2["residual"],
+                      "roofline": d2["roofline"], "residual": d2["residual"], "chol_residual": d2["chol_residual"],
                       "stage_ms_per_step": d2["stage_ms_per_step"], "lp_solve": d2["lp_solve"]}
                 if with_cpu:
                     v2, ms2, cb2 = cpu_dense_rate(m2, n2, 3, 1)

@@ -156,7 +156,8 @@ def affine_scaling(state, max_iter=100000, native_loop=False):
             iters, obj, res = C.c_int(0), C.c_double(0), C.c_double(0)
             rc = c.check(c.lib.nes_affine_solve(state.handle(), max_iter, C.byref(iters), C.byref(obj),
                                                 C.byref(res), c.ptr), "nes_affine_solve")
-            if rc != 0:
+            state.converged = rc == 0
+            if rc not in (0, nes.NES_MAXITER):
                 raise nes.NesError("affine-scaling: Cholesky failed")
             return obj.value, state.x, res.value, iters.value
         i = 0
@@ -164,9 +165,11 @@ def affine_scaling(state, max_iter=100000, native_loop=False):
             _, cont = one_iteration(state, (i + 1) % 16 == 0)
             norm, obj = residual(state)
             if not (cont or norm > 1e-6 * state.ncons):
+                state.converged = True
                 return obj, state.x, norm, i + 1
             i += 1
         norm, obj = residual(state)
+        state.converged = False
         return obj, state.x, norm, i
     finally:
         free_affine_A(state)

@@ -115,15 +115,17 @@ __global__ void trtri_diag_kernel(const double* __restrict__ M, long long ld, in
                                   const double* __restrict__ dinv_g, double* __restrict__ Winv);
 
 static int chol_configure(nes_ctx* c) {
-    static bool done = false;
-    if (done) return 0;
-    NES_CUDA(c, cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     CH_DIAG_SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     TR_SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(trtri_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     TI_SMEM_FWD));
-    done = true;
+    static PerDeviceOnce once;
+    int dev;
+    if (!once.begin(&dev)) return 0;
+    cudaError_t e = cudaFuncSetAttribute(potrf_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         CH_DIAG_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(trsm_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TR_SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(trtri_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TI_SMEM_FWD);
+    once.finish(dev, e == cudaSuccess);
+    NES_CUDA(c, e);
     return 0;
 }
 

@@ -316,11 +316,13 @@ trsv_dataflow_kernel(const double* __restrict__ M, long long ld, int m, const do
 
 static int dense_trsv_dataflow(nes_ctx* c, const double* M, long long ld, int m, const double* Winv,
                                double* d_x, int* d_flags, int* epoch) {
-    static bool configured = false;
-    if (!configured) {
-        NES_CUDA(c, cudaFuncSetAttribute(trsv_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         DF_SMEM));
-        configured = true;
+    static PerDeviceOnce once;
+    int dev;
+    if (once.begin(&dev)) {
+        cudaError_t e = cudaFuncSetAttribute(trsv_dataflow_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             DF_SMEM);
+        once.finish(dev, e == cudaSuccess);
+        NES_CUDA(c, e);
     }
     const int nblk = (m + SV_NB - 1) / SV_NB;
     const int grid = nblk < c->num_sms ? nblk : c->num_sms;
@@ -339,11 +341,13 @@ static int dense_trsv_dataflow(nes_ctx* c, const double* M, long long ld, int m,
 // the right-hand sides and of dinv).  nbatch = 1, brows = 0 is the single-matrix case.
 int dense_trsv_sweeps(nes_ctx* c, const double* M, long long ld, int m, const double* dinv, double* d_x,
                       int nbatch, int brows) {
-    static bool configured = false;
-    if (!configured) {
-        NES_CUDA(c, cudaFuncSetAttribute(trsv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         SV_SMEM));
-        configured = true;
+    static PerDeviceOnce once;
+    int dev;
+    if (once.begin(&dev)) {
+        cudaError_t e = cudaFuncSetAttribute(trsv_diag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             SV_SMEM);
+        once.finish(dev, e == cudaSuccess);
+        NES_CUDA(c, e);
     }
     // L y = b
     for (int j0 = 0; j0 < m; j0 += SV_NB) {

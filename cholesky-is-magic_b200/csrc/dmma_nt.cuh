@@ -439,16 +439,16 @@ inline int make_operand_map(CUtensorMap* map, const double* base, long long rows
 }
 
 inline cudaError_t nt_configure() {
-    static bool done = false;
-    if (done) return cudaSuccess;
+    static PerDeviceOnce once;  // per translation unit (each has its own copy of the kernel) and per device
+    int dev;
+    if (!once.begin(&dev)) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(dmma_nt_kernel<true>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, NT_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(dmma_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             NT_SMEM_BYTES);
-    if (e != cudaSuccess) return e;
-    done = true;
-    return cudaSuccess;
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(dmma_nt_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 NT_SMEM_BYTES);
+    once.finish(dev, e == cudaSuccess);
+    return e;
 }
 
 // Tail-balancing plan for a launch with `ntiles` equal-cost tiles of `kchunks` k-chunks on `grid`

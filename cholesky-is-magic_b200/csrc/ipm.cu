@@ -42,7 +42,8 @@ __global__ void kkt_pre_kernel(size_t n, int filters, const double* __restrict__
                                double* __restrict__ wp, double* __restrict__ ep, double* __restrict__ lp,
                                double* __restrict__ fp, double* __restrict__ d_out,
                                double* __restrict__ h3, double* __restrict__ s_out,
-                               double* __restrict__ v_out) {
+                               double* __restrict__ v_out, int* __restrict__ div0) {
+    bool zero_div = false;
     for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n;
          i += (size_t)gridDim.x * blockDim.x) {
         double l = l_in[i], u = u_in[i], w = w_in[i], z = z_in[i], e = e_in[i], f = f_in[i], h = h_in[i];
@@ -58,6 +59,9 @@ __global__ void kkt_pre_kernel(size_t n, int filters, const double* __restrict__
                 z = 0.0;
             }
         }
+        // scale-U / scale-Z divide by u and z: filter-Z leaves z = 0 behind (the reference traps here with
+        // DIVISION-BY-ZERO under SBCL); the flag turns the resulting NaN factorization into an explicit status
+        zero_div |= (u == 0.0) | (z == 0.0);
         const double iu = 1.0 / u;
         w = iu * w;
         e = iu * e;
@@ -78,6 +82,7 @@ __global__ void kkt_pre_kernel(size_t n, int filters, const double* __restrict__
         s_out[i] = sqrt(l * d);
         v_out[i] = l * h - f;
     }
+    if (zero_div) *div0 = 1;
 }
 
 // newton-solve.lisp:127-137: dz = h3 - d (A'dy);  dx = f' - dz l';  dw = dx w' + e'.
@@ -123,6 +128,7 @@ struct KktVectors {
     // outputs
     double *dw, *dx, *dz;  // n
     double* dy;            // m
+    int* div0;             // device flag: scale-U / scale-Z divided by zero (filter-Z, see kkt_pre_kernel)
 };
 
 // Returns 0, NES_NOT_POSDEF, or a negative error.  `step_partial` (may be null) enables the fused
@@ -133,9 +139,10 @@ static int kkt_newton_dev(nes_ctx* c, nes_matrix* A, nes_factor* L, int filters,
     const int grid = vec_grid(c, n);
     {
         StageTimer t(c, NES_STAGE_VECTOR);
+        NES_CUDA(c, cudaMemsetAsync(kv.div0, 0, sizeof(int), c->stream));
         kkt_pre_kernel<<<grid, RED_THREADS, 0, c->stream>>>(n, filters, kv.l, kv.u, kv.w, kv.z, kv.e,
                                                             kv.f, kv.h, kv.wp, kv.ep, kv.lp, kv.fp, kv.d,
-                                                            kv.h3, kv.s, kv.v);
+                                                            kv.h3, kv.s, kv.v, kv.div0);
         NES_CHECK_LAUNCH(c);
     }
     // solve-delta-y: scale the columns of (a copy of) A by s, factorize (A s)(A s)', solve
@@ -143,6 +150,16 @@ static int kkt_newton_dev(nes_ctx* c, nes_matrix* A, nes_factor* L, int filters,
     // g2 = g - A f' + A (l' h3) = g + A v      (newton-solve.lisp:61-62, 96-98)
     NES_TRY(matvec_unscaled(c, A->base, 0, 1.0, kv.v, 1.0, kv.g));
     const int rc = factorize_dev(c, A, L);
+    if (rc == NES_NOT_POSDEF) {
+        // a zero divisor made theta NaN, so the first pivot failed: report the cause, not " singular "
+        int flag = 0;
+        NES_TRY(download(c, &flag, kv.div0, sizeof(int)));
+        if (flag) {
+            fail(c, NES_DIV_BY_ZERO, "solve-kkt-newton: division by zero in scale-U/scale-Z (filter-Z sets z = 0 "
+                                     "for x - lo > 1e7, sparse-newton-solve.lisp:40-45, then scale-Z divides by it)");
+            return NES_DIV_BY_ZERO;
+        }
+    }
     if (rc != 0) return rc;
     NES_CUDA(c, cudaMemcpyAsync(kv.dy, kv.g, m * sizeof(double), cudaMemcpyDeviceToDevice, c->stream));
     NES_TRY(solve_dev(c, L, kv.dy));
@@ -391,7 +408,7 @@ int nes_kkt_newton(nes_matrix* A, nes_factor* L, int filters, const double* l, c
     if (!A || !l || !u || !w || !z || !e || !f || !g || !h || !dw || !dx || !dy || !dz)
         return fail(c, NES_ERR_INVALID, "nes_kkt_newton: null argument");
     const size_t n = A->base->n, m = A->base->m, pn = pad2(n), pm = pad2(m);
-    double* ws = ensure_ws(c, WS_DRIVER, (21 * pn + 2 * pm) * sizeof(double));
+    double* ws = ensure_ws(c, WS_DRIVER, (21 * pn + 2 * pm + 16) * sizeof(double));
     if (!ws) return c->status;
     double* p = ws;
     auto take = [&](size_t len) {
@@ -407,6 +424,7 @@ int nes_kkt_newton(nes_matrix* A, nes_factor* L, int filters, const double* l, c
     kv.h3 = take(pn); kv.s = take(pn); kv.v = take(pn); kv.r = take(pn);
     kv.dw = take(pn); kv.dx = take(pn); kv.dz = take(pn);
     kv.g = take(pm); kv.dy = take(pm);
+    kv.div0 = reinterpret_cast<int*>(take(16));
     const double* hv[7] = {l, u, w, z, e, f, h};
     double* dv[7] = {dl, du, dwv, dzv, de, df, dh};
     for (int k = 0; k < 7; ++k)
@@ -549,6 +567,8 @@ int nes_pdas_newton_direction(nes_pdas* st, double* step, nes_ctx* c) {
     kv.wp = st->wp; kv.ep = st->ep; kv.lp = st->lp; kv.fp = st->fp; kv.d = st->d; kv.h3 = st->h3;
     kv.s = st->s; kv.v = st->v; kv.r = st->r;
     kv.dw = st->dw; kv.dx = st->dx; kv.dz = st->dz; kv.dy = st->dy;
+    kv.div0 = reinterpret_cast<int*>(st->scal + 15);
+    // g2 overwrites st->rp: selector 'p' (Ax - b) is valid between nes_pdas_violation and this call only
     int blocks = 0;
     const int rc = kkt_newton_dev(c, st->A, st->L, st->filters, kv, st->partial, &blocks);
     if (rc != 0) return rc;
@@ -568,6 +588,7 @@ int nes_pdas_apply_step(nes_pdas* st, double alpha, nes_ctx* c) {
     apply_step_kernel<<<vec_grid(c, st->n > st->m ? st->n : st->m), RED_THREADS, 0, c->stream>>>(
         st->n, st->m, alpha, st->dw, st->dx, st->dz, st->dy, st->w, st->x, st->z, st->y);
     NES_CHECK_LAUNCH(c);
+    st->have_direction = 0;  // a direction is applied once (like nes_affine_apply)
     return 0;
 }
 
@@ -644,6 +665,9 @@ int nes_pdas_one_iteration(nes_pdas* st, int repair, double out[9], nes_ctx* c) 
     if (!(v[6] > 0.0) || !(v[7] > 0.0))
         return fail(c, NES_ERR_INVALID, "pdas: iterate left the box (min l = %g, min u = %g)", v[6], v[7]);
     const double pobj = v[0], dobj = v[1];
+    // fmax/fmin reductions drop NaN, the sums do not: a NaN anywhere in x, y, z, w shows in pobj / dobj
+    if (!std::isfinite(pobj) || !std::isfinite(dobj) || !std::isfinite(v[2]) || !std::isfinite(v[3]))
+        return fail(c, NES_ERR_INVALID, "pdas: non-finite iterate (pobj = %g, dobj = %g)", pobj, dobj);
     const double gap = fabs(pobj - dobj) / fmax(fmax(fabs(pobj), fabs(dobj)), 1.0);  // :345-346
     out[0] = gap;
     out[1] = dobj;
@@ -691,10 +715,12 @@ int nes_pdas_solve(nes_pdas* st, int max_iter, int* iters, double* obj, double* 
             return 0;
         }
     }
+    // max_iter exhausted: the Lisp loop falls through and returns NIL (:388-396)
     if (iters) *iters = i - 1;
     if (obj) *obj = out[1];
     if (gap) *gap = out[0];
-    return 0;
+    c->status = NES_MAXITER;
+    return NES_MAXITER;
 }
 
 static double* pdas_vec(nes_pdas* st, int which, size_t* len) {
@@ -729,6 +755,7 @@ int nes_pdas_set(nes_pdas* st, int which, const double* in, nes_ctx* c) {
     size_t len = 0;
     double* p = st ? pdas_vec(st, which, &len) : nullptr;
     if (!p || !in) return fail(c, NES_ERR_INVALID, "nes_pdas_set: bad selector");
+    st->have_direction = 0;  // a direction computed for the previous iterate must not be applied to this one
     return upload(c, p, in, len * sizeof(double));
 }
 
@@ -1070,6 +1097,7 @@ int nes_affine_solve(nes_affine* st, int max_iter, int* iters, double* obj, doub
     if (!st) return fail(c, NES_ERR_INVALID, "nes_affine_solve: null state");
     double out[4], r2[2] = {0, 0};
     int i = 0;
+    bool stopped = false;
     for (; max_iter <= 0 || i < max_iter; ++i) {
         const int rc = nes_affine_one_iteration(st, ((i + 1) % 16) == 0, out, c);  // (:283)
         if (rc != 0) {
@@ -1079,12 +1107,17 @@ int nes_affine_solve(nes_affine* st, int max_iter, int* iters, double* obj, doub
         NES_TRY(nes_affine_residual(st, r2, c));
         if (!(out[3] != 0.0 || r2[0] > 1e-6 * (double)st->m)) {  // (:284-287)
             ++i;
+            stopped = true;
             break;
         }
     }
     if (iters) *iters = i;
     if (obj) *obj = r2[1];
     if (resnorm) *resnorm = r2[0];
+    if (!stopped) {  // max_iter is an addition (the Lisp loop has none): say that the stop rule never fired
+        c->status = NES_MAXITER;
+        return NES_MAXITER;
+    }
     return 0;
 }
 

@@ -1,5 +1,8 @@
 // analyze / factorize / solve / sdmult entry points: the CHOLMOD-shaped part of the boundary
 // (sparse-cholesky.lisp:261-288, 335-342 declarations; call sites :409-431, :506-560, :567-614).
+#include <cmath>
+#include <vector>
+
 #include "dmma_nt.cuh"
 #include "nes_internal.h"
 
@@ -18,6 +21,41 @@ int factorize_dev(nes_ctx* c, nes_matrix* A, nes_factor* L) {
     L->factorized = 0;
     NES_TRY(dense_form_normal(c, A, L, true));
     return dense_cholesky(c, L, A);
+}
+
+// ---- device-side check of the north-star gate ||L L' - M||_F / ||M||_F on the WHOLE matrix -------------
+// Lc = tril(L) with explicit zeros above the diagonal (the factor's buffer keeps stale values there)
+__global__ void tril_copy_kernel(const double* __restrict__ L, double* __restrict__ out, long long ld, int m) {
+    const long long total = ld * (long long)m;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / ld), i = (int)(idx - (long long)j * ld);
+        out[idx] = (i >= j && i < m) ? L[idx] : 0.0;
+    }
+}
+
+// sum of squares over the lower triangle, off-diagonal entries counted twice (= the full symmetric
+// matrix's Frobenius norm squared); per-block partials, combined in fixed order by the caller's finish
+__global__ void frob_lower_kernel(const double* __restrict__ T, long long ld, int m, double* __restrict__ partial) {
+    __shared__ double buf[32];
+    double acc = 0.0;
+    const long long total = ld * (long long)m;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(idx / ld), i = (int)(idx - (long long)j * ld);
+        if (i >= j && i < m) {
+            const double v = T[idx];
+            acc = fma(i == j ? 1.0 : 2.0, v * v, acc);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, off);
+    if ((threadIdx.x & 31) == 0) buf[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) v += buf[w];
+        partial[blockIdx.x] = v;
+    }
 }
 
 int solve_dev(nes_ctx* c, nes_factor* L, double* d_x) {
@@ -178,6 +216,70 @@ int nes_factor_to_dense(nes_factor* L, double* Lout, size_t ld, int* perm, nes_c
         for (size_t i = 0; i < j; ++i) Lout[i + j * ld] = 0.0;
     if (perm)
         for (size_t i = 0; i < m; ++i) perm[i] = (int)i;
+    return 0;
+}
+
+int nes_factor_residual(nes_matrix* A, nes_factor* L, double out[3], nes_ctx* c) {
+    NES_ENTER(c);
+    if (!A || !L || !out) return fail(c, NES_ERR_INVALID, "nes_factor_residual: null argument");
+    if (!A->base->dense || !L->dense || A->base->m != L->m)
+        return fail(c, NES_ERR_INVALID, "nes_factor_residual: dense matrix and its dense factor only");
+    if (!L->factorized) return fail(c, NES_ERR_INVALID, "nes_factor_residual: factor is not factorized");
+    const size_t m = L->m;
+    const long long ld = (long long)L->ld;
+    // T: a second factor object holds the freshly formed M (whole lower triangle on every rank: the check
+    // runs replicated, every rank holds the complete factor after a distributed factorization)
+    const int nranks = c->nranks;
+    c->nranks = 1;
+    nes_factor* T = nes_analyze(A, c);
+    int rc = T ? dense_form_normal(c, A, T) : c->status;
+    c->nranks = nranks;
+    double* Lc = T ? static_cast<double*>(dev_alloc(c, (size_t)ld * m * sizeof(double))) : nullptr;
+    const int G = c->num_sms * 4;
+    double* part = T ? static_cast<double*>(dev_alloc(c, (size_t)G * sizeof(double))) : nullptr;
+    std::vector<double> h(G);
+    auto frob = [&](double* res) -> int {
+        frob_lower_kernel<<<G, 256, 0, c->stream>>>(T->d_M, ld, (int)m, part);
+        NES_CHECK_LAUNCH(c);
+        NES_TRY(download(c, h.data(), part, (size_t)G * sizeof(double)));
+        double v = 0.0;
+        for (int i = 0; i < G; ++i) v += h[i];
+        *res = sqrt(v);
+        return 0;
+    };
+    double normM = 0.0, normR = 0.0;
+    if (rc == 0 && (!Lc || !part)) rc = c->status;
+    if (rc == 0) rc = frob(&normM);
+    if (rc == 0) {
+        tril_copy_kernel<<<G, 256, 0, c->stream>>>(L->d_M, Lc, ld, (int)m);
+        ++c->launches;
+        CUtensorMap mapL;
+        if (make_operand_map(&mapL, Lc, (long long)m, (long long)m, ld) != 0)
+            rc = fail(c, NES_ERR_CUDA, "cuTensorMapEncodeTiled failed for the copy of L");
+        if (rc == 0) {  // T(lower tiles) -= Lc Lc'  on the FP64 tensor cores (K = m)
+            NtArgs a{};
+            a.C = T->d_M;
+            a.ldc = ld;
+            a.M = a.N = (int)m;
+            a.K = (int)m;
+            a.alpha = -1.0;
+            a.beta = 1.0;
+            a.lower = 1;
+            a.same_operand = 1;
+            cudaError_t e = nt_launch(mapL, mapL, a, c->num_sms, c->stream);
+            ++c->launches;
+            if (e != cudaSuccess) rc = fail(c, NES_ERR_CUDA, "residual product failed: %s", cudaGetErrorString(e));
+        }
+    }
+    if (rc == 0) rc = frob(&normR);
+    if (c->started) cudaStreamSynchronize(c->stream);
+    dev_free(c, Lc);
+    dev_free(c, part);
+    nes_free_factor(&T, c);
+    if (rc != 0) return rc;
+    out[0] = normM > 0.0 ? normR / normM : normR;
+    out[1] = normM;
+    out[2] = normR;
     return 0;
 }
 

@@ -6,8 +6,35 @@
 #pragma once
 #include <cstdint>
 #include <cuda.h>
+#include <cuda_runtime.h>
+#include <mutex>
 
 namespace nes {
+
+// cudaFuncSetAttribute is per DEVICE: one process may open contexts on several GPUs (nes_set_device +
+// nes_start), so "configured" bits are kept per device ordinal and guarded against concurrent host threads.
+struct PerDeviceOnce {
+    std::mutex mu;
+    bool done[64] = {};
+    // returns true when the caller must run the configuration for the current device (mutex held until
+    // finish() is called)
+    bool begin(int* dev_out) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        dev &= 63;
+        mu.lock();
+        if (done[dev]) {
+            mu.unlock();
+            return false;
+        }
+        *dev_out = dev;
+        return true;
+    }
+    void finish(int dev, bool ok) {
+        if (ok) done[dev] = true;
+        mu.unlock();
+    }
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

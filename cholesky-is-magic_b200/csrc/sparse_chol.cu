@@ -869,18 +869,23 @@ __global__ void gather_perm_kernel(int m, const int* __restrict__ perm, const do
 // host: analysis (upload of the symbolic structure, tensor maps, launch schedule)
 // ------------------------------------------------------------------------------------------------
 static int sparse_configure(nes_ctx* c) {
-    static bool done = false;
-    if (done) return 0;
-    NES_CUDA(c, cudaFuncSetAttribute(mf_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mf_diag_smem(CH_NB)));
-    NES_CUDA(c, cudaFuncSetAttribute(mf_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mf_tr_smem(CH_NB)));
-    NES_CUDA(c, cudaFuncSetAttribute(mf_syrk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SyrkCfg<128>::SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(mf_syrk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     SyrkCfg<64>::SMEM));
-    NES_CUDA(c, cudaFuncSetAttribute(mf_syrk_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     cudaSharedmemCarveoutMaxShared));
-    NES_CUDA(c, cudaFuncSetAttribute(mf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_TI_SMEM));
-    done = true;
+    static PerDeviceOnce once;
+    int dev;
+    if (!once.begin(&dev)) return 0;
+    cudaError_t e = cudaFuncSetAttribute(mf_potrf_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mf_diag_smem(CH_NB));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(mf_trsm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, mf_tr_smem(CH_NB));
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(mf_syrk_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SyrkCfg<128>::SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(mf_syrk_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, SyrkCfg<64>::SMEM);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(mf_syrk_kernel<64>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+    if (e == cudaSuccess)
+        e = cudaFuncSetAttribute(mf_trtri_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MF_TI_SMEM);
+    once.finish(dev, e == cudaSuccess);
+    NES_CUDA(c, e);
     return 0;
 }
 

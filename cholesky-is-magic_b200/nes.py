@@ -18,6 +18,8 @@ LIB_PATH = os.path.join(_HERE, "libnes.so")
 
 NES_OK = 0
 NES_NOT_POSDEF = 1
+NES_DIV_BY_ZERO = 2
+NES_MAXITER = 3
 NES_ERR_NO_DEVICE = -1
 NES_ERR_OUT_OF_MEMORY = -2
 NES_ERR_INVALID = -4
@@ -84,6 +86,7 @@ def _prototypes(lib):
     fn("nes_solve_dense", C.c_int, _dp, C.c_size_t, C.c_size_t, _dp, _dp, _vp)
     fn("nes_factor_to_dense", C.c_int, _vp, _dp, C.c_size_t, _ip, _vp)
     fn("nes_normal_matrix_to_dense", C.c_int, _vp, _dp, C.c_size_t, _vp)
+    fn("nes_factor_residual", C.c_int, _vp, _vp, _dp, _vp)
     fn("nes_kkt_newton", C.c_int, _vp, _vp, C.c_int, *([_dp] * 12), _vp)
     fn("nes_pdas_create", _vp, _vp, *([_dp] * 8), C.c_int, _vp)
     fn("nes_pdas_free", C.c_int, _vpp, _vp)
@@ -440,6 +443,13 @@ class Factor:
         rc = self.common.lib.nes_solve(0, self.ptr, bp, x.ctypes.data_as(_dp), self.common.ptr)
         self.common.check(rc, "nes_solve")
         return x
+
+    def residual(self, matrix):
+        """||L L' - M||_F / ||M||_F over the whole matrix, computed on the device (nes_factor_residual)."""
+        out = (C.c_double * 3)()
+        self.common.check(self.common.lib.nes_factor_residual(matrix.ptr, self.ptr, out, self.common.ptr),
+                          "nes_factor_residual")
+        return out[0]
 
     def to_dense(self):
         out = np.zeros((self.m, self.m), order="F")

@@ -30,6 +30,8 @@ def solve_kkt_newton(l, u, w, z, A, e, f, g, h, filters=None, factor=None):
                               dw.ctypes.data_as(nes._dp), dx.ctypes.data_as(nes._dp),
                               dy.ctypes.data_as(nes._dp), dz.ctypes.data_as(nes._dp), c.ptr)
     c.check(rc, "nes_kkt_newton")
+    if rc == nes.NES_DIV_BY_ZERO:   # the reference traps in scale-Z (SBCL DIVISION-BY-ZERO) after filter-Z
+        raise ZeroDivisionError(c.error())
     if rc != 0:
         raise nes.NesError(f"solve-delta-y: Cholesky failed (status {rc}, minor {c.minor})")
     return dw, dx, dy, dz

@@ -189,6 +189,8 @@ def direction(state: PdasState):
     step = C.c_double(0.0)
     rc = c.check(c.lib.nes_pdas_newton_direction(state.handle(), C.byref(step), c.ptr),
                  "nes_pdas_newton_direction")
+    if rc == nes.NES_DIV_BY_ZERO:   # the reference traps in scale-Z (SBCL DIVISION-BY-ZERO) after filter-Z
+        raise ZeroDivisionError(c.error())
     if rc != 0:
         raise nes.NesError(f"solve-delta-y: Cholesky failed (status {rc}, minor {c.minor})")
     return step.value
@@ -256,17 +258,24 @@ def pdas(state: PdasState, max_iter=None, native_loop=False):
             iters, obj, gap = C.c_int(0), C.c_double(0), C.c_double(0)
             rc = c.check(c.lib.nes_pdas_solve(state.handle(), max_iter or 0, C.byref(iters),
                                               C.byref(obj), C.byref(gap), c.ptr), "nes_pdas_solve")
-            if rc != 0:
+            # NES_MAXITER: the loop ran out of iterations (the Lisp returns NIL there); the last iterate is
+            # returned with state.converged = False so a caller cannot mistake it for a solution
+            state.converged = rc == 0
+            if rc == nes.NES_DIV_BY_ZERO:
+                raise nes.NesError(f"pdas: {c.error()} (iteration {iters.value})")
+            if rc not in (0, nes.NES_MAXITER):
                 raise nes.NesError(f"pdas: Cholesky failed at iteration {iters.value}")
             state.final = {k: state.get(k) for k in "xywz"}
             return obj.value, gap.value, iters.value
         repair = False
         i = 0
+        state.converged = False
         while max_iter is None or i < max_iter:
             i += 1
             viol, obj, step = one_pdas_iteration(state, repair)
             repair = step is not None and step < 1e-6       # :393
             if viol < 1e-4:                                  # :394
+                state.converged = True
                 break
         state.final = {k: state.get(k) for k in "xywz"}
         return obj, viol, i

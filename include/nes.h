@@ -26,6 +26,11 @@ extern "C" {
 /* status codes: same sign convention as cholmod_common.status (0 ok, >0 warning, <0 error) */
 #define NES_OK 0
 #define NES_NOT_POSDEF 1        /* CHOLMOD_NOT_POSDEF: non-positive pivot, see nes_get_minor() */
+#define NES_DIV_BY_ZERO 2       /* solve-kkt-newton divided by a zero u or z: filter-Z (sparse-newton-solve.lisp:40-45)
+                                   zeroes z for x - lo > 1e7 and scale-Z then divides by it -- SBCL traps there,
+                                   here the step is refused with this status (positive: no result, like 1) */
+#define NES_MAXITER 3           /* nes_pdas_solve / nes_affine_solve ran out of iterations before the stop rule
+                                   fired (the Lisp loops return NIL); iters/obj/gap hold the last iterate */
 #define NES_ERR_NO_DEVICE (-1)  /* no usable sm_100 device / library not started */
 #define NES_ERR_OUT_OF_MEMORY (-2)
 #define NES_ERR_INVALID (-4)    /* CHOLMOD_INVALID: bad argument */
@@ -131,6 +136,11 @@ int nes_solve_dense(const double* B, size_t nrow, size_t ncol, const double* b, 
  * factor; sparse factors are expanded, with the fill-reducing permutation in perm if non-NULL). */
 int nes_factor_to_dense(nes_factor* L, double* Lout, size_t ld, int* perm, nes_ctx* c);
 /* copy the formed normal matrix A diag(s^2) A' back (lower triangle valid). */
+/* Whole-matrix check of the factorization gate on the device (dense only): forms M = A diag(s^2) A' again,
+ * subtracts tril(L) tril(L)' on the FP64 tensor cores and returns out = { ||L L' - M||_F / ||M||_F,
+ * ||M||_F, ||L L' - M||_F } (norms of the full symmetric matrices).  A must still carry the scale it was
+ * factorized with.  Test / bench instrumentation: the reference has no counterpart. */
+int nes_factor_residual(nes_matrix* A, nes_factor* L, double out[3], nes_ctx* c);
 int nes_normal_matrix_to_dense(nes_matrix* A, double* Mout, size_t ld, nes_ctx* c);
 
 /* ---- solve-kkt-newton (newton-solve.lisp:139-154 dense, sparse-newton-solve.lisp:150-168 sparse)

@@ -47,6 +47,11 @@ def kkt_case(m, n, seed):
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "config2":
+        # BASELINE config 2 on the host: ~100 oracle iterations of 2.4e12 flops each (a quarter of an hour on
+        # 8 cores); run once, the fixture pins the GPU's iteration count / objective at full size
+        pdas_case(8192, 16384, 0)
+        sys.exit(0)
     pdas_case(20, 50, 0)
     pdas_case(200, 500, 0)
     kkt_case(12, 30, 5)
