@@ -437,7 +437,7 @@ int nes_kkt_newton(nes_matrix* A, nes_factor* L, int filters, const double* l, c
     // carved out of the workspace (no allocation per call).  Analysis per call unless the caller
     // recycles a factor.
     nes_matrix view;
-    view.base = A->base;
+    view.set_base(A->base);
     view.d_scale = take(pn);
     view.d_theta = take(pn);
     nes_matrix* As = &view;

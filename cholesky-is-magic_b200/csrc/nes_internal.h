@@ -160,7 +160,16 @@ struct MatrixBase {
 }  // namespace nes
 
 struct nes_matrix {
+    // Public prefix (include/nes.h): the leading fields of cholmod_sparse (sparse-cholesky.lisp:45-48), so
+    // the Lisp's (slot A 'nrow) / (slot A 'ncol) / (slot A 'nzmax) keep working on a (* nes-matrix).
+    size_t nrow = 0, ncol = 0, nzmax = 0;
     nes::MatrixBase* base = nullptr;
+    void set_base(nes::MatrixBase* b) {
+        base = b;
+        nrow = b->m;
+        ncol = b->n;
+        nzmax = b->dense ? b->m * b->n : b->nnz;
+    }
     double* d_scale = nullptr;  // column scale s (n doubles) or nullptr (cholmod_scale folded lazily)
     double* d_theta = nullptr;  // s^2 padded to a multiple of 16 (formation operand), or nullptr
 };

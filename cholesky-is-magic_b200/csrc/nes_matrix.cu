@@ -134,7 +134,7 @@ static nes_matrix* new_dense(nes_ctx* c, size_t m, size_t n) {
         return nullptr;
     }
     nes_matrix* A = new nes_matrix();
-    A->base = b;
+    A->set_base(b);
     return A;
 }
 
@@ -263,7 +263,7 @@ nes_matrix* nes_csc_to_matrix(const int* colptr, const int* rowidx, const double
     b->h_colptr = std::move(cp);
     b->h_rowidx = std::move(ri);
     nes_matrix* A = new nes_matrix();
-    A->base = b;
+    A->set_base(b);
     return A;
 }
 
@@ -301,7 +301,7 @@ nes_matrix* nes_copy_matrix(nes_matrix* A, nes_ctx* c) {
         return nullptr;
     }
     nes_matrix* B = new nes_matrix();
-    B->base = A->base;
+    B->set_base(A->base);
     B->base->refs++;
     if (A->d_scale) {
         const size_t n = A->base->n, npad = (n + 15) / 16 * 16;

@@ -82,6 +82,12 @@ NES_DECLARE_ACCESSOR(blas_ok, int)
 int nes_get_minor(const nes_ctx* c);            /* column of the failed pivot (cholmod_factor.minor) */
 
 /* ---- constraint matrix A (device resident, immutable values + optional column scale) --------- */
+/* A nes_matrix is opaque except for its first three words, which mirror the leading fields of
+ * cholmod_sparse (sparse-cholesky.lisp:45-48) so that the Lisp's (slot A 'nrow), (slot A 'ncol) and
+ * (slot A 'nzmax) (affine-scaling.lisp:34,218; primal-dual-affine-scaling.lisp:226) keep working: */
+struct nes_matrix_header {
+    size_t nrow, ncol, nzmax;
+};
 /* make-dense-from-matlisp + cholmod_dense_to_sparse (sparse-cholesky.lisp:346-368, 411-414):
  * A is m x n column-major with leading dimension ld >= m. */
 nes_matrix* nes_dense_to_matrix(const double* A, size_t nrow, size_t ncol, size_t ld, nes_ctx* c);
