@@ -76,9 +76,13 @@ constexpr int TR_THREADS = 256;  // 4 threads per row (trsm_slab_smem)
 // read) and the 64x128 slab of the panel (box lands as Xs[p*64 + row], rows past the matrix edge are
 // zero-filled); the solved slab leaves by one TMA store (clipped at the edge).  Thread-issued staging of
 // these 192 KB cost ~12 us per CTA, more than the substitution itself.
+// Row mapping: slab s covers 64 rows of block s*64 / bh of the set {row_start + b*stride .. + bh}, b = 0, 1, ...
+// (a contiguous panel is one block with bh >= its height; the row pieces of a P x Q distribution are the
+// block rows one rank owns, `stride` = P * nbo rows apart).  Rows >= m_end are not touched.
 __global__ void __launch_bounds__(TR_THREADS)
 trsm_panel_kernel(const __grid_constant__ CUtensorMap mapBlk, const __grid_constant__ CUtensorMap mapSlab,
-                  int j0, int m, const double* __restrict__ dinv_g, int brows) {
+                  int j0, int row_start, int bh, int stride, int m_end, const double* __restrict__ dinv_g,
+                  int brows) {
     extern __shared__ __align__(128) double sm[];
     double* Ls = sm;                       // Ls[c + p*128] = L[c][p]
     double* Xs = Ls + CH_NB * CH_NB;       // Xs[p*64 + row]
@@ -86,8 +90,12 @@ trsm_panel_kernel(const __grid_constant__ CUtensorMap mapBlk, const __grid_const
     uint64_t* bar = reinterpret_cast<uint64_t*>(dv + CH_NB);
     const int tid = threadIdx.x;
     const int brow = blockIdx.y * brows;   // batched mode: this problem's rows
-    const int row0 = j0 + CH_NB + blockIdx.x * TR_ROWS;
-    const int nrows = min(TR_ROWS, m - row0);
+    const int off = blockIdx.x * TR_ROWS;
+    const int blk = (bh > m_end) ? 0 : off / bh;
+    const int row0 = row_start + blk * stride + (off - blk * bh);
+    const int bend = (bh > m_end) ? m_end : min(m_end, row_start + blk * stride + bh);
+    const int nrows = min(TR_ROWS, bend - row0);
+    if (nrows <= 0) return;
     if (tid == 0) {
         mbar_init(bar, 1);
         fence_mbar_init();
@@ -104,7 +112,8 @@ trsm_panel_kernel(const __grid_constant__ CUtensorMap mapBlk, const __grid_const
     if (tid == 0) {
         // rows of the slab past the matrix edge are clipped by the tensor map; in batched mode a slab
         // never crosses into the next problem (row stride is a multiple of 128) and the problem's own
-        // padding rows are stored back unchanged
+        // padding rows are stored back unchanged.  Rows between nrows and 64 inside the matrix (a slab
+        // that ends at m_end < m) were loaded and are stored back unchanged.
         tma_store_2d(&mapSlab, brow + row0, j0, Xs);
         tma_store_commit_and_wait();
     }
@@ -355,7 +364,7 @@ int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, const CUtensorMap& 
     const int rest = m - i0 - ib;
     if (rest > 0) {
         trsm_panel_kernel<<<dim3((rest + TR_ROWS - 1) / TR_ROWS, nbatch), TR_THREADS, TR_SMEM, c->stream>>>(
-            mapBlk, mapSlab, i0, m, dinv, brows);
+            mapBlk, mapSlab, i0, i0 + CH_NB, 1 << 30, 0, m, dinv, brows);
         NES_CHECK_LAUNCH(c);
     }
     return 0;
@@ -430,106 +439,123 @@ __global__ void info_to_minor_kernel(int* info) {
     if (threadIdx.x == 0 && info[0] == 0) info[1] = 0x7fffffff;
 }
 
-// ---- distributed factorization (1 x Q block-cyclic outer panels) with look-ahead ------------------
-// After panel J has arrived everywhere, the owner of panel J+1 first updates only its tiles of block
-// column J+1, factors that panel and starts its broadcast, and only then updates the rest of its
-// columns; the other ranks update all their columns with panel J and then join the broadcast.  The
-// panel factorization (latency-bound, one GPU) therefore overlaps the other ranks' trailing updates
-// instead of sitting between every two of them.  Collectives are issued in the same order on every
-// rank, on the one stream the kernels use.
-static int dist_factor_panel(nes_ctx* c, nes_factor* L, int J) {
-    const int m = (int)L->m, nbo = L->nbo, j0 = J * nbo;
-    const int jbo = (m - j0 < nbo) ? m - j0 : nbo;
-    const long long ld = (long long)L->ld;
-    for (int i0 = j0; i0 < j0 + jbo; i0 += CH_NB) {
-        const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
-        if (i0 > j0) NES_TRY(chol_update(c, L, i0, i0, m - i0, ib, j0, i0 - j0, 0));
-        potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, c->stream>>>(L->mapBlk, i0, ib, L->d_dinv, c->dbound,
-                                                              L->d_info, 0);
-        NES_CHECK_LAUNCH(c);
-        const int rest = m - i0 - ib;
-        if (rest > 0) {
-            trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM, c->stream>>>(
-                L->mapBlk, L->mapSlab, i0, m, L->d_dinv, 0);
-            NES_CHECK_LAUNCH(c);
+// ---- distributed factorization (P x Q block-cyclic, panels pipelined in row chunks) ---------------------
+// nes_dist.cu plans, for every panel (block column J), the fixed sequence of messages it travels in: row
+// chunks (and, for P > 1, the diagonal block first).  Streams on every rank:
+//   stream    (high)  the message that carries the diagonal block, when this rank is its root: update of those
+//                     rows with panel J-1, the inner 128-column panels (narrow DMMA update, potrf_diag,
+//                     trsm_panel), pack
+//   stream_c  (mid)   the other messages this rank is the root of: update, trsm against the finished diagonal
+//                     block, narrow updates, pack -- chunk by chunk
+//   stream_b  (high)  communication: one ncclBroadcast per message in plan order, unpack on the receivers
+//   stream_aux (low)  the trailing update with panel J of this rank's tiles in block columns >= J+2, one tile
+//                     per CTA; the tiles of column J+2 go first and signal ev_colready[J+2]
+// The root of a message of panel J+1 waits only for the message(s) of panel J that carry the same rows and
+// block row J+1 (absolute chunk boundaries make that one message), so the owner of the next panel starts on
+// its first chunk while the later chunks of the current one are still being solved and sent, and the
+// panel chain per step is diagonal block + first chunk + one small broadcast instead of whole panel +
+// whole-panel broadcast.  Every rank issues the same collectives in the same order on stream_b.
+__global__ void pack_rows_kernel(double* __restrict__ M, long long ld, int m, int col0, int ncols, int row_start,
+                                 int nblocks, int bh, int stride, double* __restrict__ buf, int ldp,
+                                 double* __restrict__ dinv, int unpack) {
+    const long long body = (long long)ldp * ncols, total = body + (dinv ? ncols : 0);
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        if (idx >= body) {
+            const int cidx = (int)(idx - body);
+            if (unpack) dinv[col0 + cidx] = buf[idx];
+            else buf[idx] = dinv[col0 + cidx];
+            continue;
         }
+        const int cidx = (int)(idx / ldp), r = (int)(idx - (long long)cidx * ldp);
+        const int blk = r / bh;
+        const int row = row_start + blk * stride + (r - blk * bh);
+        if (blk >= nblocks || row >= m) continue;
+        double* src = M + row + (long long)(col0 + cidx) * ld;
+        if (unpack) *src = buf[idx];
+        else buf[idx] = *src;
     }
-    const size_t rows = (size_t)(m - j0);
-    NES_CUDA(c, cudaMemcpy2DAsync(L->d_stage, rows * 8, L->d_M + j0 + (long long)j0 * ld, ld * 8, rows * 8, jbo,
-                                  cudaMemcpyDeviceToDevice, c->stream));
-    NES_CUDA(c, cudaMemcpyAsync(L->d_stage + rows * jbo, L->d_dinv + j0, jbo * sizeof(double),
-                                cudaMemcpyDeviceToDevice, c->stream));
+}
+
+static int dist_setup(nes_ctx* c, nes_factor* L) {
+    DistPlan& pl = *L->dist;
+    if (pl.ev_start) return 0;
+    auto mk = [&](cudaEvent_t* e) { return cudaEventCreateWithFlags(e, cudaEventDisableTiming) == cudaSuccess; };
+    bool ok = mk(&pl.ev_start) && mk(&pl.ev_end[0]) && mk(&pl.ev_end[1]) && mk(&pl.ev_end[2]);
+    const int nmsg = pl.msg_base[pl.nblk];
+    pl.ev_arrived.assign(nmsg, nullptr);
+    pl.ev_packed.assign(nmsg, nullptr);
+    pl.ev_colready.assign(pl.nblk, nullptr);
+    pl.ev_diagdone.assign(pl.nblk, nullptr);
+    for (int i = 0; i < nmsg && ok; ++i) ok = mk(&pl.ev_arrived[i]) && mk(&pl.ev_packed[i]);
+    for (int i = 0; i < pl.nblk && ok; ++i) ok = mk(&pl.ev_colready[i]) && mk(&pl.ev_diagdone[i]);
+    if (!ok) return fail(c, NES_ERR_CUDA, "cudaEventCreate failed for the distributed factorization");
+    for (int i = 0; i < DistPlan::kStages; ++i) {
+        pl.d_stage[i] = static_cast<double*>(dev_alloc(c, (pl.max_msg_doubles + 16) * sizeof(double)));
+        if (!pl.d_stage[i]) return c->status;
+    }
     return 0;
 }
 
-static int dist_exchange_panel(nes_ctx* c, nes_factor* L, int J) {
-    const int m = (int)L->m, nbo = L->nbo, j0 = J * nbo;
-    const int jbo = (m - j0 < nbo) ? m - j0 : nbo;
-    const long long ld = (long long)L->ld;
-    const size_t rows = (size_t)(m - j0);
-    const int owner = dist_owner(J, c->nranks);
-    NES_TRY(dist_broadcast(c, L->d_stage, rows * jbo + jbo, owner));
-    if (c->rank != owner) {
-        NES_CUDA(c, cudaMemcpy2DAsync(L->d_M + j0 + (long long)j0 * ld, ld * 8, L->d_stage, rows * 8, rows * 8,
-                                      jbo, cudaMemcpyDeviceToDevice, c->stream));
-        NES_CUDA(c, cudaMemcpyAsync(L->d_dinv + j0, L->d_stage + rows * jbo, jbo * sizeof(double),
-                                    cudaMemcpyDeviceToDevice, c->stream));
-    }
-    return 0;
-}
-
-// owned tiles [tile_begin, tile_end) -= panel J panel J'
-static int dist_update(nes_ctx* c, nes_factor* L, int J, int tile_begin, int tile_end,
-                       cudaStream_t stream = nullptr, bool one_tile_per_cta = false) {
-    if (tile_begin >= tile_end) return 0;
-    const int m = (int)L->m, nbo = L->nbo, j0 = J * nbo;
+// this rank's tiles [tile_begin, tile_end) -= panel(k0, K) panel(k0, K)'
+static int dist_update(nes_ctx* c, nes_factor* L, int k0, int K, int tile_begin, int tile_end, cudaStream_t stream,
+                       bool one_tile_per_cta) {
+    if (tile_begin >= tile_end || K <= 0) return 0;
     NtArgs a{};
     a.C = L->d_M;
     a.ldc = (long long)L->ld;
-    a.M = a.N = m;
+    a.M = a.N = (int)L->m;
     a.rowA0 = a.rowB0 = 0;
-    a.k0 = j0;
-    a.K = (m - j0 < nbo) ? m - j0 : nbo;
+    a.k0 = k0;
+    a.K = K;
     a.alpha = -1.0;
     a.beta = 1.0;
     a.same_operand = 1;
     a.tile_list = L->d_tile_list + tile_begin;
     a.ntiles = tile_end - tile_begin;
-    cudaError_t e = nt_launch(L->mapM, L->mapM, a, one_tile_per_cta ? (1 << 30) : c->num_sms,
-                              stream ? stream : c->stream);
+    cudaError_t e = nt_launch(L->mapM, L->mapM, a, one_tile_per_cta ? (1 << 30) : c->num_sms, stream);
     ++c->launches;
     if (e != cudaSuccess)
         return fail(c, NES_ERR_CUDA, "distributed update launch failed: %s", cudaGetErrorString(e));
     return 0;
 }
 
-// Every rank: the main (high-priority) stream carries the panel chain -- update of the next block
-// column (owner only), its factorization (owner only), the broadcast and the unpack -- while the
-// low-priority side stream applies the previous panel to the rest of this rank's tiles, one tile per
-// CTA so the chain (and NCCL's kernels) get SMs at tile granularity.  Same two events as the
-// single-GPU look-ahead.
-static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L) {
-    const int m = (int)L->m, nbo = L->nbo, P = c->nranks;
-    const int nblk = (m + nbo - 1) / nbo;
-    const int* tf = L->tile_first.data();
-    if (c->rank == dist_owner(0, P)) NES_TRY(dist_factor_panel(c, L, 0));
-    NES_TRY(dist_exchange_panel(c, L, 0));
-    bool pending_update = false;
-    for (int J = 0; J + 1 < nblk; ++J) {
-        const int next = J + 1;
-        NES_CUDA(c, cudaEventRecord(c->ev_panel, c->stream));                       // panel J is here
-        if (pending_update) NES_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_update, 0));
-        NES_TRY(dist_update(c, L, J, tf[next], tf[next + 1]));                      // block column `next` (owner)
-        if (tf[next + 1] < L->ntiles_owned) {                                       // the rest, side stream
-            NES_CUDA(c, cudaStreamWaitEvent(c->stream_aux, c->ev_panel, 0));
-            NES_TRY(dist_update(c, L, J, tf[next + 1], L->ntiles_owned, c->stream_aux, true));
-            NES_CUDA(c, cudaEventRecord(c->ev_update, c->stream_aux));
-            pending_update = true;
+// the inner 128-column panels of panel `pn` on the rows of message `d` (root only)
+static int dist_factor_rows(nes_ctx* c, nes_factor* L, const DistPanel& pn, const DistMsg& d, cudaStream_t stream) {
+    const int m = (int)L->m;
+    for (int t = 0; t * CH_NB < pn.jbo; ++t) {
+        const int i0 = pn.j0 + t * CH_NB;
+        const int ib = (m - i0 < CH_NB) ? m - i0 : CH_NB;
+        if (t > 0) NES_TRY(dist_update(c, L, pn.j0, t * CH_NB, d.seg[t], d.seg[t + 1], stream, true));
+        if (d.has_diag) {
+            potrf_diag_kernel<<<1, 256, CH_DIAG_SMEM, stream>>>(L->mapBlk, i0, ib, L->d_dinv, c->dbound, L->d_info, 0);
+            NES_CHECK_LAUNCH(c);
+            const int end = std::min(m, d.row_start + d.bh);   // contiguous rows below the diagonal block
+            const int rest = end - i0 - ib;
+            if (rest > 0) {
+                trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM, stream>>>(
+                    L->mapBlk, L->mapSlab, i0, i0 + CH_NB, 1 << 30, 0, end, L->d_dinv, 0);
+                NES_CHECK_LAUNCH(c);
+            }
+        } else {
+            const int slabs = d.nblocks * (d.bh / TR_ROWS);
+            trsm_panel_kernel<<<slabs, TR_THREADS, TR_SMEM, stream>>>(L->mapBlk, L->mapSlab, i0, d.row_start, d.bh,
+                                                                     d.stride, m, L->d_dinv, 0);
+            NES_CHECK_LAUNCH(c);
         }
-        if (c->rank == dist_owner(next, P)) NES_TRY(dist_factor_panel(c, L, next));
-        NES_TRY(dist_exchange_panel(c, L, next));
     }
-    if (pending_update) NES_CUDA(c, cudaStreamWaitEvent(c->stream, c->ev_update, 0));
+    return 0;
+}
+
+static int dist_pack(nes_ctx* c, nes_factor* L, const DistPanel& pn, const DistMsg& d, double* buf, int unpack,
+                     cudaStream_t stream) {
+    const long long total = (long long)d.rows * pn.jbo + pn.jbo;
+    int grid = (int)std::min<long long>((total + 255) / 256, (long long)c->num_sms * 8);
+    if (grid < 1) grid = 1;
+    pack_rows_kernel<<<grid, 256, 0, stream>>>(L->d_M, (long long)L->ld, (int)L->m, pn.j0, pn.jbo, d.row_start,
+                                               d.nblocks, d.bh, d.stride, buf, d.rows,
+                                               d.has_diag ? L->d_dinv : nullptr, unpack);
+    NES_CHECK_LAUNCH(c);
     return 0;
 }
 
@@ -542,6 +568,7 @@ struct CholTrace {
         cudaEvent_t a, b;
     };
     bool on = false;
+    int rank = 0;
     cudaEvent_t base = nullptr;
     std::vector<Span> spans;
     void begin(cudaStream_t s) {
@@ -569,8 +596,8 @@ struct CholTrace {
             float t0 = 0.f, t1 = 0.f;
             cudaEventElapsedTime(&t0, base, sp.a);
             cudaEventElapsedTime(&t1, base, sp.b);
-            fprintf(stderr, "chol-trace %-6s col %5d  %9.3f -> %9.3f  (%7.3f ms)\n", sp.what, sp.col, t0, t1,
-                    t1 - t0);
+            fprintf(stderr, "chol-trace r%d %-6s col %5d  %9.3f -> %9.3f  (%7.3f ms)\n", rank, sp.what, sp.col, t0,
+                    t1, t1 - t0);
             cudaEventDestroy(sp.a);
             cudaEventDestroy(sp.b);
         }
@@ -579,6 +606,74 @@ struct CholTrace {
     }
 };
 
+static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L, CholTrace& tr) {
+    NES_TRY(dist_setup(c, L));
+    DistPlan& pl = *L->dist;
+    const int nblk = pl.nblk, me = c->rank, P = pl.P, tpb = pl.tpb;
+    cudaStream_t S0 = c->stream, S1 = c->stream_aux, S2 = c->stream_b, S3 = c->stream_c;
+    NES_CUDA(c, cudaEventRecord(pl.ev_start, S0));
+    NES_CUDA(c, cudaStreamWaitEvent(S1, pl.ev_start, 0));
+    NES_CUDA(c, cudaStreamWaitEvent(S2, pl.ev_start, 0));
+    NES_CUDA(c, cudaStreamWaitEvent(S3, pl.ev_start, 0));
+    for (int J = 0; J < nblk; ++J) {
+        const DistPanel& pn = pl.panels[J];
+        for (size_t k = 0; k < pn.msgs.size(); ++k) {
+            const DistMsg& d = pn.msgs[k];
+            const int gi = pl.msg_base[J] + (int)k;
+            double* stage = pl.d_stage[gi % DistPlan::kStages];
+            const size_t count = (size_t)d.rows * pn.jbo + (d.has_diag ? pn.jbo : 0);
+            if (d.root == me) {
+                cudaStream_t st = d.has_diag ? S0 : S3;
+                int t = -1;
+                if (J > 0) {
+                    const DistPanel& pv = pl.panels[J - 1];
+                    if (d.dep >= 0) NES_CUDA(c, cudaStreamWaitEvent(st, pl.ev_arrived[pl.msg_base[J - 1] + d.dep], 0));
+                    if (J >= 2) NES_CUDA(c, cudaStreamWaitEvent(st, pl.ev_colready[J], 0));
+                    t = tr.open(d.has_diag ? "upd0" : "upd", pn.j0, st);
+                    NES_TRY(dist_update(c, L, pv.j0, pv.jbo, d.seg[0], d.seg[tpb], st, true));
+                    tr.close(t, st);
+                }
+                if (!d.has_diag)
+                    NES_CUDA(c, cudaStreamWaitEvent(st, P > 1 ? pl.ev_arrived[pl.msg_base[J] + pn.diag_msg]
+                                                              : pl.ev_diagdone[J], 0));
+                t = tr.open(d.has_diag ? "diag" : "rows", pn.j0, st);
+                NES_TRY(dist_factor_rows(c, L, pn, d, st));
+                tr.close(t, st);
+                if (d.has_diag) NES_CUDA(c, cudaEventRecord(pl.ev_diagdone[J], st));
+                if (gi >= DistPlan::kStages)  // the staging slot's previous broadcast is over
+                    NES_CUDA(c, cudaStreamWaitEvent(st, pl.ev_arrived[gi - DistPlan::kStages], 0));
+                NES_TRY(dist_pack(c, L, pn, d, stage, 0, st));
+                NES_CUDA(c, cudaEventRecord(pl.ev_packed[gi], st));
+                NES_CUDA(c, cudaStreamWaitEvent(S2, pl.ev_packed[gi], 0));
+                t = tr.open("send", pn.j0, S2);
+                NES_TRY(dist_broadcast(c, stage, count, d.root, S2));
+                tr.close(t, S2);
+            } else {
+                int t = tr.open("recv", pn.j0, S2);
+                NES_TRY(dist_broadcast(c, stage, count, d.root, S2));
+                NES_TRY(dist_pack(c, L, pn, d, stage, 1, S2));
+                tr.close(t, S2);
+            }
+            NES_CUDA(c, cudaEventRecord(pl.ev_arrived[gi], S2));
+        }
+        // trailing update with panel J: block columns >= J+2 (column J+1 is updated by the roots of its messages)
+        if (J + 2 < nblk) {
+            NES_CUDA(c, cudaStreamWaitEvent(S1, pl.ev_arrived[pl.msg_base[J + 1] - 1], 0));
+            const DistPanel& p2 = pl.panels[J + 2];
+            int t = tr.open("rest", pn.j0, S1);
+            NES_TRY(dist_update(c, L, pn.j0, pn.jbo, p2.col_begin, p2.col_end, S1, true));
+            NES_CUDA(c, cudaEventRecord(pl.ev_colready[J + 2], S1));
+            NES_TRY(dist_update(c, L, pn.j0, pn.jbo, p2.col_end, L->ntiles_owned, S1, true));
+            tr.close(t, S1);
+        }
+    }
+    NES_CUDA(c, cudaEventRecord(pl.ev_end[0], S1));
+    NES_CUDA(c, cudaEventRecord(pl.ev_end[1], S2));
+    NES_CUDA(c, cudaEventRecord(pl.ev_end[2], S3));
+    for (int i = 0; i < 3; ++i) NES_CUDA(c, cudaStreamWaitEvent(S0, pl.ev_end[i], 0));
+    return 0;
+}
+
 int dense_cholesky(nes_ctx* c, nes_factor* L, const nes_matrix* A) {
     StageTimer timer(c, NES_STAGE_FACTOR);
     NES_TRY(chol_configure(c));
@@ -586,7 +681,13 @@ int dense_cholesky(nes_ctx* c, nes_factor* L, const nes_matrix* A) {
     const long long ld = (long long)L->ld;
     const int P = c->nranks;
     NES_CUDA(c, cudaMemsetAsync(L->d_info, 0, 2 * sizeof(int), c->stream));
-    if (P > 1) NES_TRY(dense_cholesky_dist_steps(c, L));
+    if (P > 1) {
+        CholTrace tr;
+        tr.rank = c->rank;
+        tr.begin(c->stream);
+        NES_TRY(dense_cholesky_dist_steps(c, L, tr));
+        tr.dump(c->stream);
+    }
     if (P == 1) {
         // Look-ahead (single GPU).  After panel J: (1) `stream` brings block column J+1 up to date and
         // factors panel J+1 (latency-bound: one CTA for the diagonal block, a few for the TRSM), while
@@ -610,7 +711,7 @@ int dense_cholesky(nes_ctx* c, nes_factor* L, const nes_matrix* A) {
                 const int rest = m - i0 - ib;
                 if (rest > 0) {
                     trsm_panel_kernel<<<(rest + TR_ROWS - 1) / TR_ROWS, TR_THREADS, TR_SMEM, c->stream>>>(
-                        L->mapBlk, L->mapSlab, i0, m, L->d_dinv, 0);
+                        L->mapBlk, L->mapSlab, i0, i0 + CH_NB, 1 << 30, 0, m, L->d_dinv, 0);
                     NES_CHECK_LAUNCH(c);
                 }
             }

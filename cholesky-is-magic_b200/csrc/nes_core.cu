@@ -219,6 +219,7 @@ int nes_start(nes_ctx* c) {
     if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->stream_aux, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->stream_b, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->stream_c, cudaStreamNonBlocking, (prio_lo + prio_hi) / 2) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) != cudaSuccess ||
         cudaEventCreateWithFlags(&c->ev_panel, cudaEventDisableTiming) != cudaSuccess ||
@@ -280,6 +281,8 @@ int nes_finish(nes_ctx* c) {
     c->ev_fork = c->ev_join = nullptr;
     if (c->stream_b) cudaStreamDestroy(c->stream_b);
     c->stream_b = nullptr;
+    if (c->stream_c) cudaStreamDestroy(c->stream_c);
+    c->stream_c = nullptr;
     if (c->stream_aux) cudaStreamDestroy(c->stream_aux);
     c->stream_aux = nullptr;
     if (c->stream) cudaStreamDestroy(c->stream);

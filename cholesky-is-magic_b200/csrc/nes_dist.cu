@@ -1,16 +1,24 @@
 // Multi-GPU plumbing: one process per GPU, NCCL over NVLink 5 / NVSwitch.
 //
-// Distribution: the normal matrix M and its factor are laid out block-cyclically
-// by outer block columns (width NBO) over a 1 x Q process grid -- the 2D block-cyclic scheme with P = 1.
-// With NVSwitch every GPU receives a broadcast at full link bandwidth, so nothing is gained by also
-// splitting panel rows (P > 1) at 2..8 GPUs, while P = 1 keeps every panel factorization (diagonal block
-// + TRSM) local to its owner: the only exchange step is one ncclBroadcast of the finished panel per
-// outer block column (<= 134 MB at m = 32768, NBO = 512).  A and the IPM vectors are replicated
-// (A is regenerated or uploaded once per rank; all ranks run the O(n) vector kernels redundantly and
-// deterministically, so no scalar ever needs to be exchanged).
+// Distribution: the normal matrix M and its factor are laid out 2D block-cyclically in
+// nbo x nbo blocks over a P x Q process grid (rank = p*Q + q): block (I, J) of the lower triangle belongs to
+// process row I mod P and to the process column that owns block column J (columns are dealt back and forth,
+// 0..Q-1, Q-1..0, which balances the triangle).  Default grid: 1 x nranks -- with NVSwitch every GPU receives
+// a broadcast at full link bandwidth, so splitting the panel rows as well (P > 1) only adds a latency-bound
+// exchange of the diagonal block per panel; NES_DIST_GRID=PxQ selects another grid (measured in DESIGN.md).
+//
+// A panel (block column J) travels as a fixed sequence of MESSAGES, the same on every rank: [P > 1: the
+// diagonal block] and then, for every chunk of `chunk` rows (absolute row ranges, so chunk k of panel J+1
+// needs exactly chunk k of panel J) and every process row, the block rows that rank owns.  Each message is
+// one ncclBroadcast on a dedicated communication stream, issued as soon as its root has solved those rows:
+// the next panel's owner starts on the first chunk while the later ones are still being solved and sent
+// (dense_chol.cu has the schedule).  A and the IPM vectors are replicated (A is regenerated or uploaded
+// once per rank; all ranks run the O(n) vector kernels redundantly and deterministically, so no scalar
+// ever needs to be exchanged).
 //
 // NCCL is resolved at run time (dlopen) so the library still loads on hosts without it; the unique id
 // travels through the caller's launcher (torch.distributed in bench.py / tests).
+#include <algorithm>
 #include <cstdlib>
 #include <dlfcn.h>
 #include <nccl.h>
@@ -72,34 +80,168 @@ int dist_owner(int J, int nranks) {
     return q < nranks ? q : 2 * nranks - 1 - q;
 }
 
-// Owned tiles (128 x 128) of the lower triangle for `rank`: tile column bj belongs to outer block
-// column J = bj*128 / nbo, owned by dist_owner(J).  Ordered by J, then tile row, then tile column, so that
-// (a) the tiles updated after panel J are a suffix of the list (from tile_first[J + 1]) and (b) consecutive tiles share rows.
-int dist_plan_tiles(int m, int nbo, int nranks, int rank, std::vector<int2>& tiles,
-                    std::vector<int>& tile_first) {
-    const int tm = (m + 127) / 128;
-    const int tpb = nbo / 128;  // tile columns per outer block
-    const int nblk = (m + nbo - 1) / nbo;
-    tiles.clear();
-    tile_first.assign(nblk + 1, 0);
-    for (int J = 0; J < nblk; ++J) {
-        tile_first[J] = (int)tiles.size();  // first tile with block column >= J (fixed up below)
-        if (dist_owner(J, nranks) != rank) continue;
-        const int c_lo = J * tpb, c_hi = (c_lo + tpb < tm) ? c_lo + tpb : tm;
-        for (int bi = c_lo; bi < tm; ++bi)
-            for (int bj = c_lo; bj < c_hi && bj <= bi; ++bj) tiles.push_back(make_int2(bi, bj));
+// Rows per chunk of a panel: a multiple of P*nbo (every process row owns whole blocks of every chunk).
+// Small chunks shorten the pipeline stages (the next owner starts sooner), large ones cost fewer launches
+// and broadcasts.  NES_DIST_CHUNK overrides (testing / tuning).
+int dist_chunk_rows(int m, int nbo, int P) {
+    int want = 8192;
+    if (const char* e = getenv("NES_DIST_CHUNK")) {
+        const int v = atoi(e);
+        if (v > 0) want = v;
     }
-    tile_first[nblk] = (int)tiles.size();
-    // tile_first[J] = first owned tile with block column >= J; the update after panel J starts at
-    // tile_first[J + 1]
-    return (int)tiles.size();
+    const int unit = P * nbo;
+    int r = (want + unit - 1) / unit * unit;
+    if (r < unit) r = unit;
+    (void)m;
+    return r;
 }
 
-int dist_broadcast(nes_ctx* c, double* d_buf, size_t count, int root) {
+// Message schedule + this rank's tile list.  Host only (checked without a GPU through nes_dist_plan_grid).
+int dist_make_plan(DistPlan& pl, int m, int nbo, int P, int Q, int rank, int chunk_rows) {
+    pl = DistPlan();
+    pl.m = m; pl.nbo = nbo; pl.P = P; pl.Q = Q; pl.rank = rank; pl.chunk = chunk_rows;
+    pl.tpb = nbo / 128;
+    pl.nblk = (m + nbo - 1) / nbo;
+    const int myp = rank / Q, myq = rank % Q;
+    const int tm = (m + 127) / 128, tpb = pl.tpb, nblk = pl.nblk;
+    pl.panels.resize(nblk);
+    pl.msg_base.assign(nblk + 1, 0);
+    for (int J = 0; J < nblk; ++J) {
+        DistPanel& pn = pl.panels[J];
+        pn.j0 = J * nbo;
+        pn.jbo = (m - pn.j0 < nbo) ? m - pn.j0 : nbo;
+        pn.group_q = dist_owner(J, Q);
+        const int pJ = J % P;
+        if (P > 1) {  // the diagonal block goes first, to everyone (the P ranks of the column need L_JJ)
+            DistMsg d;
+            d.root = pJ * Q + pn.group_q;
+            d.has_diag = 1;
+            d.row_start = pn.j0;
+            d.nblocks = 1;
+            d.bh = nbo;
+            d.stride = 0;
+            d.rows = nbo;
+            pn.msgs.push_back(d);
+        }
+        const int c_first = pn.j0 / chunk_rows, c_last = (m - 1) / chunk_rows;
+        for (int ck = c_first; ck <= c_last; ++ck) {
+            const int r_lo = std::max(pn.j0, ck * chunk_rows), r_hi = std::min(m, (ck + 1) * chunk_rows);
+            if (P == 1) {
+                DistMsg d;
+                d.root = pn.group_q;
+                d.has_diag = (r_lo == pn.j0);
+                d.row_start = r_lo;
+                d.nblocks = 1;
+                d.bh = (r_hi - r_lo + 63) / 64 * 64;
+                d.stride = 0;
+                d.rows = d.bh;
+                pn.msgs.push_back(d);
+                continue;
+            }
+            // block rows I > J inside [r_lo, r_hi), process row by process row, starting below the diagonal
+            const int I_lo = std::max(J + 1, r_lo / nbo), I_hi = (r_hi + nbo - 1) / nbo;  // [I_lo, I_hi)
+            for (int k = 0; k < P; ++k) {
+                const int p = (pJ + 1 + k) % P;
+                int I0 = I_lo + ((p - I_lo % P) % P + P) % P;
+                if (I0 >= I_hi) continue;
+                DistMsg d;
+                d.root = p * Q + pn.group_q;
+                d.row_start = I0 * nbo;
+                d.nblocks = (I_hi - 1 - I0) / P + 1;
+                d.bh = nbo;
+                d.stride = P * nbo;
+                d.rows = d.nblocks * nbo;
+                pn.msgs.push_back(d);
+            }
+        }
+        for (size_t k = 0; k < pn.msgs.size(); ++k)
+            if (pn.msgs[k].has_diag) pn.diag_msg = (int)k;
+        pl.msg_base[J + 1] = pl.msg_base[J] + (int)pn.msgs.size();
+        for (const DistMsg& d : pn.msgs)
+            pl.max_msg_doubles = std::max(pl.max_msg_doubles, (size_t)d.rows * pn.jbo + (size_t)nbo);
+    }
+    // which message of the previous panel must have arrived before the root updates a message's rows:
+    // the ones that carry the same rows (A operand) and block row J (B operand); the communication stream
+    // is in order, so the last of them is enough
+    auto rows_of = [&](const DistMsg& d, int b) {  // [lo, hi) of block b of the message
+        const int lo = d.row_start + b * d.stride;
+        return std::make_pair(lo, std::min(m, lo + d.bh));
+    };
+    auto overlaps = [&](const DistMsg& d, int lo, int hi) {
+        for (int b = 0; b < d.nblocks; ++b) {
+            auto r = rows_of(d, b);
+            if (r.first < hi && lo < r.second) return true;
+        }
+        return false;
+    };
+    for (int J = 1; J < nblk; ++J) {
+        DistPanel& pn = pl.panels[J];
+        const DistPanel& pv = pl.panels[J - 1];
+        for (DistMsg& d : pn.msgs) {
+            int dep = -1;
+            for (size_t k = 0; k < pv.msgs.size(); ++k) {
+                bool need = overlaps(pv.msgs[k], pn.j0, pn.j0 + pn.jbo);
+                for (int b = 0; b < d.nblocks && !need; ++b) {
+                    auto r = rows_of(d, b);
+                    need = overlaps(pv.msgs[k], r.first, r.second);
+                }
+                if (need) dep = (int)k;
+            }
+            d.dep = dep;
+        }
+    }
+    // this rank's tiles: by block column, then message, then tile column, then tile row
+    for (int J = 0; J < nblk; ++J) {
+        DistPanel& pn = pl.panels[J];
+        pn.col_begin = (int)pl.tiles.size();
+        if (pn.group_q == myq) {
+            const int c_lo = J * tpb, c_hi = std::min(tm, c_lo + tpb);
+            for (DistMsg& d : pn.msgs) {
+                if (d.root != rank) continue;
+                d.seg.assign(tpb + 1, (int)pl.tiles.size());
+                for (int t = 0; t < tpb; ++t) {
+                    d.seg[t] = (int)pl.tiles.size();
+                    const int bj = c_lo + t;
+                    if (bj < c_hi)
+                        for (int b = 0; b < d.nblocks; ++b) {
+                            auto r = rows_of(d, b);
+                            for (int bi = r.first / 128; bi * 128 < r.second; ++bi)
+                                if (bi >= bj) pl.tiles.push_back(make_int2(bi, bj));
+                        }
+                    d.seg[t + 1] = (int)pl.tiles.size();
+                }
+            }
+        }
+        pn.col_end = (int)pl.tiles.size();
+    }
+    (void)myp;
+    return (int)pl.tiles.size();
+}
+
+void dist_free_plan(nes_ctx* c, DistPlan* pl) {
+    if (!pl) return;
+    for (auto& v : {&pl->ev_arrived, &pl->ev_packed, &pl->ev_colready, &pl->ev_diagdone}) {
+        for (cudaEvent_t e : *v)
+            if (e) cudaEventDestroy(e);
+        v->clear();
+    }
+    if (pl->ev_start) cudaEventDestroy(pl->ev_start);
+    pl->ev_start = nullptr;
+    for (auto& e : pl->ev_end) {
+        if (e) cudaEventDestroy(e);
+        e = nullptr;
+    }
+    for (auto& p : pl->d_stage) {
+        dev_free(c, p);
+        p = nullptr;
+    }
+}
+
+int dist_broadcast(nes_ctx* c, double* d_buf, size_t count, int root, cudaStream_t stream) {
     NcclApi* api = nccl_api();
     if (!api || !c->nccl_comm) return fail(c, NES_ERR_COMM, "NCCL communicator not initialised");
     ncclResult_t r = api->Broadcast(d_buf, d_buf, count, ncclDouble, root,
-                                    static_cast<ncclComm_t>(c->nccl_comm), c->stream);
+                                    static_cast<ncclComm_t>(c->nccl_comm), stream ? stream : c->stream);
     if (r != ncclSuccess)
         return fail(c, NES_ERR_COMM, "ncclBroadcast failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
     return 0;
@@ -147,6 +289,17 @@ int nes_comm_init(nes_ctx* c, int nranks, int rank, const unsigned char* id128) 
     if (c->nccl_comm) return fail(c, NES_ERR_INVALID, "communicator already initialised");
     c->nranks = nranks;
     c->rank = rank;
+    c->grid_p = 1;
+    c->grid_q = nranks;
+    if (const char* e = getenv("NES_DIST_GRID")) {  // "PxQ", every rank must see the same value
+        int gp = 0, gq = 0;
+        if (sscanf(e, "%dx%d", &gp, &gq) == 2 && gp >= 1 && gq >= 1 && gp * gq == nranks) {
+            c->grid_p = gp;
+            c->grid_q = gq;
+        } else {
+            return fail(c, NES_ERR_INVALID, "NES_DIST_GRID=%s does not describe a grid of %d ranks", e, nranks);
+        }
+    }
     if (nranks == 1) return 0;
     NcclApi* api = nccl_api();
     if (!api) return fail(c, NES_ERR_COMM, "libnccl.so.2 not found");
@@ -171,6 +324,7 @@ int nes_comm_finalize(nes_ctx* c) {
     }
     c->nranks = 1;
     c->rank = 0;
+    c->grid_p = c->grid_q = 1;
     return 0;
 }
 
@@ -179,8 +333,18 @@ int nes_comm_finalize(nes_ctx* c) {
 int nes_dist_layout(const nes_ctx* c, int m, int* nbo, int* P, int* Q) {
     const int nr = c ? c->nranks : 1;
     if (nbo) *nbo = dense_outer_block(m, nr);
-    if (P) *P = 1;
-    if (Q) *Q = nr;
+    if (P) *P = c ? c->grid_p : 1;
+    if (Q) *Q = c ? c->grid_q : nr;
+    return 0;
+}
+
+// Process grid of the dense factorization (default 1 x nranks, or NES_DIST_GRID at nes_comm_init): every rank
+// must set the same grid, before the factors that use it are analyzed.
+int nes_dist_set_grid(nes_ctx* c, int P, int Q) {
+    if (!c) return NES_ERR_INVALID;
+    if (P < 1 || Q < 1 || P * Q != c->nranks) return fail(c, NES_ERR_INVALID, "grid %d x %d is not %d ranks", P, Q, c->nranks);
+    c->grid_p = P;
+    c->grid_q = Q;
     return 0;
 }
 
@@ -188,16 +352,34 @@ int nes_comm_rank(const nes_ctx* c) { return c ? c->rank : 0; }
 int nes_comm_nranks(const nes_ctx* c) { return c ? c->nranks : 1; }
 
 // Host-only planner, exposed so the partition can be checked without a GPU: writes up to `cap`
-// (tile row, tile column) pairs of the tiles `rank` owns and returns how many there are.
+// (tile row, tile column) pairs of the tiles `rank` owns on a 1 x nranks grid and returns how many there are.
 int nes_dist_plan(int m, int nranks, int rank, int* tile_rows, int* tile_cols, int cap) {
-    if (m <= 0 || nranks < 1 || rank < 0 || rank >= nranks) return NES_ERR_INVALID;
-    std::vector<int2> tiles;
-    std::vector<int> first;
-    const int n = dist_plan_tiles(m, dense_outer_block(m, nranks), nranks, rank, tiles, first);
+    return nes_dist_plan_grid(m, 0, 1, nranks, rank, 0, tile_rows, tile_cols, cap, nullptr, nullptr);
+}
+
+// The same for a P x Q grid, distribution block nbo (0 = default) and chunk_rows (0 = default); also reports
+// the number of broadcasts of the whole factorization and how many of them this rank is the root of.
+int nes_dist_plan_grid(int m, int nbo, int P, int Q, int rank, int chunk_rows, int* tile_rows, int* tile_cols,
+                       int cap, int* nmsgs, int* nroot) {
+    if (m <= 0 || P < 1 || Q < 1 || rank < 0 || rank >= P * Q) return NES_ERR_INVALID;
+    if (nbo <= 0) nbo = dense_outer_block(m, P * Q);
+    if (nbo != 128 && nbo != 256 && nbo != 512) return NES_ERR_INVALID;
+    if (chunk_rows <= 0) chunk_rows = dist_chunk_rows(m, nbo, P);
+    if (chunk_rows % (P * nbo) != 0) return NES_ERR_INVALID;
+    DistPlan pl;
+    const int n = dist_make_plan(pl, m, nbo, P, Q, rank, chunk_rows);
     for (int i = 0; i < n && i < cap; ++i) {
-        if (tile_rows) tile_rows[i] = tiles[i].x;
-        if (tile_cols) tile_cols[i] = tiles[i].y;
+        if (tile_rows) tile_rows[i] = pl.tiles[i].x;
+        if (tile_cols) tile_cols[i] = pl.tiles[i].y;
     }
+    int total = 0, mine = 0;
+    for (const DistPanel& pn : pl.panels)
+        for (const DistMsg& d : pn.msgs) {
+            ++total;
+            if (d.root == rank) ++mine;
+        }
+    if (nmsgs) *nmsgs = total;
+    if (nroot) *nroot = mine;
     return n;
 }
 

@@ -108,14 +108,15 @@ nes_factor* nes_analyze(nes_matrix* A, nes_ctx* c) {
         return nullptr;
     }
     if (c->nranks > 1) {
-        // distributed factorization: owned-tile list + packed-panel staging buffer
+        // distributed factorization: message schedule + owned-tile list (nes_dist.cu); events and the staging
+        // ring are created on the first factorization
         L->nbo = dense_outer_block((int)m, c->nranks);
-        std::vector<int2> tiles;
-        L->ntiles_owned = dist_plan_tiles((int)m, L->nbo, c->nranks, c->rank, tiles, L->tile_first);
-        L->d_tile_list = static_cast<int2*>(dev_alloc(c, (tiles.size() + 1) * sizeof(int2)));
-        L->d_stage = static_cast<double*>(dev_alloc(c, ((size_t)m * L->nbo + L->nbo + 16) * sizeof(double)));
-        if (!L->d_tile_list || !L->d_stage ||
-            upload(c, L->d_tile_list, tiles.data(), tiles.size() * sizeof(int2)) != 0) {
+        L->dist = new DistPlan();
+        L->ntiles_owned = dist_make_plan(*L->dist, (int)m, L->nbo, c->grid_p, c->grid_q, c->rank,
+                                         dist_chunk_rows((int)m, L->nbo, c->grid_p));
+        L->d_tile_list = static_cast<int2*>(dev_alloc(c, (L->dist->tiles.size() + 1) * sizeof(int2)));
+        if (!L->d_tile_list ||
+            upload(c, L->d_tile_list, L->dist->tiles.data(), L->dist->tiles.size() * sizeof(int2)) != 0) {
             nes_free_factor(&L, c);
             return nullptr;
         }
@@ -168,7 +169,11 @@ static void nes_free_factor_impl(nes_factor* L, nes_ctx* c) {
     dev_free(c, L->d_flags);
     dev_free(c, L->d_Winv);
     dev_free(c, L->d_tile_list);
-    dev_free(c, L->d_stage);
+    if (L->dist) {
+        dist_free_plan(c, L->dist);
+        delete L->dist;
+        L->dist = nullptr;
+    }
     dev_free(c, L->d_defer_tiles);
     dev_free(c, L->d_defer_ws);
     dev_free(c, L->d_defer_counters);

@@ -43,12 +43,15 @@ struct nes_ctx {
     // wide ones instead of in front of them (sparse_chol.cu: run_factor_phase)
     cudaStream_t stream_b = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // medium-priority stream: the bulk row pieces of a distributed panel (dense_chol.cu)
+    cudaStream_t stream_c = nullptr;
     char err[512] = {0};
     long long launches = 0;
     double form_flops = 0;  // algorithmic flops of the last up-front formation launch (nes_get_form_flops)
 
-    // multi-GPU (one process per GPU; 1 x Q block-cyclic column distribution of M, see nes_dist.cu)
+    // multi-GPU (one process per GPU; P x Q block-cyclic distribution of M, see nes_dist.cu); rank = p*Q + q
     int nranks = 1, rank = 0;
+    int grid_p = 1, grid_q = 1;
     void* nccl_comm = nullptr;
 
     // allocation ledger (device + pinned host), so frees can be accounted without sizes
@@ -178,6 +181,10 @@ namespace nes {
 struct SparseFactor;
 }
 
+namespace nes {
+struct DistPlan;
+}
+
 struct nes_factor {
     bool dense = true;
     nes::SparseFactor* sparse = nullptr;  // supernodal factor (sparse_chol.cu) when !dense
@@ -200,8 +207,7 @@ struct nes_factor {
     int nbo = 0;                 // distribution block = outer panel width
     int2* d_tile_list = nullptr;
     int ntiles_owned = 0;
-    std::vector<int> tile_first;
-    double* d_stage = nullptr;   // packed panel for ncclBroadcast (+ dinv tail)
+    nes::DistPlan* dist = nullptr;  // message schedule, tile segments, events, staging ring (nes_dist.cu)
     // deferred formation (single GPU, dense_chol.cu): the tiles of M in block columns >= defer_split are
     // not formed up front but strip by strip inside the factorization, where they fill the SMs the
     // panel chain leaves idle.  Planned once per (m, n); 0 = everything is formed up front.
@@ -241,9 +247,42 @@ int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, const CUtensorMap& 
 int dense_trsv_sweeps(nes_ctx* c, const double* M, long long ld, int m, const double* dinv, double* d_x,
                       int nbatch, int brows);
 // multi-GPU pieces (nes_dist.cu)
-int dist_plan_tiles(int m, int nbo, int nranks, int rank, std::vector<int2>& tiles,
-                    std::vector<int>& tile_first);
-int dist_broadcast(nes_ctx* c, double* d_buf, size_t count, int root);
+// One broadcast of a distributed panel: a set of block rows of the panel (all from one root).
+struct DistMsg {
+    int root = 0;         // world rank that computes and sends it
+    int has_diag = 0;     // contains the diagonal block (+ the panel's dinv rides at the end of the message)
+    int row_start = 0;    // first row of the first block
+    int nblocks = 1;      // blocks of `bh` rows, `stride` rows apart (P x Q: the root's block rows of one chunk)
+    int bh = 0, stride = 0;
+    int rows = 0;         // nblocks * bh: leading dimension of the packed message (rows past m stay unused)
+    int dep = -1;         // index of the last message of the PREVIOUS panel the root's update of these rows needs
+    std::vector<int> seg; // root only: tpb + 1 offsets into the rank's tile list, one range per tile column
+};
+struct DistPanel {
+    int j0 = 0, jbo = 0, group_q = 0;
+    int diag_msg = 0;            // index of the message that carries the diagonal block
+    std::vector<DistMsg> msgs;   // in broadcast order (the same on every rank)
+    int col_begin = 0, col_end = 0;  // this rank's tiles of block column J: [col_begin, col_end)
+};
+struct DistPlan {
+    int m = 0, nbo = 0, P = 1, Q = 1, rank = 0, chunk = 0, nblk = 0, tpb = 1;
+    std::vector<DistPanel> panels;
+    std::vector<int2> tiles;     // this rank's tiles of tril(M), ordered by (block column, message, tile column, row)
+    size_t max_msg_doubles = 0;
+    // device / stream objects (created by dense_chol.cu on first use, destroyed with the factor)
+    static constexpr int kStages = 4;
+    double* d_stage[kStages] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_arrived;  // per message, global index (panel-major)
+    std::vector<cudaEvent_t> ev_packed;   // per message (used on the root)
+    std::vector<cudaEvent_t> ev_colready; // per panel: block column J carries every update up to panel J-2
+    std::vector<cudaEvent_t> ev_diagdone; // per panel: the diagonal block is factored (root of the diag message)
+    std::vector<int> msg_base;            // global index of panel J's first message
+    cudaEvent_t ev_start = nullptr, ev_end[3] = {nullptr, nullptr, nullptr};
+};
+int dist_make_plan(DistPlan& plan, int m, int nbo, int P, int Q, int rank, int chunk_rows);
+void dist_free_plan(nes_ctx* c, DistPlan* plan);
+int dist_chunk_rows(int m, int nbo, int P);
+int dist_broadcast(nes_ctx* c, double* d_buf, size_t count, int root, cudaStream_t stream = nullptr);
 int dist_allreduce_int(nes_ctx* c, int* d_buf, size_t count, int op_max_else_min);
 int dense_outer_block(int m, int nranks);
 int dist_owner(int J, int nranks);

@@ -124,6 +124,8 @@ def _prototypes(lib):
     fn("nes_comm_rank", C.c_int, _vp)
     fn("nes_comm_nranks", C.c_int, _vp)
     fn("nes_dist_plan", C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int)
+    fn("nes_dist_plan_grid", C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, _ip, _ip)
+    fn("nes_dist_set_grid", C.c_int, _vp, C.c_int, C.c_int)
     fn("nes_dist_layout", C.c_int, _vp, C.c_int, _ip, _ip, _ip)
     fn("nes_mark_begin", C.c_int, _vp)
     fn("nes_mark_end", C.c_int, _vp, _dp)
@@ -210,6 +212,20 @@ def dist_plan(m, nranks, rank):
     cols = np.empty(max(n, 1), dtype=np.int32)
     lib.nes_dist_plan(m, nranks, rank, rows.ctypes.data_as(_ip), cols.ctypes.data_as(_ip), n)
     return np.stack([rows[:n], cols[:n]], axis=1)
+
+
+def dist_plan_grid(m, P, Q, rank, nbo=0, chunk_rows=0):
+    """(tiles (ntiles, 2), broadcasts per factorization, broadcasts rooted at `rank`) on a P x Q grid."""
+    lib = load_library()
+    nm, nr = C.c_int(0), C.c_int(0)
+    n = lib.nes_dist_plan_grid(m, nbo, P, Q, rank, chunk_rows, None, None, 0, C.byref(nm), C.byref(nr))
+    if n < 0:
+        raise NesError("nes_dist_plan_grid: bad arguments")
+    rows = np.empty(max(n, 1), dtype=np.int32)
+    cols = np.empty(max(n, 1), dtype=np.int32)
+    lib.nes_dist_plan_grid(m, nbo, P, Q, rank, chunk_rows, rows.ctypes.data_as(_ip), cols.ctypes.data_as(_ip), n,
+                           C.byref(nm), C.byref(nr))
+    return np.stack([rows[:n], cols[:n]], axis=1), nm.value, nr.value
 
 
 def vec(a):

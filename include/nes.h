@@ -237,9 +237,9 @@ int nes_batch_get_x(nes_batch* bt, double* x_all, nes_ctx* c);
 
 /* ---- multi-GPU: one process per GPU, NCCL over NVLink/NVSwitch --------------------------------
  * The reference has no distributed code at all; these calls are additions.  M and L are distributed
- * block-cyclically by outer block columns over the ranks (1 x Q grid); each finished panel is
- * broadcast with ncclBroadcast, so after nes_factorize every rank holds the complete factor and the
- * solves run replicated.  A and all vectors are replicated.  Rank 0 obtains a 128-byte unique id,
+ * 2D block-cyclically over a P x Q grid of the ranks (default 1 x nranks, NES_DIST_GRID=PxQ); each panel is
+ * broadcast in row chunks with ncclBroadcast as soon as its rows are solved, so after nes_factorize every
+ * rank holds the complete factor and the solves run replicated.  A and all vectors are replicated.  Rank 0 obtains a 128-byte unique id,
  * the launcher (torch.distributed, MPI, ...) ships it to the other ranks, and every rank calls
  * nes_comm_init before the first nes_analyze. */
 int nes_comm_unique_id(unsigned char* id128);
@@ -250,6 +250,12 @@ int nes_comm_nranks(const nes_ctx* c);
 /* host-only: the 128x128 tiles of tril(M) owned by `rank` (m rows, `nranks` ranks); returns the count
  * and fills up to `cap` (tile row, tile column) pairs. */
 int nes_dist_plan(int m, int nranks, int rank, int* tile_rows, int* tile_cols, int cap);
+/* the same for a P x Q grid (rank = p*Q + q), distribution block nbo (0 = default) and panel chunk of
+ * chunk_rows rows (0 = default); *nmsgs = broadcasts per factorization, *nroot = those rooted at `rank` */
+int nes_dist_plan_grid(int m, int nbo, int P, int Q, int rank, int chunk_rows, int* tile_rows, int* tile_cols,
+                       int cap, int* nmsgs, int* nroot);
+/* choose the P x Q grid (P*Q = nranks; same call on every rank, before nes_analyze of the factors that use it) */
+int nes_dist_set_grid(nes_ctx* c, int P, int Q);
 /* distribution block and P x Q process grid the dense factorization of an m x m matrix uses on c's ranks */
 int nes_dist_layout(const nes_ctx* c, int m, int* nbo, int* P, int* Q);
 

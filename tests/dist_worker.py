@@ -165,6 +165,26 @@ def main():
             counts = [int((g >= 0).sum()) for g in gathered]
             if m >= 8192:
                 assert max(counts) - min(counts) <= 0.02 * max(counts), counts
+        # P x Q grids (planned for any rank count on the host): every tile of tril(M) exactly once, every
+        # broadcast has exactly one root, for several distribution blocks / chunk sizes
+        for (P, Q) in ((1, 2), (2, 1), (2, 2), (1, 8), (2, 4), (4, 2), (3, 2)):
+            for (m, nbo, chunk) in ((200, 128, 0), (1153, 256, 512 * P), (5000, 256, 1024 * P), (8192, 512, 0),
+                                    (32768, 256, 0)):
+                if m == 32768 and rank != 0:
+                    continue
+                seen, nroot_sum, nm0 = set(), 0, None
+                for r in range(P * Q):
+                    tiles, nmsgs, nroot = nes.dist_plan_grid(m, P, Q, r, nbo, chunk)
+                    enc = (tiles[:, 0].astype(np.int64) * 100000 + tiles[:, 1]).tolist()
+                    assert not (seen & set(enc)) and len(set(enc)) == len(enc), (P, Q, m, r)
+                    assert (tiles[:, 0] >= tiles[:, 1]).all()
+                    seen |= set(enc)
+                    nroot_sum += nroot
+                    nm0 = nmsgs if nm0 is None else nm0
+                    assert nmsgs == nm0
+                tm = (m + 127) // 128
+                assert len(seen) == tm * (tm + 1) // 2, (P, Q, m, nbo)
+                assert nroot_sum == nm0 > 0
         cpu_sparse_and_batch(rank, world)
         dist.destroy_process_group()
         print(f"rank {rank}: cpu dist ok")
@@ -184,6 +204,48 @@ def main():
         dist.broadcast(idt, 0)
         c.comm_init(world, rank, bytes(idt.cpu().numpy().tobytes()))
         rng = np.random.default_rng(5)
+        # every process grid of this rank count x distribution block x chunk size: whole-matrix residual gate
+        # on the device, solve residual through the GEMV kernels, bit-identical factors across ranks
+        grids = [(p, world // p) for p in range(1, world + 1) if world % p == 0]
+        for (P, Q) in grids:
+            c.check(c.lib.nes_dist_set_grid(c.ptr, P, Q), "nes_dist_set_grid")
+            for (m, n, nbo, chunk) in ((700, 900, 128, 128 * P), (1153, 1400, 256, 256 * P), (2600, 3000, 256, 512 * P),
+                                       (2600, 3000, 512, 0), (4100, 4500, 128, 1024 * P)):
+                os.environ["NES_DIST_NBO"] = str(nbo)
+                os.environ["NES_DIST_CHUNK"] = str(chunk) if chunk else "8192"
+                Ad = nes.Matrix.generate_dense(c, m, n, 3)
+                Ad.scale(np.sqrt(0.1 + 10 * rng.random(n)))
+                L = nes.Factor(c, Ad)
+                assert L.factorize(Ad)
+                res = L.residual(Ad)
+                assert res <= 1e-12, (P, Q, m, nbo, chunk, res)
+                b = rng.random(m)
+                x = L.solve(b)
+                r = Ad.sdmult(Ad.sdmult(x, transpose=True)) - b
+                assert np.linalg.norm(r) / np.linalg.norm(b) <= 1e-9, (P, Q, m, nbo, chunk)
+                t = torch.from_numpy(x).cuda()
+                ref = t.clone()
+                dist.broadcast(ref, 0)
+                assert torch.equal(t, ref)
+                assert L.factorize(Ad)                      # refactorization reuses events / staging
+                np.testing.assert_array_equal(L.solve(b), x)
+                L.free()
+                Ad.free()
+        os.environ.pop("NES_DIST_NBO", None)
+        os.environ.pop("NES_DIST_CHUNK", None)
+        # config-2 size on the default and the squarest grid
+        for (P, Q) in {grids[0], grids[len(grids) // 2]}:
+            c.check(c.lib.nes_dist_set_grid(c.ptr, P, Q), "nes_dist_set_grid")
+            m, n = 8192, 16384
+            Ad = nes.Matrix.generate_dense(c, m, n, 0)
+            Ad.scale(np.sqrt(0.1 + 10 * rng.random(n)))
+            L = nes.Factor(c, Ad)
+            assert L.factorize(Ad)
+            res = L.residual(Ad)
+            assert res <= 1e-12, (P, Q, m, res)
+            L.free()
+            Ad.free()
+        c.check(c.lib.nes_dist_set_grid(c.ptr, 1, world), "nes_dist_set_grid")
         for (m, n) in ((300, 700), (1000, 1500), (1153, 2000)):
             l, u, w, z, A, e, f, g, h = ons.random_dense_case(rng, m, n)
             Ad = nes.Matrix.from_dense(c, A)
