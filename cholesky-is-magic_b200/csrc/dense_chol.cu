@@ -513,7 +513,16 @@ static int dist_update(nes_ctx* c, nes_factor* L, int k0, int K, int tile_begin,
     a.same_operand = 1;
     a.tile_list = L->d_tile_list + tile_begin;
     a.ntiles = tile_end - tile_begin;
-    cudaError_t e = nt_launch(L->mapM, L->mapM, a, one_tile_per_cta ? (1 << 30) : c->num_sms, stream);
+    // one_tile_per_cta: SMs come free at tile granularity for the panel chain on the higher-priority streams.
+    // NES_REST_TPC = tiles per CTA of these launches (default 1; 0 = persistent, one CTA per SM).
+    static int tpc = -1;
+    if (tpc < 0) {
+        const char* ev = getenv("NES_REST_TPC");
+        tpc = ev ? atoi(ev) : 1;
+    }
+    int max_ctas = c->num_sms;
+    if (one_tile_per_cta && tpc > 0) max_ctas = std::max(c->num_sms, (a.ntiles + tpc - 1) / tpc);
+    cudaError_t e = nt_launch(L->mapM, L->mapM, a, max_ctas, stream);
     ++c->launches;
     if (e != cudaSuccess)
         return fail(c, NES_ERR_CUDA, "distributed update launch failed: %s", cudaGetErrorString(e));

@@ -31,6 +31,7 @@ struct NcclApi {
     void* handle = nullptr;
     ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
@@ -49,6 +50,7 @@ static NcclApi* nccl_api() {
     if (!h) return nullptr;
     api.GetUniqueId = reinterpret_cast<decltype(api.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
     api.CommInitRank = reinterpret_cast<decltype(api.CommInitRank)>(dlsym(h, "ncclCommInitRank"));
+    api.CommInitRankConfig = reinterpret_cast<decltype(api.CommInitRankConfig)>(dlsym(h, "ncclCommInitRankConfig"));
     api.CommDestroy = reinterpret_cast<decltype(api.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
     api.Broadcast = reinterpret_cast<decltype(api.Broadcast)>(dlsym(h, "ncclBroadcast"));
     api.AllReduce = reinterpret_cast<decltype(api.AllReduce)>(dlsym(h, "ncclAllReduce"));
@@ -307,7 +309,21 @@ int nes_comm_init(nes_ctx* c, int nranks, int rank, const unsigned char* id128) 
     ncclUniqueId id;
     memcpy(&id, id128, 128);
     ncclComm_t comm;
-    ncclResult_t r = api->CommInitRank(&comm, nranks, id, rank);
+    // A dmma_nt CTA needs every register of its SM, so each resident NCCL CTA takes one SM away from the
+    // trailing updates for as long as a receiver waits for its panel (32 channels by default on NVSwitch:
+    // measured 217 -> 204 ms per factorization at m = 32768 on 2 GPUs with 8).  The panels are small against
+    // NVLink bandwidth, a few CTAs move them fast enough.  NES_NCCL_CTAS overrides (0 = NCCL's default).
+    int max_ctas = 8;
+    if (const char* e = getenv("NES_NCCL_CTAS")) max_ctas = atoi(e);
+    ncclResult_t r;
+    if (api->CommInitRankConfig && max_ctas > 0) {
+        ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+        cfg.minCTAs = 1;
+        cfg.maxCTAs = max_ctas;
+        r = api->CommInitRankConfig(&comm, nranks, id, rank, &cfg);
+    } else {
+        r = api->CommInitRank(&comm, nranks, id, rank);
+    }
     if (r != ncclSuccess)
         return fail(c, NES_ERR_COMM, "ncclCommInitRank failed: %s", api->GetErrorString ? api->GetErrorString(r) : "?");
     c->nccl_comm = comm;
