@@ -514,14 +514,15 @@ static int dist_update(nes_ctx* c, nes_factor* L, int k0, int K, int tile_begin,
     a.tile_list = L->d_tile_list + tile_begin;
     a.ntiles = tile_end - tile_begin;
     // one_tile_per_cta: SMs come free at tile granularity for the panel chain on the higher-priority streams.
-    // NES_REST_TPC = tiles per CTA of these launches (default 1; 0 = persistent, one CTA per SM).
-    static int tpc = -1;
-    if (tpc < 0) {
-        const char* ev = getenv("NES_REST_TPC");
-        tpc = ev ? atoi(ev) : 1;
-    }
+    // NES_REST_TPC = tiles per CTA of these launches (default 1; measured at m = 32768 on 2 GPUs: 204 ms per
+    // factorization with 1 or 2, 208 with 4; one persistent CTA per SM is 266 ms -- the chain starves -- and is
+    // not offered: its residual at m = 32768 was 1e-7 even with every stream serialised, an open defect of
+    // dmma_nt's beta != 0 path at > 100 tiles per CTA that the one-tile launches do not exercise).
+    const char* ev = getenv("NES_REST_TPC");
+    int tpc = ev ? atoi(ev) : 1;
+    if (tpc < 1) tpc = 1;
     int max_ctas = c->num_sms;
-    if (one_tile_per_cta && tpc > 0) max_ctas = std::max(c->num_sms, (a.ntiles + tpc - 1) / tpc);
+    if (one_tile_per_cta) max_ctas = std::max(c->num_sms, (a.ntiles + tpc - 1) / tpc);
     cudaError_t e = nt_launch(L->mapM, L->mapM, a, max_ctas, stream);
     ++c->launches;
     if (e != cudaSuccess)
@@ -620,6 +621,7 @@ static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L, CholTrace& tr) {
     DistPlan& pl = *L->dist;
     const int nblk = pl.nblk, me = c->rank, P = pl.P, tpb = pl.tpb;
     cudaStream_t S0 = c->stream, S1 = c->stream_aux, S2 = c->stream_b, S3 = c->stream_c;
+    if (getenv("NES_DIST_SERIAL")) S1 = S2 = S3 = S0;  // debugging: everything in program order on one stream
     NES_CUDA(c, cudaEventRecord(pl.ev_start, S0));
     NES_CUDA(c, cudaStreamWaitEvent(S1, pl.ev_start, 0));
     NES_CUDA(c, cudaStreamWaitEvent(S2, pl.ev_start, 0));

@@ -19,7 +19,9 @@ with with_cholmod(device=local, timing=True) as c:
     A = nes.Matrix.generate_dense(c, m, n, 0)
     A.scale(np.sqrt(0.1 + 10 * np.random.default_rng(0).random(n)))
     for cfg in configs:
-        grid, nbo, chunk = cfg.split(":")
+        parts = cfg.split(":")
+        grid, nbo, chunk = parts[:3]
+        os.environ["NES_REST_TPC"] = parts[3] if len(parts) > 3 else "1"
         P, Q = map(int, grid.split("x"))
         os.environ["NES_DIST_NBO"], os.environ["NES_DIST_CHUNK"] = nbo, chunk
         c.check(c.lib.nes_dist_set_grid(c.ptr, P, Q), "grid")
