@@ -22,6 +22,7 @@
 #include <vector>
 
 #include "dmma_nt.cuh"
+#include "dmma_nt64.cuh"
 #include "nes_internal.h"
 #include "potrf_block.cuh"
 #include "trtri_block.cuh"
@@ -370,6 +371,13 @@ int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, const CUtensorMap& 
     return 0;
 }
 
+// Which kernel applies the Cholesky updates: the 128 x 64 half-tile kernel with two CTAs per SM (dmma_nt64.cuh,
+// default) or the 128 x 128 one (NES_UPDATE_KERNEL=128, kept for the comparison in DESIGN.md).
+static bool update_uses_nt64() {
+    const char* e = getenv("NES_UPDATE_KERNEL");
+    return !(e && atoi(e) == 128);
+}
+
 // One dmma_nt launch: C[r0.., c0..c0+ncols) -= X[r0.., k0..k0+K) X[c0..c0+ncols, k0..k0+K)^T
 static int chol_update(nes_ctx* c, nes_factor* L, int r0, int c0, int nrows, int ncols, int k0, int K,
                        int lower, cudaStream_t stream = nullptr, bool one_tile_per_cta = false) {
@@ -389,8 +397,11 @@ static int chol_update(nes_ctx* c, nes_factor* L, int r0, int c0, int nrows, int
     a.same_operand = (r0 == c0) ? 1 : 0;
     // one_tile_per_cta: a non-persistent grid, so SMs come free every tile and a higher-priority stream
     // (the panel factorization of the look-ahead) gets them at tile granularity
-    cudaError_t e = nt_launch(L->mapM, L->mapM, a, one_tile_per_cta ? (1 << 30) : c->num_sms,
-                              stream ? stream : c->stream);
+    cudaError_t e = update_uses_nt64()
+                        ? nt64_launch(L->mapM, L->mapM68, a, one_tile_per_cta ? 0 : 2 * c->num_sms,
+                                      stream ? stream : c->stream)
+                        : nt_launch(L->mapM, L->mapM, a, one_tile_per_cta ? (1 << 30) : c->num_sms,
+                                    stream ? stream : c->stream);
     ++c->launches;
     if (e != cudaSuccess)
         return fail(c, NES_ERR_CUDA, "Cholesky update launch failed: %s", cudaGetErrorString(e));
@@ -523,7 +534,8 @@ static int dist_update(nes_ctx* c, nes_factor* L, int k0, int K, int tile_begin,
     if (tpc < 1) tpc = 1;
     int max_ctas = c->num_sms;
     if (one_tile_per_cta) max_ctas = std::max(c->num_sms, (a.ntiles + tpc - 1) / tpc);
-    cudaError_t e = nt_launch(L->mapM, L->mapM, a, max_ctas, stream);
+    cudaError_t e = update_uses_nt64() ? nt64_launch(L->mapM, L->mapM68, a, 0, stream)
+                                       : nt_launch(L->mapM, L->mapM, a, max_ctas, stream);
     ++c->launches;
     if (e != cudaSuccess)
         return fail(c, NES_ERR_CUDA, "distributed update launch failed: %s", cudaGetErrorString(e));

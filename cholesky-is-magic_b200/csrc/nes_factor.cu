@@ -101,6 +101,7 @@ nes_factor* nes_analyze(nes_matrix* A, nes_ctx* c) {
     // pad rows m..ld of M are never written by the kernels; keep them finite for the TMA boxes
     cudaMemsetAsync(L->d_M, 0, L->ld * m * sizeof(double), c->stream);
     if (make_operand_map(&L->mapM, L->d_M, (long long)m, (long long)m, (long long)L->ld) != 0 ||
+        make_operand_map(&L->mapM68, L->d_M, (long long)m, (long long)m, (long long)L->ld, 68, NT_BK) != 0 ||
         make_operand_map(&L->mapBlk, L->d_M, (long long)m, (long long)m, (long long)L->ld, 128, 128) != 0 ||
         make_operand_map(&L->mapSlab, L->d_M, (long long)m, (long long)m, (long long)L->ld, 64, 128) != 0) {
         fail(c, NES_ERR_CUDA, "cuTensorMapEncodeTiled failed for M (%zu x %zu)", m, m);

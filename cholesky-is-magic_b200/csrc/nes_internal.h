@@ -197,7 +197,8 @@ struct nes_factor {
     int* d_flags = nullptr;    // per-block-row ready flags of the dataflow TRSV (epoch numbered)
     double* d_Winv = nullptr;  // inverses of the 128x128 diagonal blocks of L (solve phase only)
     int flag_epoch = 0;
-    CUtensorMap mapM;    // 132 x 16 operand boxes (dmma_nt)
+    CUtensorMap mapM;    // 132 x 32 operand boxes (dmma_nt)
+    CUtensorMap mapM68;  // 68 x 32 boxes: the column operand of the half-tile update kernel (dmma_nt64)
     CUtensorMap mapBlk;  // 128 x 128 block boxes (diagonal-block kernels)
     CUtensorMap mapSlab; // 64 x 128 slabs of a panel (TRSM)
     int factorized = 0;

@@ -18,7 +18,7 @@ from oracle import pdas as opdas  # noqa: E402
 HERE = os.path.dirname(os.path.abspath(__file__))
 
 
-def pdas_case(m, n, seed):
+def pdas_case(m, n, seed, suffix=""):
     sf = lpgen.dense_lp(m, n, seed)
     st = opdas.make_pdas(sf.nvars, sf.ncons, sf.c_dense(), sf.A_dense, sf.b, sf.l, sf.u)
     obj, gap, iters = opdas.pdas(st, 500)
@@ -33,7 +33,7 @@ def pdas_case(m, n, seed):
         "stop_margin": {"previous_gap": gaps[-2], "last_gap": gaps[-1]},
         "x_head": st.x[:8].tolist(), "y_head": st.y[:8].tolist(),
     }
-    json.dump(out, open(os.path.join(HERE, f"pdas_dense_m{m}_n{n}_seed{seed}.json"), "w"), indent=1)
+    json.dump(out, open(os.path.join(HERE, f"pdas_dense_m{m}_n{n}_seed{seed}{suffix}.json"), "w"), indent=1)
     print(m, n, seed, iters, obj, gaps[-2], gaps[-1])
 
 
@@ -50,7 +50,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "config2":
         # BASELINE config 2 on the host: ~100 oracle iterations of 2.4e12 flops each (a quarter of an hour on
         # 8 cores); run once, the fixture pins the GPU's iteration count / objective at full size
-        pdas_case(8192, 16384, 0)
+        # a second argument names a variant run (e.g. under another OPENBLAS_NUM_THREADS: a different
+        # summation order in dgemm / dpotrf) whose fixture shows how far the oracle moves against itself
+        pdas_case(8192, 16384, 0, suffix=("_" + sys.argv[2]) if len(sys.argv) > 2 else "")
         sys.exit(0)
     pdas_case(20, 50, 0)
     pdas_case(200, 500, 0)
