@@ -296,6 +296,12 @@ def run_dense(c, m, n, K, W, seed, world, barrier, local, lp_solve):
             traffic = 6.81e9
             traffic_source = ("ncu --set full capture profiles/r01_ncu_full_formation_dmma_nt_m8192.details.txt "
                               "(dram read+write of one launch), not measured in this run; algorithmic 1.34e9")
+        elif (m, n, world) == (32768, 65536, 1):
+            traffic = 6.664e11
+            traffic_source = ("ncu --set full capture profiles/r02_ncu_full_formation_dmma_nt_m32768.raw_metrics.csv "
+                              "(dram__bytes_read.sum 661.98 GB + dram__bytes_write.sum 4.47 GB of one launch, DRAM at "
+                              "4% of peak), not measured in this run; algorithmic 8mn + 4m^2 = 2.15e10: one 128-row "
+                              "block of A is 67 MB, so only tiles running at the same time share it through L2")
         roof = {"bound": "tensor", "kernel": "dmma_nt_kernel<true> (fused scale+SYRK)",
                 "achieved": ach, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": ach / FP64_DMMA_PEAK_TFLOPS, "traffic": traffic, "traffic_source": traffic_source,
