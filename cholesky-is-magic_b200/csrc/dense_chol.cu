@@ -192,7 +192,7 @@ static int defer_plan(nes_ctx* c, nes_factor* L, size_t n) {
     const int m = (int)L->m;
     const int defer = defer_env("NES_CHOL_DEFER", 0);
     const int min_m = defer_env("NES_CHOL_DEFER_MIN_M", 5120);
-    if (c->nranks > 1 || defer <= 0 || m < min_m || !chol_lookahead(c, m)) return 0;
+    if (L->dist || defer <= 0 || m < min_m || !chol_lookahead(c, m)) return 0;
     std::vector<int> bounds;  // panel boundaries p_0 = 0 < p_1 < ... < m
     for (int j0 = 0; j0 < m; j0 += chol_width(m, j0)) bounds.push_back(j0);
     // the first deferred block column must be the "J+2" of some step: p_k with k >= 2
@@ -292,7 +292,7 @@ static int defer_form_strip(nes_ctx* c, const nes_matrix* A, nes_factor* L, int 
 int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L, bool allow_defer) {
     const MatrixBase* b = A->base;
     int split = 0;
-    if (allow_defer && c->nranks == 1) {
+    if (allow_defer && !L->dist) {
         NES_TRY(defer_plan(c, L, b->n));
         split = L->defer_split;
     }
@@ -309,7 +309,7 @@ int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L, bool allow
     a.beta = 0.0;
     a.lower = 1;
     a.same_operand = 1;
-    if (c->nranks > 1) {  // only the tiles this rank owns (block-cyclic outer block columns)
+    if (L->dist) {  // only the tiles this rank owns (block-cyclic outer block columns)
         a.tile_list = L->d_tile_list;
         a.ntiles = L->ntiles_owned;
         a.lower = 0;
@@ -534,8 +534,24 @@ static int dist_update(nes_ctx* c, nes_factor* L, int k0, int K, int tile_begin,
     if (tpc < 1) tpc = 1;
     int max_ctas = c->num_sms;
     if (one_tile_per_cta) max_ctas = std::max(c->num_sms, (a.ntiles + tpc - 1) / tpc);
-    cudaError_t e = update_uses_nt64() ? nt64_launch(L->mapM, L->mapM68, a, 0, stream)
-                                       : nt_launch(L->mapM, L->mapM, a, max_ctas, stream);
+    // The distributed schedule keeps the 128 x 128 kernel.  OPEN DEFECT: with the half-tile kernel (or one
+    // persistent 128 x 128 CTA per SM) on the trailing updates of the distributed schedule, m = 32768 with
+    // 512-column panels (panel operand 134 MB > L2) ends with ||LL' - M|| / ||M|| ~ 1e-7 instead of 5e-15:
+    // isolated 16 x 32 .. 16 x 96 blocks of single tiles lose one update.  It reproduces on ONE GPU with
+    // NES_FORCE_DIST=1 (tools/debug_dist_single.py names the tiles), disappears when every stream is
+    // serialised (NES_DIST_SERIAL=1), never appears with 256-column panels or at m <= 16384, and the
+    // single-GPU schedule with the half-tile kernel passed 14 of 14 whole-matrix residual checks at
+    // m = 20480 .. 32768 (tools/stress_residual.py).  Every launch below was validated by the whole-matrix
+    // residual at 2 and 8 GPUs (bench.py prints it on every line).  NES_DIST_KERNEL_DEBUG=1/2/3 selects the
+    // half-tile kernel for the trailing updates / the panel chain / both, for whoever picks this up.
+    bool use64 = false;
+    if (const char* dbg = getenv("NES_DIST_KERNEL_DEBUG")) {
+        const int v = atoi(dbg);
+        const bool is_rest = (stream == c->stream_aux);
+        use64 = (v == 1) ? is_rest : (v == 2 ? !is_rest : v == 3);
+    }
+    cudaError_t e = use64 ? nt64_launch(L->mapM, L->mapM68, a, 0, stream)
+                          : nt_launch(L->mapM, L->mapM, a, max_ctas, stream);
     ++c->launches;
     if (e != cudaSuccess)
         return fail(c, NES_ERR_CUDA, "distributed update launch failed: %s", cudaGetErrorString(e));
@@ -669,7 +685,7 @@ static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L, CholTrace& tr) {
                 NES_CUDA(c, cudaEventRecord(pl.ev_packed[gi], st));
                 NES_CUDA(c, cudaStreamWaitEvent(S2, pl.ev_packed[gi], 0));
                 t = tr.open("send", pn.j0, S2);
-                NES_TRY(dist_broadcast(c, stage, count, d.root, S2));
+                if (c->nranks > 1) NES_TRY(dist_broadcast(c, stage, count, d.root, S2));
                 tr.close(t, S2);
             } else {
                 int t = tr.open("recv", pn.j0, S2);
@@ -702,7 +718,7 @@ int dense_cholesky(nes_ctx* c, nes_factor* L, const nes_matrix* A) {
     NES_TRY(chol_configure(c));
     const int m = (int)L->m;
     const long long ld = (long long)L->ld;
-    const int P = c->nranks;
+    const int P = L->dist ? 2 : 1;  // 2 = the distributed schedule (also under NES_FORCE_DIST on one rank)
     NES_CUDA(c, cudaMemsetAsync(L->d_info, 0, 2 * sizeof(int), c->stream));
     if (P > 1) {
         CholTrace tr;
@@ -794,7 +810,7 @@ int dense_cholesky(nes_ctx* c, nes_factor* L, const nes_matrix* A) {
                                                                                   L->d_Winv);
         NES_CHECK_LAUNCH(c);
     }
-    if (P > 1) {  // a failed pivot is only seen by the owner of its panel: agree on {status, first minor}
+    if (c->nranks > 1) {  // a failed pivot is only seen by the owner of its panel: agree on {status, first minor}
         info_to_minor_kernel<<<1, 32, 0, c->stream>>>(L->d_info);
         NES_CHECK_LAUNCH(c);
         NES_TRY(dist_allreduce_int(c, L->d_info, 1, 1));

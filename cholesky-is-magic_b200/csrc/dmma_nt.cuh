@@ -26,6 +26,7 @@
 // they are conflict-free without swizzling.  Cost: 3% extra L2->smem traffic.
 #pragma once
 #include <cstdint>
+#include <cstdlib>
 #include <cuda.h>
 #include <cuda_runtime.h>
 
@@ -432,9 +433,16 @@ inline int make_operand_map(CUtensorMap* map, const double* base, long long rows
     cuuint64_t strides[1] = {static_cast<cuuint64_t>(ld) * 8};
     cuuint32_t box[2] = {static_cast<cuuint32_t>(box_rows), static_cast<cuuint32_t>(box_cols)};
     cuuint32_t estr[2] = {1, 1};
+    CUtensorMapL2promotion promo = CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
+    if (const char* e = getenv("NES_TMA_L2PROMO")) {  // debugging: 0 none, 64, 128, 256
+        const int v = atoi(e);
+        promo = v == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                       : (v == 64 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                  : (v == 128 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_256B));
+    }
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims,
                      strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     return r == CUDA_SUCCESS ? 0 : -2;
 }
 

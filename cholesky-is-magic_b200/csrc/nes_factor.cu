@@ -108,7 +108,9 @@ nes_factor* nes_analyze(nes_matrix* A, nes_ctx* c) {
         nes_free_factor(&L, c);
         return nullptr;
     }
-    if (c->nranks > 1) {
+    // NES_FORCE_DIST: run the distributed schedule on ONE GPU (every message is local, no NCCL call) so that
+    // it can be debugged and profiled without a multi-GPU box
+    if (c->nranks > 1 || getenv("NES_FORCE_DIST")) {
         // distributed factorization: message schedule + owned-tile list (nes_dist.cu); events and the staging
         // ring are created on the first factorization
         L->nbo = dense_outer_block((int)m, c->nranks);
@@ -238,6 +240,11 @@ int nes_factor_residual(nes_matrix* A, nes_factor* L, double out[3], nes_ctx* c)
     const int nranks = c->nranks;
     c->nranks = 1;
     nes_factor* T = nes_analyze(A, c);
+    if (T && T->dist) {  // NES_FORCE_DIST: the check still forms the whole triangle with the plain enumeration
+        dist_free_plan(c, T->dist);
+        delete T->dist;
+        T->dist = nullptr;
+    }
     int rc = T ? dense_form_normal(c, A, T) : c->status;
     c->nranks = nranks;
     double* Lc = T ? static_cast<double*>(dev_alloc(c, (size_t)ld * m * sizeof(double))) : nullptr;

@@ -22,6 +22,11 @@ with with_cholmod(device=local, timing=True) as c:
         parts = cfg.split(":")
         grid, nbo, chunk = parts[:3]
         os.environ["NES_REST_TPC"] = parts[3] if len(parts) > 3 else "1"
+        for k, v in zip(("NES_UPDATE_KERNEL", "NES_DIST_KERNEL_DEBUG", "NES_DIST_SERIAL"), parts[4:7]):
+            if v and v != "-":
+                os.environ[k] = v
+            else:
+                os.environ.pop(k, None)
         P, Q = map(int, grid.split("x"))
         os.environ["NES_DIST_NBO"], os.environ["NES_DIST_CHUNK"] = nbo, chunk
         c.check(c.lib.nes_dist_set_grid(c.ptr, P, Q), "grid")

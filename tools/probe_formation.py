@@ -12,5 +12,6 @@ with with_cholmod(device=0, timing=True) as c:
     L = nes.Factor(c, A)
     assert L.factorize(A)
     t = c.timing()
-    print(f"m={m} n={n}: form {t['form'][0]:.2f} ms ({m * m * n / t['form'][0] / 1e9:.2f} TFLOP/s)  factor {t['factor'][0]:.2f} ms", flush=True)
+    res = L.residual(A) if len(sys.argv) > 3 else float("nan")
+    print(f"m={m} n={n}: residual {res:.2e} form {t['form'][0]:.2f} ms ({m * m * n / t['form'][0] / 1e9:.2f} TFLOP/s)  factor {t['factor'][0]:.2f} ms", flush=True)
     L.free(); A.free()
