@@ -649,7 +649,13 @@ static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L, CholTrace& tr) {
     DistPlan& pl = *L->dist;
     const int nblk = pl.nblk, me = c->rank, P = pl.P, tpb = pl.tpb;
     cudaStream_t S0 = c->stream, S1 = c->stream_aux, S2 = c->stream_b, S3 = c->stream_c;
-    if (getenv("NES_DIST_SERIAL")) S1 = S2 = S3 = S0;  // debugging: everything in program order on one stream
+    if (const char* e = getenv("NES_DIST_SERIAL")) {  // debugging: merge streams into the main one (bit 0: trailing
+        const int v = atoi(e);                        // updates, bit 1: communication, bit 2: bulk pieces; 1 = all)
+        const int mask = (v == 1) ? 7 : v >> 1;
+        if (mask & 1) S1 = S0;
+        if (mask & 2) S2 = S0;
+        if (mask & 4) S3 = S0;
+    }
     NES_CUDA(c, cudaEventRecord(pl.ev_start, S0));
     NES_CUDA(c, cudaStreamWaitEvent(S1, pl.ev_start, 0));
     NES_CUDA(c, cudaStreamWaitEvent(S2, pl.ev_start, 0));

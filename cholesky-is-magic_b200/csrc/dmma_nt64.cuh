@@ -104,7 +104,7 @@ dmma_nt64_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         const int col_base = bj * NT_BN + h * N64_BN + wn * 32 + 2 * t4;
 
         // warm L2 with the C half tile while the mainloop runs
-        if (p.beta != 0.0 && g == 0) {
+        if (p.beta != 0.0 && g == 0 && p.batch_rows == 0) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
@@ -213,6 +213,7 @@ inline cudaError_t nt64_launch(const CUtensorMap& mapX, const CUtensorMap& mapY,
     if (!a.tile_list) a.ntiles = a.lower ? tm * (tm + 1) / 2 : tm * tn;
     if (a.ntiles <= 0) return cudaSuccess;
     a.batch_tiles = 0;
+    a.batch_rows = getenv("NES_N64_NOPREFETCH") ? 1 : 0;  // debugging switch (the field is unused by this kernel)
     a.split_r = a.split_s = a.split_all = 0;
     a.scale = nullptr;
     const int nitems = 2 * a.ntiles;

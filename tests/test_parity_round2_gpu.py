@@ -135,13 +135,26 @@ def test_sparse_pdas_with_a_free_variable_reports_the_filter_z_trap(common):
 
 
 def test_config2_iteration_count_and_objective_against_the_oracle_golden(common):
-    """BASELINE config 2 (m=8192, n=16384, seed 0): the oracle's whole PDAS run was computed once on the host
-    (tests/golden/make_golden.py config2).  Gate: identical iteration count, objective within 1e-9 relative.
-    The count is decided by the gap crossing 1e-4; the fixture records the margin on both sides."""
+    """BASELINE config 2 (m=8192, n=16384, seed 0) against the oracle's whole PDAS run, computed once on the
+    host (tests/golden/make_golden.py config2: 95 iterations).
+
+    What can be pinned at this size, and what cannot.  The iteration map amplifies rounding differences by
+    about a decade every eight iterations: the ORACLE AGAINST ITSELF, re-run with 5 instead of 8 OpenBLAS
+    threads (second fixture, *_blas5threads.json), agrees on the step length to 2e-10 at iteration 11, 6e-7
+    at 51, 4e-3 at 81 and 4e-2 at 91; its final dual objective moves by 1.8e-5 relative and its last two
+    gaps from (2.6e-4, 3.5e-5) to (1.4e-4, 1.7e-5) around the 1e-4 stop threshold.  The GPU path diverges
+    from either oracle run at the same rate (profiles/r02_config2_trajectory_vs_oracle.log) and crosses the
+    threshold one iteration later (gaps 2.6e-4, 6.2e-5).  So: the first 40 steps must agree to 1e-6, the
+    iteration count within one of the oracle's, the primal objective (which does not carry the 1e8-clamped
+    bound multipliers) to 1e-7 relative, the dual objective within the stop tolerance 1e-4.  The north star's
+    "identical iteration count, objective to 1e-9" is met on config 1 (test_dense_gpu.py), where the run is
+    36 iterations long; at 95 iterations the reference could not meet it against a rebuild of itself."""
     path = os.path.join(GOLDEN, "pdas_dense_m8192_n16384_seed0.json")
-    if not os.path.exists(path):
-        pytest.skip("golden for config 2 not generated")
     gold = json.load(open(path))
+    var = json.load(open(os.path.join(GOLDEN, "pdas_dense_m8192_n16384_seed0_blas5threads.json")))
+    # the premise above, checked: the two oracle runs differ from each other as described
+    assert gold["iterations"] == var["iterations"] == 95
+    assert 1e-6 < abs(gold["dobj"] - var["dobj"]) / abs(gold["dobj"]) < 1e-4
     m, n, seed = gold["m"], gold["n"], gold["seed"]
     A = nes.Matrix.generate_dense(common, m, n, seed)
     xs, ys, zs = lpgen.aux_vectors(m, n, seed)
@@ -152,13 +165,16 @@ def test_config2_iteration_count_and_objective_against_the_oracle_golden(common)
     sf = StandardForm(nvars=n, ncons=m, c=list(enumerate(cvec.tolist())), A=None, b=b,
                       l=np.zeros(n), u=np.full(n, np.inf), initial_vars=n)
     st = pdas.make_pdas(sf, scale=True, generated_seed=seed)
-    obj, gap, it = pdas.pdas(st, 300, native_loop=True)
+    obj, gap, it = pdas.pdas(st, 300)               # stepwise: the log carries every step
     assert st.converged
-    margin = gold["stop_margin"]
-    # a gap within 5% of the threshold on either side would make the count a coin toss: say so loudly
-    assert not (0.95e-4 < margin["previous_gap"] < 1.05e-4 or 0.95e-4 < margin["last_gap"] < 1.05e-4), margin
-    assert it == gold["iterations"], (it, gold["iterations"], gap, margin)
-    assert abs(obj - gold["dobj"]) <= 1e-9 * abs(gold["dobj"])
+    assert [e["branch"] for e in st.log][:len(gold["branches"]) - 1] == gold["branches"][:-1]
+    steps = [e.get("step") for e in st.log]
+    for k in range(2, 40):
+        assert abs(steps[k] - gold["steps"][k]) <= 1e-6 * gold["steps"][k], (k, steps[k], gold["steps"][k])
+    assert abs(it - gold["iterations"]) <= 1, (it, gold["iterations"], gap, gold["stop_margin"])
+    assert abs(obj - gold["dobj"]) <= 1e-4 * abs(gold["dobj"])
+    pobj = float(st.c @ st.final["x"])
+    assert abs(pobj - gold["pobj_last"]) <= 1e-7 * abs(gold["pobj_last"]), (pobj, gold["pobj_last"])
 
 
 def test_whole_matrix_factor_residual_on_the_device_m8192(common):
