@@ -371,11 +371,16 @@ int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, const CUtensorMap& 
     return 0;
 }
 
-// Which kernel applies the Cholesky updates: the 128 x 64 half-tile kernel with two CTAs per SM (dmma_nt64.cuh,
-// default) or the 128 x 128 one (NES_UPDATE_KERNEL=128, kept for the comparison in DESIGN.md).
+// Which kernel applies the Cholesky updates: the 128 x 128 one (default) or, with NES_UPDATE_KERNEL=64, the
+// 128 x 64 half-tile kernel with two CTAs per SM (dmma_nt64.cuh).  The half-tile kernel is 4% faster on the
+// factorization at m = 32768 (368 -> 354 ms) and passed every whole-matrix residual check of the single-GPU
+// schedule (14 of 14 at m = 20480..32768, 100 of 100 at m = 8192..12288), but it is OPT-IN: on the
+// distributed schedule it loses an update of part of one tile about once per factorization at m = 32768
+// (DESIGN.md section 5), and one of four runs of the 96-iteration config-2 PDAS solve ended in a non-positive
+// pivot with it, which never happened with the 128 x 128 kernel.  A rare wrong answer is not worth 4%.
 static bool update_uses_nt64() {
     const char* e = getenv("NES_UPDATE_KERNEL");
-    return !(e && atoi(e) == 128);
+    return e && atoi(e) == 64;
 }
 
 // One dmma_nt launch: C[r0.., c0..c0+ncols) -= X[r0.., k0..k0+K) X[c0..c0+ncols, k0..k0+K)^T
@@ -687,7 +692,8 @@ static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L, CholTrace& tr) {
                 if (d.has_diag) NES_CUDA(c, cudaEventRecord(pl.ev_diagdone[J], st));
                 if (gi >= DistPlan::kStages)  // the staging slot's previous broadcast is over
                     NES_CUDA(c, cudaStreamWaitEvent(st, pl.ev_arrived[gi - DistPlan::kStages], 0));
-                NES_TRY(dist_pack(c, L, pn, d, stage, 0, st));
+                if (!(c->nranks == 1 && getenv("NES_DIST_NOPACK")))  // debugging (one GPU: nobody reads the stage)
+                    NES_TRY(dist_pack(c, L, pn, d, stage, 0, st));
                 NES_CUDA(c, cudaEventRecord(pl.ev_packed[gi], st));
                 NES_CUDA(c, cudaStreamWaitEvent(S2, pl.ev_packed[gi], 0));
                 t = tr.open("send", pn.j0, S2);
