@@ -13,7 +13,10 @@
 #include <cmath>
 #include <vector>
 
+#include <cstdlib>
+
 #include "dmma_nt.cuh"
+#include "potrf_block.cuh"
 #include "ipm_kernels.cuh"
 #include "nes_internal.h"
 
@@ -210,6 +213,67 @@ __global__ void batch_pack_rows_kernel(const double* __restrict__ src, size_t sr
 }
 
 // form + factor all problems:  M_b = A_b diag(theta_b) A_b',  M_b = L_b L_b'
+// ---- batched Cholesky on 64 x 64 diagonal blocks (round 2) -------------------------------------------
+// The 128 x 128 panel kernels of the dense path need 133 KB (potrf) / 196 KB (trsm) of shared memory: one CTA
+// per SM, and both are latency chains, so 1024 problems take 7 + 14 waves of 43 / 20 us (1.05 ms per batched
+// factorization, 0.15 of the tensor roofline).  With 64 x 64 blocks a CTA needs 33 KB / 66 KB and two / three are
+// resident per SM; the trailing updates stay on the DMMA kernel (K = 64).  MEASURED (1024 x 256 x 512, B200):
+// 1.17 ms against 1.05 ms -- the potrf/trsm chains do get shorter, but the ten launches' trailing updates on
+// 128 x 128 tiles with K = 64 pay the tile's fixed cost (operand fill + 256 KB read-modify-write) 5120 times.
+// Kept opt-in (NES_BATCH_PANEL64=1) with its parity tests; what the batched factor needs is a fused
+// trsm + update kernel on 64 x 64 output tiles, not smaller panels.
+constexpr int B64 = 64;
+
+__global__ void __launch_bounds__(256, 2)
+potrf64_batch_kernel(double* __restrict__ M, long long ld, int i0, int jb, double* __restrict__ dinv_g,
+                     double dbound, int* __restrict__ info, int brows) {
+    __shared__ double S[B64 * B64];
+    __shared__ double dv[B64];
+    const int tid = threadIdx.x;
+    const long long brow = (long long)blockIdx.x * brows;
+    double* blk = M + brow + i0 + (long long)i0 * ld;
+    for (int idx = tid; idx < B64 * B64; idx += 256) {
+        const int cc = idx >> 6, r = idx & 63;
+        S[idx] = (r < jb && cc < jb) ? blk[r + (long long)cc * ld] : (r == cc ? 1.0 : 0.0);
+    }
+    __syncthreads();
+    potrf_block_smem<B64, 4>(S, dv, jb, dbound, info + 2 * blockIdx.x, i0);
+    __syncthreads();
+    for (int idx = tid; idx < B64 * B64; idx += 256) {
+        const int cc = idx >> 6, r = idx & 63;
+        if (r < jb && cc <= r) blk[r + (long long)cc * ld] = S[idx];
+    }
+    if (tid < jb) dinv_g[brow + i0 + tid] = dv[tid];
+}
+
+__global__ void __launch_bounds__(256)
+trsm64_batch_kernel(double* __restrict__ M, long long ld, int i0, int jb, int m, const double* __restrict__ dinv_g,
+                    int brows) {
+    extern __shared__ double sm64[];
+    double* Ls = sm64;                 // Ls[c + p*64] = L(c, p), zero above the diagonal
+    double* Xs = Ls + B64 * B64;       // Xs[p*64 + row]
+    double* dv = Xs + B64 * B64;
+    const int tid = threadIdx.x;
+    const long long brow = (long long)blockIdx.y * brows;
+    const int row0 = i0 + jb + blockIdx.x * 64;
+    const int nrows = min(64, m - row0);
+    const double* Lg = M + brow + i0 + (long long)i0 * ld;
+    double* Xg = M + brow + row0 + (long long)i0 * ld;
+    for (int idx = tid; idx < B64 * B64; idx += 256) {
+        const int p = idx >> 6, r = idx & 63;
+        Ls[idx] = (r < jb && p < jb && r >= p) ? Lg[r + (long long)p * ld] : 0.0;
+        Xs[idx] = (r < nrows && p < jb) ? Xg[r + (long long)p * ld] : 0.0;
+    }
+    if (tid < B64) dv[tid] = (tid < jb) ? dinv_g[brow + i0 + tid] : 1.0;
+    __syncthreads();
+    trsm_slab_smem_t<B64, B64, false>(Ls, Xs, dv, jb, nrows);
+    __syncthreads();
+    for (int idx = tid; idx < B64 * B64; idx += 256) {
+        const int p = idx >> 6, r = idx & 63;
+        if (r < nrows && p < jb) Xg[r + (long long)p * ld] = Xs[idx];
+    }
+}
+
 static int batch_factor(nes_ctx* c, nes_batch* bt) {
     const int B = bt->B, m = bt->m, mp = bt->mp;
     const int tm = (m + NT_BM - 1) / NT_BM;
@@ -236,9 +300,32 @@ static int batch_factor(nes_ctx* c, nes_batch* bt) {
     }
     StageTimer t(c, NES_STAGE_FACTOR);
     NES_CUDA(c, cudaMemsetAsync(bt->d_info, 0, 2 * B * sizeof(int), c->stream));
-    for (int i0 = 0; i0 < m; i0 += 128) {
-        const int ib = (m - i0 < 128) ? m - i0 : 128;
-        NES_TRY(chol_panel_launch(c, bt->mapBlk, bt->mapSlab, i0, ib, m, bt->d_dinv, bt->d_info, B, mp));
+    // 128-column panels by default; NES_BATCH_PANEL64=1 selects the 64 x 64 block kernels above (measured: not faster)
+    static const bool wide = getenv("NES_BATCH_PANEL64") == nullptr;
+    const int nb = wide ? 128 : B64;
+    for (int i0 = 0; i0 < m; i0 += nb) {
+        const int ib = (m - i0 < nb) ? m - i0 : nb;
+        if (wide) {
+            NES_TRY(chol_panel_launch(c, bt->mapBlk, bt->mapSlab, i0, ib, m, bt->d_dinv, bt->d_info, B, mp));
+        } else {
+            potrf64_batch_kernel<<<B, 256, 0, c->stream>>>(bt->d_M, (long long)bt->ld, i0, ib, bt->d_dinv, c->dbound,
+                                                          bt->d_info, mp);
+            NES_CHECK_LAUNCH(c);
+            if (m - i0 - ib > 0) {
+                constexpr int kTrsmSmem = (2 * B64 * B64 + B64) * 8;
+                static PerDeviceOnce once;
+                int dev;
+                if (once.begin(&dev)) {
+                    cudaError_t e = cudaFuncSetAttribute(trsm64_batch_kernel,
+                                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kTrsmSmem);
+                    once.finish(dev, e == cudaSuccess);
+                    NES_CUDA(c, e);
+                }
+                trsm64_batch_kernel<<<dim3((m - i0 - ib + 63) / 64, B), 256, kTrsmSmem, c->stream>>>(
+                    bt->d_M, (long long)bt->ld, i0, ib, m, bt->d_dinv, mp);
+                NES_CHECK_LAUNCH(c);
+            }
+        }
         const int rest = m - i0 - ib;
         if (rest > 0) {
             const int tr = (rest + NT_BM - 1) / NT_BM;

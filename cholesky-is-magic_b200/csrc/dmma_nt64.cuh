@@ -193,7 +193,7 @@ inline cudaError_t n64_configure() {
     int dev;
     if (!once.begin(&dev)) return cudaSuccess;
     cudaError_t e = cudaFuncSetAttribute(dmma_nt64_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         N64_SMEM_BYTES);
+                                         131072);
     if (e == cudaSuccess)
         e = cudaFuncSetAttribute(dmma_nt64_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
@@ -218,7 +218,9 @@ inline cudaError_t nt64_launch(const CUtensorMap& mapX, const CUtensorMap& mapY,
     a.scale = nullptr;
     const int nitems = 2 * a.ntiles;
     const int grid = (max_ctas > 0 && max_ctas < nitems) ? max_ctas : nitems;
-    dmma_nt64_kernel<<<grid, N64_THREADS, N64_SMEM_BYTES, stream>>>(mapX, mapY, a);
+    // NES_N64_ONE_CTA (debugging): ask for 128 KB so that only one CTA fits on an SM
+    const int smem = getenv("NES_N64_ONE_CTA") ? 131072 : N64_SMEM_BYTES;
+    dmma_nt64_kernel<<<grid, N64_THREADS, smem, stream>>>(mapX, mapY, a);
     return cudaGetLastError();
 }
 

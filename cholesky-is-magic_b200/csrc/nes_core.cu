@@ -4,6 +4,8 @@
 // -> release).
 #include <new>
 
+#include <cstdlib>
+
 #include "nes_internal.h"
 
 namespace nes {
@@ -216,6 +218,7 @@ int nes_start(nes_ctx* c) {
     c->num_sms = prop.multiProcessorCount;
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);  // lo = least urgent (numerically greatest)
+    if (getenv("NES_NO_PRIORITY")) prio_lo = prio_hi = 0;    // debugging: every stream at the default priority
     if (cudaStreamCreateWithPriority(&c->stream, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->stream_aux, cudaStreamNonBlocking, prio_lo) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->stream_b, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||

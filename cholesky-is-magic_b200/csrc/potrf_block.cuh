@@ -18,6 +18,9 @@ __device__ long long potrf_prof[8];
 constexpr int CH_NB = 128;
 constexpr int CH_P = 128;  // smem pitch of the diagonal block (column-major, dense TMA box)
 
+// PITCH = shared-memory pitch of the block (CH_P for the 128 x 128 kernels, 64 for the batched 64 x 64 blocks)
+// NA = 16-row groups of the largest trailing block (8 for 128 x 128, 4 for 64 x 64: a quarter of the accumulators)
+template <int PITCH = CH_P, int NA = 8>
 __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb, double dbound,
                                                  int* __restrict__ info, int col_base) {
     const int tid = threadIdx.x;
@@ -42,17 +45,17 @@ __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb
 #pragma unroll
                 for (int cc = 0; cc < W; ++cc)
 #pragma unroll
-                    for (int rr = cc; rr < W; ++rr) P[rr][cc] = S[(c0 + rr) + (c0 + cc) * CH_P];
+                    for (int rr = cc; rr < W; ++rr) P[rr][cc] = S[(c0 + rr) + (c0 + cc) * PITCH];
 #pragma unroll
-                for (int cc = 0; cc < W; ++cc) x[cc] = S[r + (c0 + cc) * CH_P];
+                for (int cc = 0; cc < W; ++cc) x[cc] = S[r + (c0 + cc) * PITCH];
             } else {
 #pragma unroll
                 for (int cc = 0; cc < W; ++cc)
 #pragma unroll
                     for (int rr = cc; rr < W; ++rr)
-                        P[rr][cc] = (rr < w && cc < w) ? S[(c0 + rr) + (c0 + cc) * CH_P] : (rr == cc ? 1.0 : 0.0);
+                        P[rr][cc] = (rr < w && cc < w) ? S[(c0 + rr) + (c0 + cc) * PITCH] : (rr == cc ? 1.0 : 0.0);
 #pragma unroll
-                for (int cc = 0; cc < W; ++cc) x[cc] = (cc < w) ? S[r + (c0 + cc) * CH_P] : 0.0;
+                for (int cc = 0; cc < W; ++cc) x[cc] = (cc < w) ? S[r + (c0 + cc) * PITCH] : 0.0;
             }
 #ifdef POTRF_PROFILE
             q1 = clock64();
@@ -96,7 +99,7 @@ __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb
             const int last = (tid < w) ? tid : w - 1;
 #pragma unroll
             for (int cc = 0; cc < W; ++cc)
-                if (cc <= last) S[r + (c0 + cc) * CH_P] = x[cc];
+                if (cc <= last) S[r + (c0 + cc) * PITCH] = x[cc];
             if (tid == 0) {
 #pragma unroll
                 for (int cc = 0; cc < W; ++cc)
@@ -121,27 +124,27 @@ __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb
         // products land in accumulators that are never stored).
         {
             const int ti = tid & 15, tj = tid >> 4;
-            double acc[8][8];
+            double acc[NA][NA];
 #pragma unroll
-            for (int a_ = 0; a_ < 8; ++a_)
+            for (int a_ = 0; a_ < NA; ++a_)
 #pragma unroll
-                for (int b_ = 0; b_ < 8; ++b_) acc[a_][b_] = 0.0;
-            const double* colbase = S + c0 * CH_P + base;
+                for (int b_ = 0; b_ < NA; ++b_) acc[a_][b_] = 0.0;
+            const double* colbase = S + c0 * PITCH + base;
             const int na = (T + 15) >> 4;  // 16-row groups in the trailing block (uniform)
             if (w == W) {
 #pragma unroll
                 for (int p = 0; p < W; ++p) {
-                    const double* col = colbase + p * CH_P;
-                    double xi[8], xj[8];
+                    const double* col = colbase + p * PITCH;
+                    double xi[NA], xj[NA];
 #pragma unroll
-                    for (int a_ = 0; a_ < 8; ++a_) {
+                    for (int a_ = 0; a_ < NA; ++a_) {
                         if (a_ < na) {
                             xi[a_] = col[ti + 16 * a_];
                             xj[a_] = col[tj + 16 * a_];
                         }
                     }
 #pragma unroll
-                    for (int a_ = 0; a_ < 8; ++a_) {
+                    for (int a_ = 0; a_ < NA; ++a_) {
                         if (a_ < na) {
 #pragma unroll
                             for (int b_ = 0; b_ <= a_; ++b_)
@@ -151,9 +154,9 @@ __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb
                 }
             } else {
                 for (int p = 0; p < w; ++p) {
-                    const double* col = colbase + p * CH_P;
+                    const double* col = colbase + p * PITCH;
 #pragma unroll
-                    for (int a_ = 0; a_ < 8; ++a_) {
+                    for (int a_ = 0; a_ < NA; ++a_) {
                         if (a_ < na) {
                             const double xa = col[ti + 16 * a_];
 #pragma unroll
@@ -164,12 +167,12 @@ __device__ __forceinline__ void potrf_block_smem(double* S, double* dinv, int jb
                 }
             }
 #pragma unroll
-            for (int a_ = 0; a_ < 8; ++a_) {
+            for (int a_ = 0; a_ < NA; ++a_) {
                 if (a_ < na) {
 #pragma unroll
                     for (int b_ = 0; b_ <= a_; ++b_) {
                         const int i = ti + 16 * a_, j = tj + 16 * b_;
-                        if (i < T && j <= i) S[(base + i) + (base + j) * CH_P] -= acc[a_][b_];
+                        if (i < T && j <= i) S[(base + i) + (base + j) * PITCH] -= acc[a_][b_];
                     }
                 }
             }
