@@ -301,7 +301,7 @@ static int batch_factor(nes_ctx* c, nes_batch* bt) {
     StageTimer t(c, NES_STAGE_FACTOR);
     NES_CUDA(c, cudaMemsetAsync(bt->d_info, 0, 2 * B * sizeof(int), c->stream));
     // 128-column panels by default; NES_BATCH_PANEL64=1 selects the 64 x 64 block kernels above (measured: not faster)
-    static const bool wide = getenv("NES_BATCH_PANEL64") == nullptr;
+    const bool wide = getenv("NES_BATCH_PANEL64") == nullptr;
     const int nb = wide ? 128 : B64;
     for (int i0 = 0; i0 < m; i0 += nb) {
         const int ib = (m - i0 < nb) ? m - i0 : nb;

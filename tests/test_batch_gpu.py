@@ -30,6 +30,30 @@ def test_batched_normal_solve_matches_oracle(common, B, m, n):
     bt.free()
 
 
+@pytest.mark.parametrize("B,m,n", [(1, 5, 9), (5, 40, 100), (3, 256, 512), (4, 200, 300), (2, 300, 400), (3, 64, 70)])
+def test_batched_64_column_panels_opt_in_path(common, monkeypatch, B, m, n):
+    """NES_BATCH_PANEL64: the 64 x 64 block potrf / trsm kernels (measured slower, kept opt-in): same gates,
+    and the failing column of a singular problem is still reported per problem."""
+    monkeypatch.setenv("NES_BATCH_PANEL64", "1")
+    rng = np.random.default_rng(B * 77 + m)
+    A = rng.random((B, m, n)) + np.eye(m, n)[None]
+    s = np.sqrt(0.1 + 10 * rng.random((B, n)))
+    rhs = rng.random((B, m))
+    bt = batched.Batch(A)
+    x, status = bt.normal_solve(s, rhs)
+    assert not status.any()
+    for b in range(B):
+        M = ons.normal_matrix(A[b], s[b])
+        assert np.linalg.norm(M @ x[b] - rhs[b]) / np.linalg.norm(rhs[b]) <= 1e-10
+    bt.free()
+    if m >= 20:
+        A[B - 1, 7, :] = A[B - 1, 6, :]
+        bt = batched.Batch(A)
+        _, status = bt.normal_solve(None, rhs)
+        assert status.tolist() == [0] * (B - 1) + [1]
+        bt.free()
+
+
 def test_batched_failure_is_per_problem(common):
     rng = np.random.default_rng(1)
     A = rng.random((3, 20, 30)) + np.eye(20, 30)[None]
