@@ -36,6 +36,9 @@ __device__ __forceinline__ bool n64_item(const NtArgs& p, int item, int& bi, int
 __global__ void __launch_bounds__(N64_THREADS, 2)
 dmma_nt64_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                  const NtArgs p) {
+    // generic addressing of the staging buffers, as in dmma_nt_kernel (a shared-typed pointer -- LDS -- was
+    // tried: 366 instead of 354 ms per factorization at m = 32768, and the lost-update defect described in
+    // DESIGN.md section 5 became rarer, 1 in 5 runs instead of every run, but did not go away)
     extern __shared__ uint8_t smem_raw64[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(
         (reinterpret_cast<uintptr_t>(smem_raw64) + 127) & ~static_cast<uintptr_t>(127));

@@ -47,11 +47,13 @@ def test_batched_64_column_panels_opt_in_path(common, monkeypatch, B, m, n):
         assert np.linalg.norm(M @ x[b] - rhs[b]) / np.linalg.norm(rhs[b]) <= 1e-10
     bt.free()
     if m >= 20:
-        A[B - 1, 7, :] = A[B - 1, 6, :]
+        A[B - 1, 7, :] = 0.0                  # a zero row: pivot 7 of the last problem is exactly 0
         bt = batched.Batch(A)
-        _, status = bt.normal_solve(None, rhs)
+        try:
+            _, status = bt.normal_solve(None, rhs)
+        finally:
+            bt.free()
         assert status.tolist() == [0] * (B - 1) + [1]
-        bt.free()
 
 
 def test_batched_failure_is_per_problem(common):
