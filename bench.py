@@ -581,7 +581,10 @@ def main():
                         c2["lp_solve"]["cpu_seconds"] = d2["lp_solve"]["iterations"] * ms2 * 1e-3
                         c2["lp_solve"]["cpu_seconds_how"] = (
                             f"estimated: {d2['lp_solve']['iterations']} iterations x {ms2:.0f} ms per restated CPU step "
-                            f"on {cb2['cores']} cores (a whole CPU solve was run once: profiles/r02_cpu_whole_solve_config2.log)")
+                            f"on {cb2['cores']} cores, the lean BLAS formulation of oracle/baseline.py; the plain oracle "
+                            "(which keeps the reference's temporaries) was run once on a 16-core GPU-box host: 95 iterations "
+                            "in 788.9 s = 8.3 s per iteration, same dobj as the golden fixture "
+                            "(profiles/r02_cpu_whole_solve_config2.log)")
                 line["config2"] = c2
                 line["config4"] = run_sparse(c, max(K, 10), W, with_cpu)
                 line["config5"] = run_batched(c, max(K, 10), W, with_cpu)

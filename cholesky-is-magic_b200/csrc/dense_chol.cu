@@ -673,13 +673,13 @@ static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L, CholTrace& tr) {
             double* stage = pl.d_stage[gi % DistPlan::kStages];
             const size_t count = (size_t)d.rows * pn.jbo + (d.has_diag ? pn.jbo : 0);
             if (d.root == me) {
-                cudaStream_t st = d.has_diag ? S0 : S3;
+                cudaStream_t st = d.urgent ? S0 : S3;
                 int t = -1;
                 if (J > 0) {
                     const DistPanel& pv = pl.panels[J - 1];
                     if (d.dep >= 0) NES_CUDA(c, cudaStreamWaitEvent(st, pl.ev_arrived[pl.msg_base[J - 1] + d.dep], 0));
                     if (J >= 2) NES_CUDA(c, cudaStreamWaitEvent(st, pl.ev_colready[J], 0));
-                    t = tr.open(d.has_diag ? "upd0" : "upd", pn.j0, st);
+                    t = tr.open(d.urgent ? "upd0" : "upd", pn.j0, st);
                     NES_TRY(dist_update(c, L, pv.j0, pv.jbo, d.seg[0], d.seg[tpb], st, true));
                     tr.close(t, st);
                 }

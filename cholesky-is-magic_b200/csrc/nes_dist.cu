@@ -98,8 +98,22 @@ int dist_chunk_rows(int m, int nbo, int P) {
     return r;
 }
 
+// Leading single-block messages of a panel on a 1 x Q grid: block row J (the diagonal block) and block row J+1
+// travel on their own, ahead of the row chunks.  The diagonal block of panel J+1 needs nothing else from panel
+// J, so the latency chain  potrf(J) -> trsm of block row J+1 -> update + potrf(J+1)  no longer waits for a whole
+// chunk to be updated, solved, packed and sent.  NES_DIST_HEAD overrides (0 = the chunks only).
+int dist_head_blocks(int nranks) {
+    if (const char* e = getenv("NES_DIST_HEAD")) {
+        const int v = atoi(e);
+        if (v >= 0 && v <= 4) return v;
+    }
+    (void)nranks;
+    return 0;
+}
+
 // Message schedule + this rank's tile list.  Host only (checked without a GPU through nes_dist_plan_grid).
-int dist_make_plan(DistPlan& pl, int m, int nbo, int P, int Q, int rank, int chunk_rows) {
+int dist_make_plan(DistPlan& pl, int m, int nbo, int P, int Q, int rank, int chunk_rows, int head_blocks) {
+    if (head_blocks < 0) head_blocks = dist_head_blocks(P * Q);
     pl = DistPlan();
     pl.m = m; pl.nbo = nbo; pl.P = P; pl.Q = Q; pl.rank = rank; pl.chunk = chunk_rows;
     pl.tpb = nbo / 128;
@@ -118,6 +132,7 @@ int dist_make_plan(DistPlan& pl, int m, int nbo, int P, int Q, int rank, int chu
             DistMsg d;
             d.root = pJ * Q + pn.group_q;
             d.has_diag = 1;
+            d.urgent = 1;
             d.row_start = pn.j0;
             d.nblocks = 1;
             d.bh = nbo;
@@ -125,13 +140,29 @@ int dist_make_plan(DistPlan& pl, int m, int nbo, int P, int Q, int rank, int chu
             d.rows = nbo;
             pn.msgs.push_back(d);
         }
-        const int c_first = pn.j0 / chunk_rows, c_last = (m - 1) / chunk_rows;
-        for (int ck = c_first; ck <= c_last; ++ck) {
-            const int r_lo = std::max(pn.j0, ck * chunk_rows), r_hi = std::min(m, (ck + 1) * chunk_rows);
+        int body0 = pn.j0;  // first row of the chunked part
+        if (P == 1)
+            for (int hb = 0; hb < head_blocks && body0 < m; ++hb) {
+                DistMsg d;
+                d.root = pn.group_q;
+                d.has_diag = (hb == 0);
+                d.urgent = 1;
+                d.row_start = body0;
+                d.nblocks = 1;
+                d.bh = nbo;
+                d.stride = 0;
+                d.rows = nbo;
+                pn.msgs.push_back(d);
+                body0 += nbo;
+            }
+        const int c_first = body0 / chunk_rows, c_last = (m - 1) / chunk_rows;
+        for (int ck = c_first; ck <= c_last && body0 < m; ++ck) {
+            const int r_lo = std::max(body0, ck * chunk_rows), r_hi = std::min(m, (ck + 1) * chunk_rows);
             if (P == 1) {
                 DistMsg d;
                 d.root = pn.group_q;
                 d.has_diag = (r_lo == pn.j0);
+                d.urgent = d.has_diag;
                 d.row_start = r_lo;
                 d.nblocks = 1;
                 d.bh = (r_hi - r_lo + 63) / 64 * 64;

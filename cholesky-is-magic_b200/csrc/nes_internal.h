@@ -252,6 +252,7 @@ int dense_trsv_sweeps(nes_ctx* c, const double* M, long long ld, int m, const do
 struct DistMsg {
     int root = 0;         // world rank that computes and sends it
     int has_diag = 0;     // contains the diagonal block (+ the panel's dinv rides at the end of the message)
+    int urgent = 0;       // on the panel chain: its root works on the main (high-priority) stream
     int row_start = 0;    // first row of the first block
     int nblocks = 1;      // blocks of `bh` rows, `stride` rows apart (P x Q: the root's block rows of one chunk)
     int bh = 0, stride = 0;
@@ -280,7 +281,8 @@ struct DistPlan {
     std::vector<int> msg_base;            // global index of panel J's first message
     cudaEvent_t ev_start = nullptr, ev_end[3] = {nullptr, nullptr, nullptr};
 };
-int dist_make_plan(DistPlan& plan, int m, int nbo, int P, int Q, int rank, int chunk_rows);
+int dist_make_plan(DistPlan& plan, int m, int nbo, int P, int Q, int rank, int chunk_rows, int head_blocks = -1);
+int dist_head_blocks(int nranks);
 void dist_free_plan(nes_ctx* c, DistPlan* plan);
 int dist_chunk_rows(int m, int nbo, int P);
 int dist_broadcast(nes_ctx* c, double* d_buf, size_t count, int root, cudaStream_t stream = nullptr);

@@ -167,7 +167,9 @@ def main():
                 assert max(counts) - min(counts) <= 0.02 * max(counts), counts
         # P x Q grids (planned for any rank count on the host): every tile of tril(M) exactly once, every
         # broadcast has exactly one root, for several distribution blocks / chunk sizes
-        for (P, Q) in ((1, 2), (2, 1), (2, 2), (1, 8), (2, 4), (4, 2), (3, 2)):
+        for (P, Q, head) in ((1, 2, 0), (2, 1, 0), (2, 2, 0), (1, 8, 0), (2, 4, 0), (4, 2, 0), (3, 2, 0), (1, 2, 2), (1, 8, 2),
+                             (1, 4, 1), (1, 8, 3)):
+            os.environ["NES_DIST_HEAD"] = str(head)       # leading single-block messages of a panel (1 x Q grids)
             for (m, nbo, chunk) in ((200, 128, 0), (1153, 256, 512 * P), (5000, 256, 1024 * P), (8192, 512, 0),
                                     (32768, 256, 0)):
                 if m == 32768 and rank != 0:
@@ -185,6 +187,7 @@ def main():
                 tm = (m + 127) // 128
                 assert len(seen) == tm * (tm + 1) // 2, (P, Q, m, nbo)
                 assert nroot_sum == nm0 > 0
+        os.environ.pop("NES_DIST_HEAD", None)
         cpu_sparse_and_batch(rank, world)
         dist.destroy_process_group()
         print(f"rank {rank}: cpu dist ok")
@@ -209,9 +212,11 @@ def main():
         grids = [(p, world // p) for p in range(1, world + 1) if world % p == 0]
         for (P, Q) in grids:
             c.check(c.lib.nes_dist_set_grid(c.ptr, P, Q), "nes_dist_set_grid")
-            for (m, n, nbo, chunk) in ((700, 900, 128, 128 * P), (1153, 1400, 256, 256 * P), (2600, 3000, 256, 512 * P),
-                                       (2600, 3000, 512, 0), (4100, 4500, 128, 1024 * P)):
+            for (m, n, nbo, chunk, head) in ((700, 900, 128, 128 * P, 0), (1153, 1400, 256, 256 * P, 2),
+                                             (2600, 3000, 256, 512 * P, 0), (2600, 3000, 512, 0, 2),
+                                             (4100, 4500, 128, 1024 * P, 2), (4100, 4500, 256, 2048 * P, 1)):
                 os.environ["NES_DIST_NBO"] = str(nbo)
+                os.environ["NES_DIST_HEAD"] = str(head)
                 os.environ["NES_DIST_CHUNK"] = str(chunk) if chunk else "8192"
                 Ad = nes.Matrix.generate_dense(c, m, n, 3)
                 Ad.scale(np.sqrt(0.1 + 10 * rng.random(n)))
@@ -233,6 +238,7 @@ def main():
                 Ad.free()
         os.environ.pop("NES_DIST_NBO", None)
         os.environ.pop("NES_DIST_CHUNK", None)
+        os.environ.pop("NES_DIST_HEAD", None)
         # config-2 size on the default and the squarest grid
         for (P, Q) in {grids[0], grids[len(grids) // 2]}:
             c.check(c.lib.nes_dist_set_grid(c.ptr, P, Q), "nes_dist_set_grid")
