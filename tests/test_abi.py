@@ -66,3 +66,74 @@ def test_no_cpu_fallback():
     assert not lib.nes_generate_dense(4, 4, 0, c)
     assert lib.nes_get_status(c) == nes.NES_ERR_NO_DEVICE
     lib.nes_release(c)
+
+
+def _c_prototypes():
+    """name -> number of parameters, from include/nes.h (accessor macro expanded)."""
+    text = open(os.path.join(ROOT, "include", "nes.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    protos = {}
+    for name, args in re.findall(r"\b(nes_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", text):
+        args = args.strip()
+        protos[name] = 0 if args in ("", "void") else args.count(",") + 1
+    for field in re.findall(r"NES_DECLARE_ACCESSOR\((\w+),", text):
+        if field != "FIELD":
+            protos["nes_get_" + field] = 1
+            protos["nes_set_" + field] = 2
+    return protos
+
+
+def test_lisp_glue_binds_only_exported_symbols_with_the_right_arity():
+    """lisp/nes-glue.lisp cannot be executed here (no Common Lisp in the image), but every C name it binds with
+    define-alien-routine must exist in libnes.so and take as many arguments as include/nes.h declares."""
+    src = open(os.path.join(ROOT, "lisp", "nes-glue.lisp")).read()
+    src = re.sub(r";[^\n]*", "", src)                         # strip comments
+    lib = ctypes.CDLL(nes.LIB_PATH)
+    protos = _c_prototypes()
+    bound = {}
+    for m in re.finditer(r'\(define-alien-routine\s+\("(nes_[a-z0-9_]+)"\s+[^)]+\)', src):
+        # the form continues until its parentheses balance: return type, then one (name type) list per argument
+        i, depth = m.start(), 0
+        while True:
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+            if depth == 0:
+                break
+        body = src[m.end():i - 1].strip()
+        # drop the return type: either a symbol or one parenthesised form
+        if body.startswith("("):
+            d, j = 0, 0
+            while True:
+                d += {"(": 1, ")": -1}.get(body[j], 0)
+                j += 1
+                if d == 0:
+                    break
+            rest = body[j:]
+        else:
+            rest = body.split(None, 1)[1] if len(body.split(None, 1)) > 1 else ""
+        nargs, d = 0, 0
+        for ch in rest:
+            if ch == "(":
+                if d == 0:
+                    nargs += 1
+                d += 1
+            elif ch == ")":
+                d -= 1
+        bound[m.group(1)] = nargs
+    # the accessor macro binds nes_get_/nes_set_ for the 19 fields through format strings
+    for field in re.findall(r'\(def #:[a-z-]+ "([a-z_]+)"', src):
+        bound["nes_get_" + field] = 1
+        bound["nes_set_" + field] = 2
+    assert len(bound) >= 19 * 2 + 15
+    for name, nargs in bound.items():
+        assert hasattr(lib, name), f"{name} bound in nes-glue.lisp but not exported"
+        assert name in protos, f"{name} not declared in include/nes.h"
+        assert protos[name] == nargs, f"{name}: glue passes {nargs} arguments, nes.h declares {protos[name]}"
+    # the names the other Lisp files of the reference call are all defined by the glue
+    for lisp_name in ("with-cholmod", "make-sparse-from-triplet-vector", "scale-sparse!", "scale-sparse", "solve-sparse",
+                      "solve-sparse-one-shot", "solve-sparse-recycle", "free-sparse-state", "solve-dense", "sparse-m*",
+                      "cholmod-copy-sparse", "cholmod-free-sparse", "cholmod-analyze", "cholmod-free-work",
+                      "cholmod-get-status", "cholmod-get-anz", "make-solve-sparse-state", "affine-A-copy", "flush"):
+        target = lisp_name.replace("make-solve-sparse-state", "defstruct solve-sparse-state")
+        assert (f"(defun {lisp_name} " in src or f"(defmacro {lisp_name} " in src or f" {lisp_name})" in src
+                or target in src or "#:" + lisp_name.replace("cholmod-get-", "") in src), lisp_name
