@@ -430,4 +430,28 @@ int nes_dist_plan_grid(int m, int nbo, int P, int Q, int rank, int chunk_rows, i
     return n;
 }
 
+// The message schedule itself (host only): for every broadcast of the factorization, in order, 8 ints
+// { panel J, root, has_diag, row_start, nblocks, bh, stride, dep } (dep = index, within panel J-1, of the last
+// message the root needs before it may update these rows; -1 = none).  Returns the number of messages; fills up
+// to `cap` of them.  tests/dist_worker.py replays the schedule in NumPy over gloo with it.
+int nes_dist_plan_msgs(int m, int nbo, int P, int Q, int chunk_rows, int head_blocks, int* out, int cap) {
+    if (m <= 0 || P < 1 || Q < 1) return NES_ERR_INVALID;
+    if (nbo <= 0) nbo = dense_outer_block(m, P * Q);
+    if (chunk_rows <= 0) chunk_rows = dist_chunk_rows(m, nbo, P);
+    if (chunk_rows % (P * nbo) != 0) return NES_ERR_INVALID;
+    DistPlan pl;
+    dist_make_plan(pl, m, nbo, P, Q, 0, chunk_rows, head_blocks);
+    int n = 0;
+    for (int J = 0; J < pl.nblk; ++J)
+        for (const DistMsg& d : pl.panels[J].msgs) {
+            if (out && n < cap) {
+                int* o = out + 8 * n;
+                o[0] = J; o[1] = d.root; o[2] = d.has_diag; o[3] = d.row_start;
+                o[4] = d.nblocks; o[5] = d.bh; o[6] = d.stride; o[7] = d.dep;
+            }
+            ++n;
+        }
+    return n;
+}
+
 }  // extern "C"

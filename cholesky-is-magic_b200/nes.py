@@ -125,6 +125,7 @@ def _prototypes(lib):
     fn("nes_comm_nranks", C.c_int, _vp)
     fn("nes_dist_plan", C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int)
     fn("nes_dist_plan_grid", C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, _ip, C.c_int, _ip, _ip)
+    fn("nes_dist_plan_msgs", C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _ip, C.c_int)
     fn("nes_dist_set_grid", C.c_int, _vp, C.c_int, C.c_int)
     fn("nes_dist_layout", C.c_int, _vp, C.c_int, _ip, _ip, _ip)
     fn("nes_mark_begin", C.c_int, _vp)
@@ -226,6 +227,18 @@ def dist_plan_grid(m, P, Q, rank, nbo=0, chunk_rows=0):
     lib.nes_dist_plan_grid(m, nbo, P, Q, rank, chunk_rows, rows.ctypes.data_as(_ip), cols.ctypes.data_as(_ip), n,
                            C.byref(nm), C.byref(nr))
     return np.stack([rows[:n], cols[:n]], axis=1), nm.value, nr.value
+
+
+def dist_plan_msgs(m, P, Q, nbo=0, chunk_rows=0, head_blocks=-1):
+    """The broadcasts of a distributed factorization in order, as dicts (host-only planner)."""
+    lib = load_library()
+    n = lib.nes_dist_plan_msgs(m, nbo, P, Q, chunk_rows, head_blocks, None, 0)
+    if n < 0:
+        raise NesError("nes_dist_plan_msgs: bad arguments")
+    buf = np.zeros(8 * max(n, 1), dtype=np.int32)
+    lib.nes_dist_plan_msgs(m, nbo, P, Q, chunk_rows, head_blocks, buf.ctypes.data_as(_ip), n)
+    keys = ("panel", "root", "has_diag", "row_start", "nblocks", "bh", "stride", "dep")
+    return [dict(zip(keys, map(int, buf[8 * i: 8 * i + 8]))) for i in range(n)]
 
 
 def vec(a):

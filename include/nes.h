@@ -254,6 +254,10 @@ int nes_dist_plan(int m, int nranks, int rank, int* tile_rows, int* tile_cols, i
  * chunk_rows rows (0 = default); *nmsgs = broadcasts per factorization, *nroot = those rooted at `rank` */
 int nes_dist_plan_grid(int m, int nbo, int P, int Q, int rank, int chunk_rows, int* tile_rows, int* tile_cols,
                        int cap, int* nmsgs, int* nroot);
+/* host-only: the broadcasts of the factorization in order, 8 ints each { panel, root, has_diag, row_start, nblocks,
+ * bh, stride, dep }: a message is `nblocks` blocks of `bh` rows, `stride` rows apart, of block column `panel`;
+ * head_blocks < 0 = default.  Returns the count, fills up to `cap`. */
+int nes_dist_plan_msgs(int m, int nbo, int P, int Q, int chunk_rows, int head_blocks, int* out, int cap);
 /* choose the P x Q grid (P*Q = nranks; same call on every rank, before nes_analyze of the factors that use it) */
 int nes_dist_set_grid(nes_ctx* c, int P, int Q);
 /* distribution block and P x Q process grid the dense factorization of an m x m matrix uses on c's ranks */

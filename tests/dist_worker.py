@@ -91,6 +91,91 @@ def cpu_sparse_and_batch(rank, world):
     assert np.array_equal(got[0], np.arange(10.0)) and np.array_equal(got[1], np.arange(10) * 2)
 
 
+def cpu_dense_schedule(rank, world):
+    """The distributed dense Cholesky replayed in NumPy over gloo, message by message, from the planner's own
+    schedule (nes.dist_plan_msgs) and ownership (nes.dist_plan_grid): every rank starts with its owned tiles of
+    M only, a message's root updates its rows with the previous panel -- asserting that everything it reads has
+    arrived in a message no later than the planned dependency --, solves them, broadcasts them (the same
+    collective order on every rank), and the trailing update touches owned tiles of block columns >= J+2 only.
+    At the end every rank must hold the complete factor."""
+    rng = np.random.default_rng(3)
+    for (P, Q, m, nbo, chunk, head) in ((1, 2, 1153, 256, 512, 0), (1, 2, 1153, 256, 512, 2), (2, 1, 1153, 256, 512, 0),
+                                        (1, 2, 700, 128, 256, 1), (2, 1, 900, 128, 256, 0)):
+        if P * Q != world:
+            continue
+        os.environ["NES_DIST_HEAD"] = str(head)
+        n = m + 50
+        A = rng.random((m, n)) + np.eye(m, n)
+        M = A @ A.T
+        want = np.linalg.cholesky(M)
+        tiles, _, _ = nes.dist_plan_grid(m, P, Q, rank, nbo, chunk)
+        msgs = nes.dist_plan_msgs(m, P, Q, nbo, chunk, head)
+        nblk = (m + nbo - 1) // nbo
+        W = np.zeros((m, m))                       # this rank's copy: owned tiles of tril(M), the rest unknown (0)
+        for bi, bj in tiles:
+            r, c_ = slice(bi * 128, min(m, bi * 128 + 128)), slice(bj * 128, min(m, bj * 128 + 128))
+            W[r, c_] = M[r, c_]
+        by_col = {}
+        for bi, bj in tiles:
+            by_col.setdefault(bj * 128 // nbo, []).append((int(bi), int(bj)))
+        arrived = [np.full(m, -1) for _ in range(nblk)]   # arrived[J][row] = index of the message that brought it
+
+        def rows_of(d):
+            out = []
+            for b in range(d["nblocks"]):
+                lo = d["row_start"] + b * d["stride"]
+                out.append((lo, min(m, lo + d["bh"])))
+            return [(lo, hi) for lo, hi in out if lo < hi]
+
+        def apply(J, K, tile_list, dep=None):
+            """owned tiles of block column J -= panel K rows x (their columns' rows of panel K)'"""
+            kc = slice(K * nbo, min(m, (K + 1) * nbo))
+            for bi, bj in tile_list:
+                r, c_ = slice(bi * 128, min(m, bi * 128 + 128)), slice(bj * 128, min(m, bj * 128 + 128))
+                need = np.concatenate([arrived[K][r], arrived[K][c_]])
+                assert (need >= 0).all(), (J, K, bi, bj, "reads rows of a panel that have not arrived")
+                if dep is not None:
+                    assert need.max() <= dep, (J, K, bi, bj, need.max(), dep)
+                W[r, c_] -= W[r, kc] @ W[c_, kc].T
+
+        per_panel = {}
+        for d in msgs:
+            per_panel.setdefault(d["panel"], []).append(d)
+        for J in range(nblk):
+            j0, j1 = J * nbo, min(m, (J + 1) * nbo)
+            for k, d in enumerate(per_panel[J]):
+                rows = rows_of(d)
+                nrows = sum(hi - lo for lo, hi in rows)
+                buf = torch.zeros(nrows * (j1 - j0), dtype=torch.float64)
+                if d["root"] == rank:
+                    mine = [(bi, bj) for bi, bj in by_col.get(J, []) if any(lo <= bi * 128 < hi for lo, hi in rows)]
+                    if J > 0:
+                        apply(J, J - 1, mine, dep=d["dep"])
+                    if d["has_diag"]:
+                        W[j0:j1, j0:j1] = np.linalg.cholesky(np.tril(W[j0:j1, j0:j1]) + np.tril(W[j0:j1, j0:j1], -1).T)
+                    else:
+                        assert (arrived[J][j0:j1] >= 0).all(), "the diagonal block has not arrived"
+                    Ljj = np.tril(W[j0:j1, j0:j1])
+                    for lo, hi in rows:
+                        lo2 = max(lo, j1)
+                        if lo2 < hi:
+                            W[lo2:hi, j0:j1] = np.linalg.solve(Ljj, W[lo2:hi, j0:j1].T).T
+                    buf = torch.from_numpy(np.concatenate([W[lo:hi, j0:j1] for lo, hi in rows]).ravel().copy())
+                dist.broadcast(buf, d["root"])
+                got = buf.numpy().reshape(nrows, j1 - j0)
+                off = 0
+                for lo, hi in rows:
+                    W[lo:hi, j0:j1] = got[off:off + hi - lo]
+                    arrived[J][lo:hi] = k
+                    off += hi - lo
+            assert (arrived[J][j0:] >= 0).all(), "the messages of a panel must cover every row below its diagonal"
+            for C_ in range(J + 2, nblk):         # trailing update: owned tiles of block columns >= J+2
+                apply(C_, J, by_col.get(C_, []))
+        L = np.tril(W)
+        assert np.linalg.norm(L - want) <= 1e-11 * np.linalg.norm(want), (P, Q, m, nbo, chunk, head)
+    os.environ.pop("NES_DIST_HEAD", None)
+
+
 def gpu_sparse_and_batch(c, rank, world):
     """Sparse multifrontal path with subtrees sharded over the ranks, and the batch split (nccl)."""
     import scipy.sparse as sp
@@ -188,6 +273,7 @@ def main():
                 assert len(seen) == tm * (tm + 1) // 2, (P, Q, m, nbo)
                 assert nroot_sum == nm0 > 0
         os.environ.pop("NES_DIST_HEAD", None)
+        cpu_dense_schedule(rank, world)
         cpu_sparse_and_batch(rank, world)
         dist.destroy_process_group()
         print(f"rank {rank}: cpu dist ok")
