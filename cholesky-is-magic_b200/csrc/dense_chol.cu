@@ -653,6 +653,8 @@ static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L, CholTrace& tr) {
     NES_TRY(dist_setup(c, L));
     DistPlan& pl = *L->dist;
     const int nblk = pl.nblk, me = c->rank, P = pl.P, tpb = pl.tpb;
+    // NES_DIST_PAIR=1: trailing updates of two consecutive panels applied together (K = 2 nbo), see below
+    const bool pair = getenv("NES_DIST_PAIR") && atoi(getenv("NES_DIST_PAIR")) != 0;
     cudaStream_t S0 = c->stream, S1 = c->stream_aux, S2 = c->stream_b, S3 = c->stream_c;
     if (const char* e = getenv("NES_DIST_SERIAL")) {  // debugging: merge streams into the main one (bit 0: trailing
         const int v = atoi(e);                        // updates, bit 1: communication, bit 2: bulk pieces; 1 = all)
@@ -714,7 +716,21 @@ static int dense_cholesky_dist_steps(nes_ctx* c, nes_factor* L, CholTrace& tr) {
             int t = tr.open("rest", pn.j0, S1);
             NES_TRY(dist_update(c, L, pn.j0, pn.jbo, p2.col_begin, p2.col_end, S1, true));
             NES_CUDA(c, cudaEventRecord(pl.ev_colready[J + 2], S1));
-            NES_TRY(dist_update(c, L, pn.j0, pn.jbo, p2.col_end, L->ntiles_owned, S1, true));
+            if (!pair) {
+                NES_TRY(dist_update(c, L, pn.j0, pn.jbo, p2.col_end, L->ntiles_owned, S1, true));
+            } else if ((J & 1) == 0) {
+                // paired updates: an even panel only reaches the next TWO block columns on its own ...
+                if (J + 3 < nblk) {
+                    const DistPanel& p3 = pl.panels[J + 3];
+                    NES_TRY(dist_update(c, L, pn.j0, pn.jbo, p3.col_begin, p3.col_end, S1, true));
+                }
+            } else {
+                // ... and travels on with its odd successor: one update with K = two panels (contiguous columns)
+                // for everything from block column J+3 on -- half the passes over the trailing matrix, and
+                // the tile's read-modify-write epilogue amortised over twice the tensor work
+                const DistPanel& pv = pl.panels[J - 1];
+                NES_TRY(dist_update(c, L, pv.j0, pv.jbo + pn.jbo, p2.col_end, L->ntiles_owned, S1, true));
+            }
             tr.close(t, S1);
         }
     }

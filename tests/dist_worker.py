@@ -303,6 +303,7 @@ def main():
                                              (4100, 4500, 128, 1024 * P, 2), (4100, 4500, 256, 2048 * P, 1)):
                 os.environ["NES_DIST_NBO"] = str(nbo)
                 os.environ["NES_DIST_HEAD"] = str(head)
+                os.environ["NES_DIST_PAIR"] = "1" if (m // 100) % 2 else "0"   # paired trailing updates on half of them
                 os.environ["NES_DIST_CHUNK"] = str(chunk) if chunk else "8192"
                 Ad = nes.Matrix.generate_dense(c, m, n, 3)
                 Ad.scale(np.sqrt(0.1 + 10 * rng.random(n)))
@@ -325,6 +326,7 @@ def main():
         os.environ.pop("NES_DIST_NBO", None)
         os.environ.pop("NES_DIST_CHUNK", None)
         os.environ.pop("NES_DIST_HEAD", None)
+        os.environ["NES_DIST_PAIR"] = "1"
         # config-2 size on the default and the squarest grid
         for (P, Q) in {grids[0], grids[len(grids) // 2]}:
             c.check(c.lib.nes_dist_set_grid(c.ptr, P, Q), "nes_dist_set_grid")
@@ -337,6 +339,7 @@ def main():
             assert res <= 1e-12, (P, Q, m, res)
             L.free()
             Ad.free()
+        os.environ.pop("NES_DIST_PAIR", None)
         c.check(c.lib.nes_dist_set_grid(c.ptr, 1, world), "nes_dist_set_grid")
         for (m, n) in ((300, 700), (1000, 1500), (1153, 2000)):
             l, u, w, z, A, e, f, g, h = ons.random_dense_case(rng, m, n)

@@ -22,7 +22,7 @@ with with_cholmod(device=local, timing=True) as c:
         parts = cfg.split(":")
         grid, nbo, chunk = parts[:3]
         os.environ["NES_REST_TPC"] = parts[3] if len(parts) > 3 else "1"
-        for k, v in zip(("NES_DIST_HEAD", "NES_DIST_KERNEL_DEBUG", "NES_DIST_SERIAL"), parts[4:7]):
+        for k, v in zip(("NES_DIST_HEAD", "NES_DIST_PAIR", "NES_DIST_SERIAL"), parts[4:7]):
             if v and v != "-":
                 os.environ[k] = v
             else:
