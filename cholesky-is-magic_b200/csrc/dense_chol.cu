@@ -140,17 +140,32 @@ static int chol_configure(nes_ctx* c) {
 }
 
 // Outer panel width by remaining size R = m - j0 (see dense_cholesky): while the trailing matrix is large
-// the updates bound the step (wide panels: fewer passes over C, K = 512 / 256), once it is small the panel
-// chain does (128 columns: no inner narrow updates).  NES_CHOL_SCHED="t512,t256" overrides the thresholds.
+// the updates bound the step (wide panels: fewer passes over C, K = 1024 / 512 / 256: the tile's
+// read-modify-write epilogue is amortised over more tensor work), once it is small the panel chain does (128
+// columns: no inner narrow updates).  Measured at m = 32768: 368.0 ms with 512-column panels throughout the
+// large phase, 352.7 ms with 1024-column panels while R > 8192 (354.0 with R > 4096, 359.0 with R > 24576);
+// m = 16384: 50.5 -> 49.7 ms; m = 8192 is untouched (10.1 ms if 1024-column panels were used there).
 static int chol_width(int m, int j0) {
-    static int t512 = -1, t256 = -1;
+    static int t1024 = -1, t512 = -1, t256 = -1;
     if (t512 < 0) {
+        t1024 = 8192;  // NES_CHOL_SCHED = "t1024,t512,t256" (or the last two) overrides the thresholds
         t512 = 6144;
         t256 = 3072;
-        if (const char* e = getenv("NES_CHOL_SCHED")) sscanf(e, "%d,%d", &t512, &t256);
+        if (const char* e = getenv("NES_CHOL_SCHED")) {
+            int a = 0, b = 0, c3 = 0;
+            const int n = sscanf(e, "%d,%d,%d", &a, &b, &c3);
+            if (n == 3) {
+                t1024 = a;
+                t512 = b;
+                t256 = c3;
+            } else if (n == 2) {
+                t512 = a;
+                t256 = b;
+            }
+        }
     }
     const int R = m - j0;
-    const int w = R > t512 ? 512 : (R > t256 ? 256 : CH_NB);
+    const int w = R > t1024 ? 1024 : (R > t512 ? 512 : (R > t256 ? 256 : CH_NB));
     return R < w ? R : w;
 }
 
