@@ -304,6 +304,58 @@ static int defer_form_strip(nes_ctx* c, const nes_matrix* A, nes_factor* L, int 
     return 0;
 }
 
+// As = A diag(s): one column per blockIdx.x, rows strided over the block and blockIdx.y (ld is a multiple of 16)
+__global__ void __launch_bounds__(256)
+scale_columns_kernel(const double* __restrict__ A, const double* __restrict__ s, double* __restrict__ As,
+                     size_t ld) {
+    const size_t col = blockIdx.x;
+    const double sj = s[col];
+    const double2* src = reinterpret_cast<const double2*>(A + col * ld);
+    double2* dst = reinterpret_cast<double2*>(As + col * ld);
+    for (size_t i = blockIdx.y * (size_t)blockDim.x + threadIdx.x; i < ld / 2; i += (size_t)gridDim.y * blockDim.x) {
+        double2 v = src[i];
+        v.x *= sj;
+        v.y *= sj;
+        dst[i] = v;
+    }
+}
+
+// Formation operand.  The fused kernel multiplies theta into the B fragment in registers (4 DMUL per 32 DMMA
+// and lane): measured 3.4% slower than the same kernel without a scale (34.7 vs 35.9 TFLOP/s at m = 16384,
+// 34.5 vs 35.7 at m = 8192; tools/probe_unscaled_formation.py) -- DMUL shares the FP64 datapath with DMMA.
+// One elementwise pass As = A diag(s) costs 16 m n bytes of HBM traffic (5.3 ms at m = 32768, n = 65536
+// against 66 ms saved) and a second buffer the size of A; M = As As' is then literally the reference's
+// formulation (scale-sparse! followed by the factorization of B B', sparse-cholesky.lisp:461-473, :408).
+// Default: pre-scaled; NES_FORM_FUSED=1, or an allocation that fails, falls back to the fused kernel.
+static int form_prescale(nes_ctx* c, const nes_matrix* A, nes_factor* L, bool* use) {
+    *use = false;
+    const MatrixBase* b = A->base;
+    if (!A->d_scale || getenv("NES_FORM_FUSED") || L->defer_split > 0) return 0;
+    if (!L->d_As || L->As_ld != b->ld || L->As_n != b->n) {
+        cudaStreamSynchronize(c->stream);
+        dev_free(c, L->d_As);
+        L->d_As = nullptr;
+        const int saved_status = c->status;
+        L->d_As = static_cast<double*>(dev_alloc(c, b->ld * (b->n ? b->n : 1) * sizeof(double)));
+        if (!L->d_As) {  // no room for the copy: the fused kernel needs none
+            c->status = saved_status;
+            c->err[0] = 0;
+            cudaGetLastError();
+            return 0;
+        }
+        L->As_ld = b->ld;
+        L->As_n = b->n;
+        if (make_operand_map(&L->mapAs, L->d_As, (long long)b->m, (long long)b->n, (long long)b->ld) != 0)
+            return fail(c, NES_ERR_CUDA, "cuTensorMapEncodeTiled failed for the scaled copy of A");
+        // rows m..ld of A are zero and stay zero in the copy (the kernel scales whole columns)
+    }
+    const unsigned gy = (unsigned)std::max<size_t>(1, std::min<size_t>(8, (b->ld / 2 + 255) / 256));
+    scale_columns_kernel<<<dim3((unsigned)b->n, gy), 256, 0, c->stream>>>(b->d_val, A->d_scale, L->d_As, b->ld);
+    NES_CHECK_LAUNCH(c);
+    *use = true;
+    return 0;
+}
+
 int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L, bool allow_defer) {
     const MatrixBase* b = A->base;
     int split = 0;
@@ -312,6 +364,9 @@ int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L, bool allow
         split = L->defer_split;
     }
     StageTimer timer(c, NES_STAGE_FORM);
+    bool prescaled = false;
+    NES_TRY(form_prescale(c, A, L, &prescaled));
+    const CUtensorMap& opmap = prescaled ? L->mapAs : b->map;
     NtArgs a{};
     a.C = L->d_M;
     a.ldc = (long long)L->ld;
@@ -319,7 +374,7 @@ int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L, bool allow
     a.rowA0 = a.rowB0 = 0;
     a.k0 = 0;
     a.K = (int)b->n;
-    a.scale = A->d_theta;  // nullptr: unscaled A A'
+    a.scale = prescaled ? nullptr : A->d_theta;  // nullptr: plain X X'
     a.alpha = 1.0;
     a.beta = 0.0;
     a.lower = 1;
@@ -362,7 +417,7 @@ int dense_form_normal(nes_ctx* c, const nes_matrix* A, nes_factor* L, bool allow
             a.split_s = ss;
         }
     }
-    cudaError_t e = nt_launch(b->map, b->map, a, c->num_sms, c->stream);
+    cudaError_t e = nt_launch(opmap, opmap, a, c->num_sms, c->stream);
     ++c->launches;
     if (e != cudaSuccess)
         return fail(c, NES_ERR_CUDA, "formation kernel launch failed: %s", cudaGetErrorString(e));

@@ -68,7 +68,7 @@ static NcclApi* nccl_api() {
 int dense_outer_block(int m, int nranks) {
     if (const char* e = getenv("NES_DIST_NBO")) {
         const int v = atoi(e);
-        if (v == 128 || v == 256 || v == 512) return v;
+        if (v == 128 || v == 256 || v == 512 || v == 1024) return v;
     }
     if (m <= 12288) return 256;
     return nranks >= 8 ? 256 : 512;  // measured at m = 32768: N=2 206 vs 220 ms, N=4 127 vs 130 ms, N=8 98 vs 94 ms
@@ -410,7 +410,7 @@ int nes_dist_plan_grid(int m, int nbo, int P, int Q, int rank, int chunk_rows, i
                        int cap, int* nmsgs, int* nroot) {
     if (m <= 0 || P < 1 || Q < 1 || rank < 0 || rank >= P * Q) return NES_ERR_INVALID;
     if (nbo <= 0) nbo = dense_outer_block(m, P * Q);
-    if (nbo != 128 && nbo != 256 && nbo != 512) return NES_ERR_INVALID;
+    if (nbo != 128 && nbo != 256 && nbo != 512 && nbo != 1024) return NES_ERR_INVALID;
     if (chunk_rows <= 0) chunk_rows = dist_chunk_rows(m, nbo, P);
     if (chunk_rows % (P * nbo) != 0) return NES_ERR_INVALID;
     DistPlan pl;

@@ -171,6 +171,7 @@ static void nes_free_factor_impl(nes_factor* L, nes_ctx* c) {
     dev_free(c, L->d_info);
     dev_free(c, L->d_flags);
     dev_free(c, L->d_Winv);
+    dev_free(c, L->d_As);
     dev_free(c, L->d_tile_list);
     if (L->dist) {
         dist_free_plan(c, L->dist);

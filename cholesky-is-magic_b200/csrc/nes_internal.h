@@ -203,6 +203,11 @@ struct nes_factor {
     CUtensorMap mapSlab; // 64 x 128 slabs of a panel (TRSM)
     int factorized = 0;
     nes_matrix* analyzed_for = nullptr;
+    // pre-scaled operand of the formation: As = A diag(s), refreshed by one elementwise pass per factorization
+    // (dense_chol.cu: dense_form_normal); owned by the factor, which outlives the per-call matrix views
+    double* d_As = nullptr;
+    size_t As_ld = 0, As_n = 0;
+    CUtensorMap mapAs;
     // distributed factorization (nranks > 1): tiles of the lower triangle owned by this rank, ordered by
     // outer block column; tile_first[J] = index of the first owned tile whose block column is > J
     int nbo = 0;                 // distribution block = outer panel width
