@@ -3,7 +3,7 @@
 
 Main line, at EVERY N: BASELINE config 3, the dense LP m=32768, n=65536 the north star names (A 17.2 GB +
 M 8.6 GB fit one B200), so 1 -> 2 -> 4 -> 8 GPUs is strong scaling of one LP.  One "step" = one primal-dual
-affine scaling iteration: violation (2 GEMV), fused scale+SYRK formation, blocked DMMA Cholesky, two
+affine scaling iteration: violation (2 GEMV), scale + SYRK formation on FP64 DMMA, blocked DMMA Cholesky, two
 triangular solves, the fused forward GEMV and the transposed GEMV of solve-kkt-newton, the fused
 elementwise passes and the step-length reductions, apply-step.  Algorithmic flops per step
 F(m,n) = m^2 n + m^3/3 + 2 m^2 + 10 m n.
@@ -11,8 +11,9 @@ F(m,n) = m^2 n + m^3/3 + 2 m^2 + 10 m n.
   value     device-resident iterations (state on the GPU, scalars only cross PCIe)
   e2e       the reference-facing C-ABI call nes_kkt_newton with HOST (pinned) vectors: H2D of
             l,u,w,z,e,f,h,g and D2H of dw,dx,dy,dz inside the timed region, A resident
-  roofline  the formation kernel (dmma_nt_kernel<true>): its flops / its CUDA-event time, against the
-            measured FP64 DMMA peak (tools/dmma_bench.cu -> profiles/; MEASURED_PEAKS.json has no FP64 entry)
+  roofline  the formation (scale pass As = A diag(s) + dmma_nt_kernel<false> on As): m^2 n flops / the CUDA-event
+            time of both launches, against the measured FP64 DMMA peak (tools/dmma_bench.cu -> profiles/;
+            MEASURED_PEAKS.json has no FP64 entry)
   residual  after the timed region: ||(As)(As)' x - b|| / ||b|| for a fresh factorization + solve, the
             products through nes_sdmult -- every line carries the proof that what it timed was correct
   cpu_baseline / --impl reference: oracle/baseline.py on ALL host cores of the affinity mask (restated
@@ -293,16 +294,22 @@ def run_dense(c, m, n, K, W, seed, world, barrier, local, lp_solve):
         ach = form_flops / world / (form_ms / form_cnt * 1e-3) / 1e12  # this rank's share
         traffic, traffic_source = None, None
         if (m, n, world) == (8192, 16384, 1):
-            traffic = 6.81e9
-            traffic_source = ("ncu --set full capture profiles/r01_ncu_full_formation_dmma_nt_m8192.details.txt "
-                              "(dram read+write of one launch), not measured in this run; algorithmic 1.34e9")
+            traffic = 8.90e9
+            traffic_source = ("ncu --set full capture profiles/r02_ncu_full_formation_prescaled_m8192.raw_metrics.csv: "
+                              "dmma_nt_kernel<0> 6.52 GB read + 0.27 GB written (tensor pipe 97.7% active, 30.80 ms) + "
+                              "scale_columns_kernel 1.07 + 1.03 GB (0.41 ms); not measured in this run; algorithmic "
+                              "8mn + 4m^2 = 1.34e9 for the product + 16mn = 2.15e9 for the scaled copy")
         elif (m, n, world) == (32768, 65536, 1):
-            traffic = 6.664e11
-            traffic_source = ("ncu --set full capture profiles/r02_ncu_full_formation_dmma_nt_m32768.raw_metrics.csv "
-                              "(dram__bytes_read.sum 661.98 GB + dram__bytes_write.sum 4.47 GB of one launch, DRAM at "
-                              "4% of peak), not measured in this run; algorithmic 8mn + 4m^2 = 2.15e10: one 128-row "
-                              "block of A is 67 MB, so only tiles running at the same time share it through L2")
-        roof = {"bound": "tensor", "kernel": "dmma_nt_kernel<true> (fused scale+SYRK)",
+            traffic = 7.01e11
+            traffic_source = ("ncu --set full capture of the FUSED variant of the same kernel at this size, "
+                              "profiles/r02_ncu_full_formation_dmma_nt_m32768.raw_metrics.csv (661.98 GB read + 4.47 GB "
+                              "written, DRAM at 4% of peak), plus 16mn = 3.44e10 for the scaled copy the default path "
+                              "writes and reads; not measured in this run; algorithmic 8mn + 4m^2 = 2.15e10: one 128-row "
+                              "block of the operand is 67 MB, so only tiles running at the same time share it through L2")
+        roof = {"bound": "tensor",
+                "kernel": "scale_columns_kernel (As = A diag(s)) + dmma_nt_kernel<false> (SYRK of As on FP64 DMMA); "
+                          "achieved = m^2 n / the CUDA-event time of BOTH (NES_FORM_FUSED=1 selects the fused "
+                          "dmma_nt_kernel<true>, 3.4% slower)",
                 "achieved": ach, "peak": FP64_DMMA_PEAK_TFLOPS, "unit": "TFLOP/s",
                 "frac": ach / FP64_DMMA_PEAK_TFLOPS, "traffic": traffic, "traffic_source": traffic_source,
                 "peak_source": "own DMMA issue-rate microbenchmark (tools/dmma_bench.cu, "
