@@ -243,3 +243,31 @@ def test_a_direction_is_applied_once_and_invalidated_by_set(common):
     with pytest.raises(nes.NesError):
         pdas.apply_step(st, 0.1)
     pdas.free_pdas_A(st)
+
+
+@pytest.mark.parametrize("m,n", [(129, 300), (1000, 1500), (2304, 2500)])
+def test_fused_and_prescaled_formation_agree(common, monkeypatch, m, n):
+    """Two formation paths: the default scales a copy of A once and runs the plain SYRK, the
+    fused kernel (NES_FORM_FUSED=1) multiplies theta into the fragments.  Same matrix to rounding, same gates."""
+    rng = np.random.default_rng(m)
+    A = rng.random((m, n)) + np.eye(m, n)
+    s = 10.0 ** rng.uniform(-3, 3, n)
+    Ad = nes.Matrix.from_dense(common, A)
+    Ad.scale(s)
+    want = ons.normal_matrix(A, s)
+    M1 = Ad.normal_matrix()
+    monkeypatch.setenv("NES_FORM_FUSED", "1")
+    M2 = Ad.normal_matrix()
+    monkeypatch.delenv("NES_FORM_FUSED")
+    for M in (M1, M2):
+        assert np.linalg.norm(M - want) / np.linalg.norm(want) <= 1e-13
+    assert np.linalg.norm(M1 - M2) / np.linalg.norm(want) <= 1e-14
+    L = nes.Factor(common, Ad)
+    assert L.factorize(Ad)
+    r1 = L.residual(Ad)
+    monkeypatch.setenv("NES_FORM_FUSED", "1")
+    assert L.factorize(Ad)
+    r2 = L.residual(Ad)
+    assert r1 <= 1e-12 and r2 <= 1e-12
+    L.free()
+    Ad.free()
