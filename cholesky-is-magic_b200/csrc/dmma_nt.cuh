@@ -311,6 +311,12 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                     for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
             __syncwarp();
+            // Plain arrive.  The hazard mbar_arrive_after (ptx_util.cuh) cures -- a fragment load that is still in
+            // the load/store unit when the stage is refilled -- needs a backlog of global traffic ahead of the
+            // load.  With ONE CTA per SM the only source is this CTA's own previous epilogue, which is fenced off
+            // below; the dependency-carrying arrive costs this kernel 2.7% (all chunks) to 4% (first chunks only:
+            // the duplicated loop body no longer fits the instruction cache), measured, and is used by the
+            // kernels that keep two CTAs on an SM (dmma_nt64, mf_syrk), where the hazard was observed.
             if (lane == 0) mbar_arrive(&empty[s]);
         }
 
@@ -398,6 +404,9 @@ dmma_nt_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                 }
             }
         }
+        // persistent grids: do not start the next tile's fragment loads behind this tile's 128 KB of stores
+        // (see the note at the stage release above)
+        __threadfence_block();
     }
 }
 

@@ -59,6 +59,7 @@ dmma_nt64_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     __syncthreads();
 
     const int kchunks = (p.K + NT_BK - 1) / NT_BK;
+    const uint32_t never = (p.K < 0) ? 0xffffffffu : 0u;  // always 0 (K > 0), unknown to the compiler
     const int nitems = 2 * p.ntiles;
 
     // producer state (thread 0): next chunk to load
@@ -138,6 +139,7 @@ dmma_nt64_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             const double* sB = diag ? sA : sA + NT_PITCH * NT_BK;
             const double* ap = sA + a_off;
             const double* bp = sB + b_off;
+            uint32_t dep = 0;
 #pragma unroll
             for (int ks = 0; ks < NT_BK / 4; ++ks) {
                 double af[8], bf[4];
@@ -145,13 +147,15 @@ dmma_nt64_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                 for (int i = 0; i < 8; ++i) af[i] = ap[ks * 4 * NT_PITCH + i * 8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) bf[j] = bp[ks * 4 * pb + j * 8];
+                dep = frag_dependency(dep, af, bf);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
+            // the stage is released only once every fragment load of it has returned (ptx_util.cuh)
+            if (lane == 0) mbar_arrive_after(&empty[s], dep, never);
         }
 
         // epilogue: lane holds rows g (+8i), cols 2*t4, 2*t4+1 of each 8x8 block; a column pair is loaded

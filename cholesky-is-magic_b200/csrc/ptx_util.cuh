@@ -62,6 +62,44 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 
+// Release of a pipeline stage that the hardware cannot perform before the stage's fragment loads have RETURNED.
+//
+// Why: the consumers read a TMA-filled stage with ordinary loads, run DMMAs on the fragments and then arrive on the
+// stage's "empty" barrier, after which the producer lets TMA overwrite the stage.  dmma884 is a non-volatile asm,
+// so the compiler sinks the last DMMAs below the arrive: in SASS the arrive then follows the last fragment LOAD
+// ISSUE, not its completion (SYNCS.ARRIVE takes no register the loads produce, so no scoreboard holds it back).
+// Normally a load returns long before a TMA refill can land; but with a second CTA on the SM (or the same CTA's
+// epilogue) keeping the load/store unit busy with global read-modify-write traffic a fragment load can be late
+// by more than the refill latency and then reads the NEXT occupant of the stage: one 8-row fragment of one
+// tile wrong, about once per 10^5 tiles (found in round 2 as "lost updates" of the half-tile update kernel; the
+// evidence trail is in DESIGN.md section 5).  Cure: a true data dependency.  `dep` must be derived from
+// every fragment register loaded from the stage; `never` is a run-time value that is always 0 but
+// that neither nvcc nor ptxas can prove to be 0, so `dep & never` costs two integer instructions, keeps the
+// dependency alive and leaves the address unchanged.
+__device__ __forceinline__ void mbar_arrive_after(uint64_t* bar, uint32_t dep, uint32_t never) {
+    asm volatile(
+        "{\n"
+        ".reg .b32 a;\n"
+        "and.b32 a, %1, %2;\n"
+        "add.u32 a, a, %0;\n"
+        "mbarrier.arrive.shared::cta.b64 _, [a];\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(dep), "r"(never)
+        : "memory");
+}
+
+// Dependency value: XOR of the high words of every fragment register loaded from the stage (8 row + 4 column
+// fragments per k-step).  The arrive then waits for the LOADS only -- issued long before, so normally complete --
+// and not for the DMMA pipeline to drain (depending on the accumulators instead cost 3.4% of the formation:
+// every warp stalled for the latency of its last DMMA at each chunk boundary).
+__device__ __forceinline__ uint32_t frag_dependency(uint32_t d, const double (&af)[8], const double (&bf)[4]) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) d ^= static_cast<uint32_t>(__double2hiint(af[i]));
+#pragma unroll
+    for (int j = 0; j < 4; ++j) d ^= static_cast<uint32_t>(__double2hiint(bf[j]));
+    return d;
+}
+
 __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     uint32_t ok;
     asm volatile(

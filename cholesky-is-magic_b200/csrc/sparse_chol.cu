@@ -428,6 +428,7 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
     }
     __syncthreads();
 
+    const uint32_t never = (ntasks < 0) ? 0xffffffffu : 0u;  // always 0, unknown to the compiler (mbar_arrive_after)
     int p_task = blockIdx.x, p_kc = 0, p_kch = 0, p_nb0 = 0;
     int4 pt = make_int4(0, 0, 0, 0);
     uint32_t p_it = 0;
@@ -499,6 +500,7 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
             const double* sB = diag ? sA : sA + NT_PITCH * NT_BK;
             const double* ap = sA + a_off;
             const double* bp = sB + b_off;
+            uint32_t dep = 0;
 #pragma unroll
             for (int ks = 0; ks < NT_BK / 4; ++ks) {
                 double af[8], bf[4];
@@ -506,13 +508,15 @@ mf_syrk_kernel(const MfDesc d, const int4* __restrict__ tasks, int ntasks) {
                 for (int i = 0; i < 8; ++i) af[i] = ap[ks * 4 * NT_PITCH + i * 8];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) bf[j] = bp[ks * 4 * bpitch + j * 8];
+                dep = frag_dependency(dep, af, bf);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)
 #pragma unroll
                     for (int j = 0; j < 4; ++j) dmma884(acc[i][j][0], acc[i][j][1], af[i], bf[j]);
             }
             __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[st_i]);
+            // the stage is released only once every fragment load of it has returned (ptx_util.cuh)
+            if (lane == 0) mbar_arrive_after(&empty[st_i], dep, never);
         }
         const int nu = d.nr[s] - nc, ldu = d.ldu[s];
         const int nslab = (nu + 63) >> 6;
