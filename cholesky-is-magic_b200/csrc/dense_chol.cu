@@ -442,12 +442,11 @@ int chol_panel_launch(nes_ctx* c, const CUtensorMap& mapBlk, const CUtensorMap& 
 }
 
 // Which kernel applies the Cholesky updates: the 128 x 128 one (default) or, with NES_UPDATE_KERNEL=64, the
-// 128 x 64 half-tile kernel with two CTAs per SM (dmma_nt64.cuh).  The half-tile kernel is 4% faster on the
-// factorization at m = 32768 (368 -> 354 ms) and passed every whole-matrix residual check of the single-GPU
-// schedule (14 of 14 at m = 20480..32768, 100 of 100 at m = 8192..12288), but it is OPT-IN: on the
-// distributed schedule it loses an update of part of one tile about once per factorization at m = 32768
-// (DESIGN.md section 5), and one of four runs of the 96-iteration config-2 PDAS solve ended in a non-positive
-// pivot with it, which never happened with the 128 x 128 kernel.  A rare wrong answer is not worth 4%.
+// 128 x 64 half-tile kernel with two CTAs per SM (dmma_nt64.cuh).  With 512-column panels the half-tile kernel is
+// 4% faster on the factorization at m = 32768 (368 -> 354 ms); 1024-column panels give the 128 x 128 kernel the
+// same gain and the two do not add up, so it is not the default here.  (Its early versions lost updates -- a
+// stage released before its fragment loads had returned; found and fixed, see ptx_util.cuh: mbar_arrive_after
+// and DESIGN.md section 5.)
 static bool update_uses_nt64() {
     const char* e = getenv("NES_UPDATE_KERNEL");
     return e && atoi(e) == 64;
@@ -609,16 +608,11 @@ static int dist_update(nes_ctx* c, nes_factor* L, int k0, int K, int tile_begin,
     if (tpc < 1) tpc = 1;
     int max_ctas = c->num_sms;
     if (one_tile_per_cta) max_ctas = std::max(c->num_sms, (a.ntiles + tpc - 1) / tpc);
-    // The distributed schedule keeps the 128 x 128 kernel.  OPEN DEFECT: with the half-tile kernel (or one
-    // persistent 128 x 128 CTA per SM) on the trailing updates of the distributed schedule, m = 32768 with
-    // 512-column panels (panel operand 134 MB > L2) ends with ||LL' - M|| / ||M|| ~ 1e-7 instead of 5e-15:
-    // isolated 16 x 32 .. 16 x 96 blocks of single tiles lose one update.  It reproduces on ONE GPU with
-    // NES_FORCE_DIST=1 (tools/debug_dist_single.py names the tiles), disappears when every stream is
-    // serialised (NES_DIST_SERIAL=1), never appears with 256-column panels or at m <= 16384, and the
-    // single-GPU schedule with the half-tile kernel passed 14 of 14 whole-matrix residual checks at
-    // m = 20480 .. 32768 (tools/stress_residual.py).  Every launch below was validated by the whole-matrix
-    // residual at 2 and 8 GPUs (bench.py prints it on every line).  NES_DIST_KERNEL_DEBUG=1/2/3 selects the
-    // half-tile kernel for the trailing updates / the panel chain / both, for whoever picks this up.
+    // The distributed schedule keeps the 128 x 128 kernel by default: every number in DESIGN.md section 5 was
+    // validated with it at 2, 4 and 8 GPUs.  NES_DIST_KERNEL_DEBUG=1/2/3 selects the half-tile kernel for the
+    // trailing updates / the panel chain / both: since the stage-release fix (ptx_util.cuh: mbar_arrive_after) it
+    // is exact in every replay (tools/debug_dist_single.py on one GPU, 2 real GPUs at m = 32768: 203 -> 197 ms)
+    // and only waits for an 8-GPU validation run to become the default.
     bool use64 = false;
     if (const char* dbg = getenv("NES_DIST_KERNEL_DEBUG")) {
         const int v = atoi(dbg);
