@@ -330,7 +330,7 @@ scale_columns_kernel(const double* __restrict__ A, const double* __restrict__ s,
 static int form_prescale(nes_ctx* c, const nes_matrix* A, nes_factor* L, bool* use) {
     *use = false;
     const MatrixBase* b = A->base;
-    if (!A->d_scale || getenv("NES_FORM_FUSED") || L->defer_split > 0) return 0;
+    if (!A->d_scale || b->n == 0 || getenv("NES_FORM_FUSED") || L->defer_split > 0) return 0;
     if (!L->d_As || L->As_ld != b->ld || L->As_n != b->n) {
         cudaStreamSynchronize(c->stream);
         dev_free(c, L->d_As);
